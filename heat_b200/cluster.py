@@ -1,0 +1,257 @@
+"""``KMeans`` with the reference's estimator API, running one fused CUDA pass + one NCCL allreduce per
+Lloyd iteration.
+
+Mirrors heat/cluster/kmeans.py:14-148 and heat/cluster/_kcluster.py:13-415 of the reference
+(/root/reference): same constructor, ``fit`` / ``predict`` / ``fit_predict``, properties, exceptions and
+behavioural quirks.
+"""
+from __future__ import annotations
+
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from . import engine as _engine
+from .communication import get_comm
+from .dndarray import DNDarray, array
+
+_FLOATS = (torch.float32, torch.float64)
+
+
+class BaseEstimator:
+    """get_params / set_params (reference: heat/core/base.py:37-93)."""
+
+    _PARAMS = ("init", "max_iter", "n_clusters", "random_state", "tol")
+
+    def get_params(self, deep: bool = True) -> dict:
+        return {p: getattr(self, p) for p in self._PARAMS}
+
+    def set_params(self, **params):
+        if not params:
+            return self
+        valid = self.get_params()
+        for key, value in params.items():
+            if key not in valid:
+                raise ValueError(f"Invalid parameter {key} for estimator {self}. "
+                                 "Check the list of available parameters with `estimator.get_params().keys()`.")
+            setattr(self, key, value)
+        return self
+
+    def __repr__(self, indent: int = 1) -> str:
+        return f"{self.__class__.__name__}({self.get_params()})"
+
+
+class KMeans(BaseEstimator):
+    """K-Means clustering (Lloyd's algorithm) — drop-in for ``heat.cluster.KMeans``.
+
+    Parameters are those of the reference (heat/cluster/kmeans.py:55-62).  ``init`` may be a DNDarray of
+    shape (n_clusters, n_features) (the parity entry point, _kcluster.py:136-143) or ``"random"``.
+    The k-means|| / batchparallel initialisers are not part of the accelerated path.
+    """
+
+    def __init__(self, n_clusters: int = 8, init: Union[str, DNDarray] = "random", max_iter: int = 300,
+                 tol: float = 1e-4, random_state: Optional[int] = None):
+        if isinstance(init, str) and init == "kmeans++":
+            init = "probability_based"
+        self.n_clusters = n_clusters
+        self.init = init
+        self.max_iter = max_iter
+        self.tol = tol
+        self.random_state = random_state
+        self._cluster_centers = None
+        self._functional_value = None
+        self._labels = None
+        self._inertia = None
+        self._n_iter = None
+        self._p = 2
+        #: "auto" | "simt" | "tc" — kernel family (tests pin it; users leave it alone)
+        self.kernel_path = "auto"
+        #: iterations enqueued between two reads of the device-side convergence flag
+        self.sync_every = 8
+
+    # -- properties (reference: _kcluster.py:63-98) ------------------------------------------------------
+    @property
+    def cluster_centers_(self) -> DNDarray:
+        return self._cluster_centers
+
+    @property
+    def labels_(self) -> DNDarray:
+        return self._labels
+
+    @property
+    def inertia_(self):
+        return self._inertia
+
+    @property
+    def n_iter_(self) -> int:
+        return self._n_iter
+
+    @property
+    def functional_value_(self) -> DNDarray:
+        return self._functional_value
+
+    # -- initialisation (reference: _kcluster.py:100-281) -------------------------------------------------
+    def _initialize_cluster_centers(self, x: DNDarray, oversampling: float, iter_multiplier: float):
+        if not isinstance(x, DNDarray):
+            raise ValueError(f"Input x needs to be a ht.DNDarray, but was {type(x)}")
+        if oversampling < 2:
+            raise ValueError(f"Oversampling factor should be at least 2, but was {oversampling}")
+        if iter_multiplier < 1:
+            raise ValueError(f"Iteration multiplier should be at least 1, but was {iter_multiplier}")
+        if len(x.shape) != 2:
+            raise NotImplementedError("Only 2D data matrices are currently supported")
+        if x.split not in (None, 0):
+            raise NotImplementedError("Not implemented for other splitting-axes")
+
+        if isinstance(self.init, DNDarray):
+            if len(self.init.shape) != 2:
+                raise ValueError(f"passed centroids need to be two-dimensional, but are {len(self.init.shape)}")
+            if self.init.shape[0] != self.n_clusters or self.init.shape[1] != x.shape[1]:
+                raise ValueError("passed centroids do not match cluster count or data shape")
+            self._cluster_centers = self.init.resplit(None)
+        elif self.init == "random":
+            g = torch.Generator()
+            g.manual_seed(0 if self.random_state is None else int(self.random_state))
+            idx = torch.randint(0, max(x.shape[0] - 1, 1), (self.n_clusters,), generator=g)
+            self._cluster_centers = _gather_rows(x, idx)
+        elif self.init in ("probability_based", "batchparallel"):
+            raise NotImplementedError(
+                f'init="{self.init}" is outside the accelerated path (SURVEY.md §8f N2); pass a DNDarray of '
+                'initial centroids or init="random"')
+        else:
+            raise ValueError(
+                'init needs to be one of "random", ht.DNDarray, "kmeans++", or "batchparallel", '
+                f"but was {self.init}")
+
+    # -- the hot loop -------------------------------------------------------------------------------------
+    def fit(self, x: DNDarray, oversampling: float = 2, iter_multiplier: float = 1):
+        """Reference: heat/cluster/kmeans.py:105-148 — same results, one device pass per iteration."""
+        if not isinstance(x, DNDarray):
+            raise TypeError(f"Input needs to be a ht.DNDarray, but was {type(x)}")
+        self._initialize_cluster_centers(x, oversampling, iter_multiplier)
+        self._n_iter = 0
+
+        xl, cdtype = _device_operands(x)
+        dev = xl.device
+        eng = _engine.get_engine(dev)
+        distributed = x.split is not None and x.comm.is_distributed()
+        if distributed:
+            eng.init_comm(x.comm)
+
+        centers0 = self._cluster_centers.larray.to(dev)
+        c_dtype = centers0.dtype if centers0.dtype in _FLOATS else cdtype
+        k, d = centers0.shape
+        use_tol = self.tol is not None
+        tol_cmp = float(np.float32(self.tol)) if use_tol else 0.0
+        state = torch.zeros(4, dtype=torch.int32, device=dev)
+        max_iter = int(self.max_iter)
+        chunk = max_iter if not use_tol else max(1, int(self.sync_every))
+
+        if c_dtype == cdtype:
+            # fused step: accumulate -> ncclAllReduce -> finalize, centroids updated in place
+            c = centers0.to(cdtype).contiguous().clone()
+            c_prev = torch.empty_like(c)
+            shift2 = torch.zeros((), dtype=cdtype, device=dev)
+            done = 0
+            while done < max_iter:
+                todo = min(chunk, max_iter - done)
+                for _ in range(todo):
+                    eng.lloyd_step(xl, c, c_prev, use_tol, tol_cmp, shift2, state, distributed,
+                                   path=self.kernel_path)
+                done += todo
+                if use_tol and done < max_iter:
+                    if int(state[0].item()):  # one host sync per `sync_every` iterations
+                        break
+            st = state.cpu()
+            self._n_iter = int(st[1])
+            centers, pre = c, c_prev
+        else:
+            # centroids keep the dtype of `init` while distances run in the data's dtype (quirk Q6)
+            c_lo = centers0.contiguous().clone()
+            pre = torch.empty((k, d), dtype=cdtype, device=dev)
+            part = torch.empty(k * (d + 1), dtype=torch.float64, device=dev)
+            shift2 = torch.zeros((), dtype=c_dtype, device=dev)
+            it = 0
+            while it < max_iter:
+                pre.copy_(c_lo)
+                eng.lloyd_accumulate(xl, pre, part, path=self.kernel_path)
+                if distributed:
+                    eng.allreduce_f64(part)
+                eng.lloyd_finalize(part, c_lo, c_lo, use_tol, tol_cmp, shift2, state)
+                it += 1
+                if use_tol and int(state[0].item()):
+                    break
+            self._n_iter = it
+            centers = c_lo
+
+        if self._n_iter == 0:  # max_iter == 0: the reference leaves labels undefined; keep it explicit
+            raise ValueError("max_iter must be at least 1")
+
+        # labels of the last iteration, i.e. against its pre-update centroids (quirk Q5)
+        labels = torch.empty((xl.shape[0], 1), dtype=torch.int64, device=dev)
+        eng.assign(xl, pre.to(cdtype), labels, path=self.kernel_path)
+
+        comm = x.comm
+        self._cluster_centers = DNDarray(centers, (k, d), centers.dtype, None, dev, comm, True)
+        self._inertia = DNDarray(shift2, (), shift2.dtype, None, dev, comm, True)
+        self._labels = DNDarray(labels, (x.shape[0], 1), torch.int64, x.split, dev, comm, x.balanced)
+        return self
+
+    def _assign_to_cluster(self, x: DNDarray, eval_functional_value: bool = False) -> DNDarray:
+        """Reference: heat/cluster/_kcluster.py:352-370."""
+        xl, cdtype = _device_operands(x)
+        dev = xl.device
+        eng = _engine.get_engine(dev)
+        c = self._cluster_centers.larray.to(device=dev, dtype=cdtype).contiguous()
+        labels = torch.empty((xl.shape[0], 1), dtype=torch.int64, device=dev)
+        fv = torch.zeros(1, dtype=torch.float64, device=dev) if eval_functional_value else None
+        eng.assign(xl, c, labels, fv, path=self.kernel_path)
+        if eval_functional_value:
+            if x.split is not None and x.comm.is_distributed():
+                eng.init_comm(x.comm)
+                eng.allreduce_f64(fv)
+            val = fv[0].to(cdtype)
+            self._functional_value = DNDarray(val, (), cdtype, None, dev, x.comm, True)
+        return DNDarray(labels, (x.shape[0], 1), torch.int64, x.split, dev, x.comm, x.balanced)
+
+    def predict(self, x: DNDarray) -> DNDarray:
+        """Reference: heat/cluster/_kcluster.py:398-415."""
+        if not isinstance(x, DNDarray):
+            raise ValueError(f"input needs to be a ht.DNDarray, but was  {type(x)}")
+        return self._assign_to_cluster(x, eval_functional_value=True)
+
+    def fit_predict(self, x: DNDarray) -> DNDarray:
+        """Reference: heat/core/base.py:200-212."""
+        self.fit(x)
+        return self.predict(x)
+
+
+def _device_operands(x: DNDarray):
+    """Local shard as a row-contiguous float tensor + the arithmetic dtype (distance.py:392-403)."""
+    xl = x.larray
+    if xl.dtype not in _FLOATS:
+        xl = xl.to(torch.float64 if xl.dtype == torch.int64 else torch.float32)
+    if xl.dim() != 2:
+        raise NotImplementedError("Only 2D data matrices are currently supported")
+    if xl.shape[0] > 0 and xl.stride(1) != 1:
+        xl = xl.contiguous()
+    return xl, xl.dtype
+
+
+def _gather_rows(x: DNDarray, idx: torch.Tensor) -> DNDarray:
+    """Replicated copy of the global rows ``idx`` of a split=0 (or replicated) array."""
+    k = idx.numel()
+    d = x.shape[1]
+    out = torch.zeros((k, d), dtype=x.larray.dtype, device=x.larray.device)
+    if x.split is None:
+        out.copy_(x.larray[idx.to(x.larray.device)])
+    else:
+        off, _, _ = x.comm.chunk(x.shape, 0)
+        n_loc = x.larray.shape[0]
+        for j, g in enumerate(idx.tolist()):
+            if off <= g < off + n_loc:
+                out[j] = x.larray[g - off]
+        if x.comm.is_distributed():
+            x.comm.Allreduce("IN_PLACE", out)
+    return DNDarray(out, (k, d), out.dtype, None, out.device, x.comm, True)

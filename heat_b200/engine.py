@@ -1,0 +1,166 @@
+"""Device engine: torch tensors in, C-ABI calls out.  One ``CudaEngine`` per (process, device)."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (HK_F32, HK_F64, HK_LABEL_I32, HK_LABEL_I64, HK_LABEL_NONE, HK_LABEL_U8, HK_PATH_AUTO,
+                   HK_PATH_SIMT, HK_PATH_TC, check)
+
+_DT = {torch.float32: HK_F32, torch.float64: HK_F64}
+_LK = {torch.uint8: HK_LABEL_U8, torch.int32: HK_LABEL_I32, torch.int64: HK_LABEL_I64}
+PATHS = {"auto": HK_PATH_AUTO, "simt": HK_PATH_SIMT, "tc": HK_PATH_TC}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(dev: torch.device):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class CudaEngine:
+    """Owns an ``hk_handle_t``; every method enqueues work on torch's current stream and returns."""
+
+    def __init__(self, device: torch.device):
+        if device.type != "cuda":
+            raise RuntimeError(
+                "heat_b200 runs the k-means path on CUDA devices only (sm_100a); "
+                f"got a tensor on {device}. There is no CPU fallback."
+            )
+        self.lib = _lib.load()
+        self.device = device
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.index = idx
+        h = ctypes.c_void_p()
+        check(self.lib.hk_create(ctypes.byref(h), idx), "hk_create")
+        self.h = h
+        self.comm_size = 1
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- communicator ----------------------------------------------------------------------------------
+    def init_comm(self, comm) -> None:
+        """Create the NCCL communicator matching ``comm`` (rank/size); id travels over torch.distributed."""
+        if comm.size == self.comm_size:
+            return
+        ident = None
+        if comm.rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            check(self.lib.hk_comm_unique_id(buf), "hk_comm_unique_id")
+            ident = buf.raw
+        ident = comm.bcast_bytes(ident, root=0)
+        check(self.lib.hk_comm_init(self.h, comm.size, comm.rank, ctypes.c_char_p(ident)), "hk_comm_init")
+        self.comm_size = comm.size
+
+    def allreduce_f64(self, buf: torch.Tensor) -> None:
+        assert buf.dtype == torch.float64 and buf.is_contiguous()
+        check(self.lib.hk_allreduce_f64(self.h, _ptr(buf), buf.numel(), _stream(self.device)),
+              "hk_allreduce_f64")
+
+    # -- hot path ----------------------------------------------------------------------------------------
+    @staticmethod
+    def _check_x(x: torch.Tensor, c: torch.Tensor):
+        if x.dtype not in _DT:
+            raise TypeError(f"unsupported dtype {x.dtype}")
+        if c.dtype != x.dtype:
+            raise TypeError("centroids must have the dtype of the data on the device path")
+        if x.dim() != 2 or c.dim() != 2 or x.shape[1] != c.shape[1]:
+            raise ValueError("shape mismatch between data and centroids")
+        if x.stride(1) != 1 and x.shape[0] > 0:
+            raise ValueError("rows of x must be contiguous")
+        if not c.is_contiguous():
+            raise ValueError("centroids must be contiguous")
+
+    def lloyd_accumulate(self, x, c, partials, labels=None, path="auto"):
+        self._check_x(x, c)
+        n, d = x.shape
+        ldx = x.stride(0) if n > 1 else d
+        lk = HK_LABEL_NONE if labels is None else _LK[labels.dtype]
+        check(self.lib.hk_lloyd_accumulate(self.h, _ptr(x), n, d, ldx, _DT[x.dtype], _ptr(c), c.shape[0],
+                                           _ptr(labels), lk, _ptr(partials), PATHS[path],
+                                           _stream(self.device)), "hk_lloyd_accumulate")
+
+    def lloyd_finalize(self, partials, c_in, c_out, use_tol, tol_cmp, shift2, state):
+        k, d = c_in.shape
+        check(self.lib.hk_lloyd_finalize(self.h, _ptr(partials), _ptr(c_in), _ptr(c_out), k, d,
+                                         _DT[c_in.dtype], int(use_tol), float(tol_cmp), _ptr(shift2),
+                                         _ptr(state), _stream(self.device)), "hk_lloyd_finalize")
+
+    def lloyd_step(self, x, c, c_prev, use_tol, tol_cmp, shift2, state, allreduce, labels=None, path="auto"):
+        self._check_x(x, c)
+        n, d = x.shape
+        ldx = x.stride(0) if n > 1 else d
+        lk = HK_LABEL_NONE if labels is None else _LK[labels.dtype]
+        check(self.lib.hk_lloyd_step(self.h, _ptr(x), n, d, ldx, _DT[x.dtype], _ptr(c), _ptr(c_prev),
+                                     c.shape[0], _ptr(labels), lk, int(use_tol), float(tol_cmp),
+                                     _ptr(shift2), _ptr(state), int(allreduce), PATHS[path],
+                                     _stream(self.device)), "hk_lloyd_step")
+
+    def assign(self, x, c, labels, fv=None, path="auto"):
+        self._check_x(x, c)
+        n, d = x.shape
+        ldx = x.stride(0) if n > 1 else d
+        check(self.lib.hk_assign(self.h, _ptr(x), n, d, ldx, _DT[x.dtype], _ptr(c), c.shape[0], _ptr(labels),
+                                 _LK[labels.dtype] if labels is not None else HK_LABEL_NONE, _ptr(fv),
+                                 PATHS[path], _stream(self.device)), "hk_assign")
+
+    def cdist(self, x, y, out, quadratic_expansion: bool, sqrt: bool = True):
+        m, f = x.shape
+        n = y.shape[0]
+        check(self.lib.hk_cdist(self.h, _ptr(x), m, f, x.stride(0) if m > 1 else f, _ptr(y), n,
+                                y.stride(0) if n > 1 else f, _ptr(out), out.stride(0) if m > 1 else n,
+                                _DT[x.dtype], int(quadratic_expansion), int(sqrt), _stream(self.device)),
+              "hk_cdist")
+
+    # -- introspection -------------------------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self.lib.hk_launch_count(self.h))
+
+    def last_variant(self) -> str:
+        return self.lib.hk_last_variant(self.h).decode()
+
+
+_ENGINES = {}
+
+
+def get_engine(device: torch.device) -> CudaEngine:
+    """Engine cache keyed by device (fails loudly on non-CUDA devices or a missing library)."""
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    key = str(device)
+    eng = _ENGINES.get(key)
+    if eng is None:
+        eng = CudaEngine(device)
+        _ENGINES[key] = eng
+    return eng
+
+
+def set_engine_factory(factory) -> None:
+    """Test hook: replace the engine constructor (used by the gloo host-logic tests, which inject a
+    checker-backed engine defined under tests/).  Not used by the product path."""
+    global get_engine
+    _ENGINES.clear()
+
+    def _get(device):
+        key = str(device)
+        if key not in _ENGINES:
+            _ENGINES[key] = factory(device)
+        return _ENGINES[key]
+
+    import heat_b200.engine as me
+
+    me.get_engine = _get

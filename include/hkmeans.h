@@ -1,0 +1,127 @@
+/*
+ * hkmeans.h — C ABI of libhkmeans.so, the B200-native (sm_100a) replacement for the
+ * k-means Lloyd hot path of helmholtz-analytics/heat.
+ *
+ * Every entry point replaces one reference interface (paths relative to /root/reference):
+ *
+ *   hk_lloyd_step / hk_lloyd_accumulate + hk_lloyd_finalize
+ *        <- KMeans.fit loop body            heat/cluster/kmeans.py:131-144
+ *           = _assign_to_cluster            heat/cluster/_kcluster.py:352-370
+ *           + KMeans._update_centroids      heat/cluster/kmeans.py:76-103
+ *           + shift^2 / tol test            heat/cluster/kmeans.py:141-144
+ *   hk_assign
+ *        <- _KCluster.predict / _assign_to_cluster(eval_functional_value=True)
+ *                                           heat/cluster/_kcluster.py:352-370, 398-415
+ *   hk_cdist
+ *        <- cdist -> _dist -> _euclidian_fast / _euclidian (X split 0|None, Y replicated)
+ *                                           heat/spatial/distance.py:32-64, 136-156, 409-414
+ *   hk_comm_* / hk_allreduce_f64
+ *        <- MPICommunication.Allreduce(MPI.IN_PLACE, t, MPI.SUM) as issued by __reduce_op
+ *                                           heat/core/communication.py:1089-1110,
+ *                                           heat/core/_operations.py:505-510
+ *   hk_chunk
+ *        <- MPICommunication.chunk          heat/core/communication.py:197-254
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all array pointers are DEVICE pointers owned by the caller
+ *     (torch tensors held by DNDarrays).  The library never frees or retains them.
+ *   - every call is asynchronous on the caller-supplied cudaStream_t (passed as void*),
+ *     except hk_create/hk_destroy/hk_comm_init/hk_comm_destroy.
+ *   - every export returns int: 0 ok, <0 bad argument / unsupported, >0 = 1000 + cudaError_t
+ *     or 2000 + ncclResult_t.  Nothing throws or aborts.  hk_last_error() gives the text
+ *     (thread-local).
+ *   - dtype: HK_F32 = 0, HK_F64 = 1 (arithmetic type of X and of the centroids handed in).
+ *   - partial buffers ("partials") are k*(d+1) doubles: row c = [sum_0 .. sum_{d-1}, count].
+ */
+#ifndef HKMEANS_H_
+#define HKMEANS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HK_F32 0
+#define HK_F64 1
+
+#define HK_LABEL_NONE 0
+#define HK_LABEL_U8 1
+#define HK_LABEL_I32 2
+#define HK_LABEL_I64 3
+
+/* distance path selection for hk_lloyd_* / hk_assign (HK_PATH_AUTO picks by shape) */
+#define HK_PATH_AUTO 0
+#define HK_PATH_SIMT 1   /* exact fp32/fp64 FMA distances                                  */
+#define HK_PATH_TC 2     /* tcgen05 TF32 filter + exact FMA refinement (fp32 only)          */
+
+typedef struct hk_handle_s* hk_handle_t;
+
+int hk_version(void);
+const char* hk_last_error(void);
+
+/* workspace + (optional) communicator; one per (process, device) */
+int hk_create(hk_handle_t* out, int device);
+int hk_destroy(hk_handle_t h);
+
+/* replaces MPICommunication.chunk for split=0: rows and offset of `rank` out of `nranks` */
+int hk_chunk(int64_t n_global, int nranks, int rank, int64_t* offset, int64_t* rows);
+
+/* ---- one Lloyd pass over this rank's row shard ------------------------------------------
+ * X        : n_local x d, row stride ldx elements
+ * C        : k x d centroids (same dtype as X), replicated
+ * labels   : optional per-row labels against C (label_kind selects the element type)
+ * partials : k*(d+1) doubles, this rank's per-cluster sums and counts (overwritten)
+ */
+int hk_lloyd_accumulate(hk_handle_t h, const void* X, int64_t n_local, int d, int64_t ldx, int dtype,
+                        const void* C, int k, void* labels, int label_kind, double* partials,
+                        int path, void* stream);
+
+/* partials (already summed over ranks) -> new centroids, shift^2, convergence flag.
+ *   C_out[c] = cast( sums[c] / double(float(max(count[c],1))) )      (quirks Q1-Q3)
+ *   shift2   = sum (C_in - C_out)^2 evaluated in the centroid dtype  (kmeans.py:141)
+ *   state    : int32[4] device scratch owned by the caller:
+ *              [0] converged flag (sticky), [1] iterations executed, [2..3] reserved.
+ *              When state[0] is already 1 the call is a no-op (lets the host enqueue
+ *              iterations ahead without a sync per iteration and still get n_iter_ exact).
+ *   use_tol  : 0 -> never converge (tol=None)
+ *   tol_cmp  : float32(tol) as the reference compares it
+ */
+int hk_lloyd_finalize(hk_handle_t h, const double* partials, const void* C_in, void* C_out, int k,
+                      int d, int dtype, int use_tol, double tol_cmp, void* shift2_out,
+                      int32_t* state, void* stream);
+
+/* fused: accumulate -> (allreduce over the handle's communicator, if any) -> finalize.
+ * C is updated IN PLACE (C_prev receives the pre-update centroids when not NULL). */
+int hk_lloyd_step(hk_handle_t h, const void* X, int64_t n_local, int d, int64_t ldx, int dtype,
+                  void* C, void* C_prev, int k, void* labels, int label_kind, int use_tol,
+                  double tol_cmp, void* shift2_out, int32_t* state, int allreduce, int path,
+                  void* stream);
+
+/* labels (+ optional sum over rows of min_j d^2, one double) — predict */
+int hk_assign(hk_handle_t h, const void* X, int64_t n_local, int d, int64_t ldx, int dtype,
+              const void* C, int k, void* labels, int label_kind, double* min_d2_sum, int path,
+              void* stream);
+
+/* out[i,j] = dist(X[i], Y[j]); quadratic_expansion != 0 -> sqrt(clamp(|x|^2+|y|^2-2xy,0)),
+ * else direct sqrt(sum (x-y)^2).  sqrt_flag = 0 returns squared distances. */
+int hk_cdist(hk_handle_t h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n,
+             int64_t ldy, void* out, int64_t ldo, int dtype, int quadratic_expansion,
+             int sqrt_flag, void* stream);
+
+/* ---- communicator (NCCL, resolved with dlopen at first use) ----------------------------- */
+int hk_comm_unique_id(void* id128);                      /* 128-byte ncclUniqueId            */
+int hk_comm_init(hk_handle_t h, int nranks, int rank, const void* id128);
+int hk_comm_destroy(hk_handle_t h);
+int hk_allreduce_f64(hk_handle_t h, double* buf, int64_t count, void* stream);
+
+/* ---- introspection for tests/bench ------------------------------------------------------- */
+/* kernels launched by this handle since creation */
+int64_t hk_launch_count(hk_handle_t h);
+/* name of the kernel variant the last hk_lloyd_accumulate / hk_assign call selected */
+const char* hk_last_variant(hk_handle_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HKMEANS_H_ */

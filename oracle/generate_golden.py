@@ -1,0 +1,134 @@
+"""TEST INFRASTRUCTURE — records outputs of the UNMODIFIED reference for the k-means path.
+
+Run in the build container only (needs /root/reference; the GPU box does not have it):
+
+    python oracle/generate_golden.py            # writes tests/golden/*.npz + MANIFEST.json
+
+The reference is imported from /root/reference under ``oracle/mpi4py_shim`` (mpi4py is not installed in
+this image).  Inputs come from seeded generators that the tests re-run (``heat_b200.synthetic`` and the
+formulas below); each fixture stores a SHA-256 of its input so a drifting RNG is detected, plus the
+reference's outputs: ``cluster_centers_``, ``labels_``, ``n_iter_``, ``inertia_``, and for predict /
+cdist the returned arrays.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "mpi4py_shim"))
+sys.path.insert(1, "/root/reference")
+sys.path.insert(2, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def sha(t: torch.Tensor) -> str:
+    return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
+
+
+# ---- the seeded inputs (re-created verbatim by tests/cases.py) -------------------------------------
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from cases import CASES, make_case  # noqa: E402
+
+
+def run_case(name: str):
+    import heat as ht
+
+    spec = CASES[name]
+    x, init = make_case(name)
+    comm = ht.MPI_WORLD
+    hx = ht.array(x, split=spec.get("split", 0))
+    hinit = ht.array(init)
+    km = ht.cluster.KMeans(n_clusters=init.shape[0], init=hinit, max_iter=spec["max_iter"], tol=spec["tol"])
+    km.fit(hx)
+    centers = km.cluster_centers_.larray.clone()
+    labels = km.labels_.larray.clone()
+    out = {
+        "centers": centers.numpy(),
+        "n_iter": np.int64(km.n_iter_),
+        "inertia": km.inertia_.larray.numpy(),
+        "x_sha": sha(x),
+        "init_sha": sha(init),
+    }
+    pred = km.predict(hx)
+    plab = pred.larray.clone()
+    out["functional_value"] = km.functional_value_.larray.numpy()
+    # labels travel per rank; gather in rank order through the stand-in's allgather
+    if comm.size > 1:
+        parts = comm.handle.allgather(labels.numpy())
+        labels_all = np.concatenate(parts, axis=0)
+        pparts = comm.handle.allgather(plab.numpy())
+        plab_all = np.concatenate(pparts, axis=0)
+    else:
+        labels_all, plab_all = labels.numpy(), plab.numpy()
+    k = init.shape[0]
+    ldt = np.uint8 if k <= 256 else np.int32
+    out["labels"] = labels_all.astype(ldt).reshape(-1)
+    out["predict_labels"] = plab_all.astype(ldt).reshape(-1)
+    return out
+
+
+def run_cdist():
+    import heat as ht
+
+    out = {}
+    g = torch.Generator().manual_seed(7)
+    for dt, nm in ((torch.float32, "f32"), (torch.float64, "f64")):
+        X = (3 * torch.randn(96, 7, generator=g, dtype=torch.float64)).to(dt)
+        Y = (3 * torch.randn(40, 7, generator=g, dtype=torch.float64) + 1).to(dt)
+        out[f"X_{nm}"] = X.numpy()
+        out[f"Y_{nm}"] = Y.numpy()
+        for q in (False, True):
+            d = ht.spatial.cdist(ht.array(X, split=0), ht.array(Y), quadratic_expansion=q)
+            out[f"D_{nm}_{'quad' if q else 'direct'}"] = d.larray.numpy()
+    # the reference's own known-answer test: ones vs zeros in 4-D -> 2.0 (tests/spatial/test_distances.py:14-40)
+    d = ht.spatial.cdist(ht.ones((4, 4), split=0), ht.zeros((6, 4)), quadratic_expansion=True)
+    out["ones_zeros"] = d.larray.numpy()
+    return out
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "--rank-worker":
+        name = sys.argv[2]
+        res = run_case(name)
+        if int(os.environ.get("RANK", "0")) == 0:
+            np.savez_compressed(os.path.join(GOLD, f"{name}__np{os.environ['WORLD_SIZE']}.npz"), **res)
+        return
+    import heat as ht
+
+    manifest = {"reference_version": ht.__version__, "torch": torch.__version__, "cases": {}}
+    for name, spec in CASES.items():
+        res = run_case(name)
+        np.savez_compressed(os.path.join(GOLD, f"{name}.npz"), **res)
+        manifest["cases"][name] = {"n_iter": int(res["n_iter"]), "inertia": float(res["inertia"]),
+                                   "np": [1]}
+        print(name, "n_iter", int(res["n_iter"]), "inertia", float(res["inertia"]), flush=True)
+        if spec.get("np2"):
+            env = dict(os.environ, WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29631",
+                       OMP_NUM_THREADS="4")
+            procs = [subprocess.Popen([sys.executable, __file__, "--rank-worker", name],
+                                      env=dict(env, RANK=str(r))) for r in range(2)]
+            assert all(p.wait() == 0 for p in procs)
+            r2 = np.load(os.path.join(GOLD, f"{name}__np2.npz"))
+            same = (np.array_equal(r2["centers"], res["centers"]) and np.array_equal(r2["labels"], res["labels"])
+                    and int(r2["n_iter"]) == int(res["n_iter"]))
+            manifest["cases"][name]["np"].append(2)
+            manifest["cases"][name]["np2_bit_identical"] = bool(same)
+            print("   np=2 bit-identical to np=1:", same, flush=True)
+            if same:
+                os.remove(os.path.join(GOLD, f"{name}__np2.npz"))  # Q7: nothing new to store
+    np.savez_compressed(os.path.join(GOLD, "cdist.npz"), **run_cdist())
+    with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()
