@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the k-means Lloyd hot path (BASELINE.json metric: Lloyd iter/s at 100M x 32, k=64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config3|config5|config2|config4]
+
+* a "step" is one Lloyd iteration (fused assign + accumulate pass, allreduce of the k x (d+1) partials,
+  finalize) over the whole 100M-row matrix, sharded split=0 over N ranks (strong scaling).
+* ``value``: iterations/s with X resident in HBM, CUDA events on the launch stream, max over ranks.
+* ``e2e``: the same iteration driven from HOST buffers through the public API / C ABI: per step the shard
+  is copied from pinned host memory to the device, one step runs, centroids + shift come back.
+* ``roofline``: algorithmic bytes (N*d*4 per iteration) / mean duration of the pass kernel (event pairs
+  recorded inside the library around that kernel) against MEASURED_PEAKS.json's HBM copy bandwidth.
+* ``cpu_baseline`` / ``--impl reference``: the oracle port of the reference (torch CPU) on a bounded row
+  sample, extrapolated linearly in N (stated in ``sample``).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[2] — the configuration the metric is quoted on
+    "config3": dict(kind="kmeans", n=100_000_000, d=32, k=64, dtype="f32",
+                    desc="KMeans N=100M d=32 k=64 fp32 split=0 (BASELINE configs[2])"),
+    "config5": dict(kind="kmeans", n=50_000_000, d=16, k=8, dtype="f64",
+                    desc="KMeans N=50M d=16 k=8 fp64 split=0 (BASELINE configs[4])"),
+    "config4": dict(kind="kmeans", n=20_000_000, d=128, k=1024, dtype="f32",
+                    desc="KMeans N=20M d=128 k=1024 fp32 split=0 (BASELINE configs[3])"),
+    "config2": dict(kind="cdist", n=1_000_000, d=64, k=4096, dtype="f32",
+                    desc="cdist X 1Mx64 vs Y 4096x64 fp32 quadratic_expansion (BASELINE configs[1])"),
+}
+DT = {"f32": torch.float32, "f64": torch.float64}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", j
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def timed_cpu_reference(n_sample: int, d: int, k: int, dtype, steps: int, warmup: int, kind: str):
+    """The oracle port (torch CPU, all host threads) on a bounded sample; returns (sec/step, threads)."""
+    from heat_b200.synthetic import blobs_shard, initial_centroids
+    from oracle import kmeans_oracle as orc
+
+    x, _ = blobs_shard(n_sample, d, k if kind == "kmeans" else 16, dtype=dtype)
+    if kind == "cdist":
+        y = torch.randn(k, d, dtype=dtype)
+        fn = lambda: orc.cdist(x, y, quadratic_expansion=True)
+    else:
+        c = initial_centroids(k, d, dtype=dtype)
+
+        def fn():
+            lab = orc.assign_to_cluster(x, c)
+            new = orc.update_centroids([x], [lab], c)
+            return ((c - new) ** 2).sum()
+
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    return (time.perf_counter() - t0) / max(steps, 1), torch.get_num_threads()
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    n, d, k, dtype = wl["n"], wl["d"], wl["k"], DT[wl["dtype"]]
+    # bounded sample: about 1.5 s of CPU work per step on ~8 cores (k full passes in fp64)
+    n_sample = {"config3": 100_000, "config5": 1_000_000, "config4": 8_000, "config2": 20_000}[args.workload]
+    sec, thr = timed_cpu_reference(n_sample, d, k, dtype, args.steps, args.warmup, wl["kind"])
+    scale = n / n_sample
+    value = 1.0 / (sec * scale)
+    sample = (f"oracle port of the reference (torch CPU, {thr} threads) on {n_sample} of {n} rows, "
+              f"{sec * 1e3:.1f} ms/step, extrapolated linearly in N (x{scale:.0f})")
+    line = {
+        "impl": "reference", "metric": metric_name(wl), "value": value, "unit": unit_name(wl),
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * scale * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": wl["dtype"],
+        "data": "synthetic", "config": {"workload": wl["desc"], "n_sample": n_sample},
+        "cpu_baseline": {"value": value, "unit": unit_name(wl), "cores": thr, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit_name(wl), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "host_cores": os.cpu_count(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def metric_name(wl):
+    return "KMeans Lloyd iter/s" if wl["kind"] == "kmeans" else "cdist calls/s"
+
+
+def unit_name(wl):
+    return "iter/s" if wl["kind"] == "kmeans" else "calls/s"
+
+
+def run_ours(args, wl):
+    import torch.distributed as dist
+
+    import heat_b200 as hb
+    from heat_b200.synthetic import blobs_shard, initial_centroids
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local % torch.cuda.device_count())
+    dev = torch.device("cuda", torch.cuda.current_device())
+    comm = hb.init_from_env("nccl") if world > 1 else hb.get_comm()
+    n, d, k, dtype = wl["n"], wl["d"], wl["k"], DT[wl["dtype"]]
+    esz = 4 if dtype == torch.float32 else 8
+    eng = hb.engine.get_engine(dev)
+    if world > 1:
+        eng.init_comm(comm)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    sampler = ClockSampler(torch.cuda.current_device())
+
+    if wl["kind"] == "kmeans":
+        x, off = blobs_shard(n, d, k, rank, world, device=dev, dtype=dtype)
+        c0 = initial_centroids(k, d, dtype=dtype).to(dev)
+        c = c0.clone()
+        c_prev = torch.empty_like(c)
+        shift2 = torch.zeros((), dtype=dtype, device=dev)
+        state = torch.zeros(4, dtype=torch.int32, device=dev)
+        n_loc = x.shape[0]
+
+        def step():
+            eng.lloyd_step(x, c, c_prev, False, 0.0, shift2, state, world > 1, path=args.path)
+
+        alg_bytes_rank = n_loc * d * esz
+    else:
+        off, n_loc = hb.communication.chunk_rows(n, world, rank)
+        g = torch.Generator(device=dev).manual_seed(1 + rank)
+        x = torch.randn(n_loc, d, generator=g, device=dev, dtype=dtype)
+        y = torch.randn(k, d, generator=torch.Generator(device=dev).manual_seed(7), device=dev, dtype=dtype)
+        out = torch.empty((n_loc, k), dtype=dtype, device=dev)
+
+        def step():
+            eng.cdist(x, y, out, quadratic_expansion=True)
+
+        alg_bytes_rank = esz * (n_loc * k + n_loc * d + k * d)
+
+    # ---- device-resident timing -----------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    eng.profile(True)
+    eng.profile_read()
+    l0 = eng.launch_count()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = sum_over_ranks(eng.launch_count() - l0)
+    kern_ms, kern_n = eng.profile_read()
+    eng.profile(False)
+    variant = eng.last_variant()
+    ms_step = ms_total / args.steps
+    value = 1e3 / ms_step
+    kern_ms_avg = max_over_ranks(kern_ms / max(kern_n, 1))
+    if wl["kind"] == "kmeans":
+        iters_done = int(state.cpu()[1])
+        assert iters_done == args.warmup + args.steps, (iters_done, args.warmup + args.steps)
+
+    # ---- end to end from host buffers -------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        try:
+            xh = torch.empty((n_loc, d), dtype=dtype, pin_memory=True)
+            xh.copy_(x)
+            torch.cuda.synchronize()
+            if wl["kind"] == "kmeans":
+                ch = torch.empty((k, d), dtype=dtype, pin_memory=True)
+                sh = torch.empty((), dtype=dtype, pin_memory=True)
+                c.copy_(c0)
+
+                def e2e_step():
+                    x.copy_(xh, non_blocking=True)
+                    eng.lloyd_step(x, c, c_prev, False, 0.0, shift2, state, world > 1, path=args.path)
+                    ch.copy_(c, non_blocking=True)
+                    sh.copy_(shift2, non_blocking=True)
+
+                d2h = k * d * esz + esz
+            else:
+                oh = torch.empty((n_loc, k), dtype=dtype, pin_memory=True)
+
+                def e2e_step():
+                    x.copy_(xh, non_blocking=True)
+                    eng.cdist(x, y, out, quadratic_expansion=True)
+                    oh.copy_(out, non_blocking=True)
+
+                d2h = n_loc * k * esz
+            e2e_steps = args.steps
+            for _ in range(min(args.warmup, 3)):
+                e2e_step()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(e2e_steps):
+                e2e_step()
+            b.record()
+            barrier()
+            e2e_ms = max_over_ranks(a.elapsed_time(b)) / e2e_steps
+            e2e = {"value": 1e3 / e2e_ms, "unit": unit_name(wl), "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": int(sum_over_ranks(n_loc * d * esz)),
+                   "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "steps": e2e_steps,
+                   "api": "heat_b200 engine.lloyd_step -> hk_lloyd_step (C ABI), pinned host X copied every step"}
+            del xh
+        except RuntimeError as ex:  # pinned allocation failure is reported, not hidden
+            e2e = {"value": None, "unit": unit_name(wl), "error": str(ex)[:200], "h2d_bytes_per_step": 0,
+                   "d2h_bytes_per_step": 0}
+
+    if rank != 0:
+        return
+    peak, peak_src, pk = peaks()
+    achieved = alg_bytes_rank / (kern_ms_avg * 1e-3) / 1e9 if kern_ms_avg > 0 else 0.0
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src, "kernel": variant, "kernel_ms_avg": kern_ms_avg,
+            "algorithmic_bytes_per_launch": alg_bytes_rank,
+            "kernel_share_of_step": kern_ms_avg / ms_step if ms_step > 0 else None}
+    line = {
+        "metric": metric_name(wl), "value": value, "unit": unit_name(wl), "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+        "config": {"workload": wl["desc"], "n_global": n, "d": d, "k": k, "rows_per_rank": n_loc,
+                   "l2": "inputs larger than L2 (per-rank shard %.1f GB vs 126 MB)" % (alg_bytes_rank / 1e9),
+                   "parallelism": f"split0 x{world}", "path": args.path},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+    }
+    if world == 1 and not args.no_cpu:
+        n_sample = {"config3": 100_000, "config5": 1_000_000, "config4": 8_000, "config2": 20_000}[args.workload]
+        sec, thr = timed_cpu_reference(n_sample, d, k, dtype, 3, 1, wl["kind"])
+        scale = n / n_sample
+        line["cpu_baseline"] = {
+            "value": 1.0 / (sec * scale), "unit": unit_name(wl), "cores": thr, "kind": "port",
+            "sample": (f"oracle port of the reference (torch CPU, {thr} threads of {os.cpu_count()} host cores) on "
+                       f"{n_sample} of {n} rows, {sec * 1e3:.1f} ms/step, extrapolated linearly in N (x{scale:.0f})")}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config3", choices=list(WORKLOADS))
+    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--n", type=int, default=None, help="override the global row count (experiments only)")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.n:
+        wl["n"] = args.n
+        wl["desc"] += f" [n overridden to {args.n}]"
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+    try:
+        import torch.distributed as dist
+
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

@@ -5,7 +5,7 @@ Public surface mirrors the reference for this one path:
 (heat/spatial/distance.py:136), ``heat_b200.array`` / ``DNDarray`` (split=0 semantics).
 The CUDA library is loaded on first use; importing the package needs neither a GPU nor the library.
 """
-from . import cluster, communication, spatial  # noqa: F401
+from . import cluster, communication, engine, spatial  # noqa: F401
 from .communication import get_comm, init_from_env, use_comm  # noqa: F401
 from .dndarray import DNDarray, array  # noqa: F401
 

@@ -54,6 +54,8 @@ SIGNATURES = {
     "hk_allreduce_f64": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "hk_launch_count": (c_int64, [c_void_p]),
     "hk_last_variant": (c_char_p, [c_void_p]),
+    "hk_profile_enable": (c_int, [c_void_p, c_int]),
+    "hk_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64)]),
 }
 
 _lib = None

@@ -91,9 +91,14 @@ class ProcessGroupCommunication(Communication):
             return local
         counts = [None] * self.size
         self._dist.all_gather_object(counts, int(local.shape[0]), group=self.group)
-        parts = [torch.empty((c,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for c in counts]
-        self._dist.all_gather(parts, local.contiguous(), group=self.group)
-        return torch.cat(parts, dim=0)
+        # all_gather needs equal block sizes: pad every block to the largest one
+        cmax = max(counts)
+        tail = tuple(local.shape[1:])
+        mine = torch.zeros((cmax,) + tail, dtype=local.dtype, device=local.device)
+        mine[: local.shape[0]] = local
+        parts = [torch.empty((cmax,) + tail, dtype=local.dtype, device=local.device) for _ in counts]
+        self._dist.all_gather(parts, mine, group=self.group)
+        return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
 
     def bcast_bytes(self, payload: Optional[bytes], root: int = 0) -> bytes:
         if self.size == 1:

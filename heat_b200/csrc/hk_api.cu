@@ -227,4 +227,30 @@ const char* hk_last_variant(hk_handle_t hh) {
     return hh ? reinterpret_cast<Handle*>(hh)->variant.c_str() : "";
 }
 
+int hk_profile_enable(hk_handle_t hh, int enable) {
+    HK_ARG(hh != nullptr, "hk_profile_enable: null handle");
+    reinterpret_cast<Handle*>(hh)->profile = enable != 0;
+    return 0;
+}
+int hk_profile_read(hk_handle_t hh, double* total_ms, int64_t* launches) {
+    HK_ARG(hh != nullptr, "hk_profile_read: null handle");
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    HK_CUDA(cudaSetDevice(h->device));
+    double tot = 0.0;
+    int64_t n = 0;
+    for (auto& ev : h->prof_events) {
+        HK_CUDA(cudaEventSynchronize(ev.second));
+        float ms = 0.f;
+        HK_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        tot += ms;
+        ++n;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    h->prof_events.clear();
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = n;
+    return 0;
+}
+
 }  // extern "C"

@@ -112,6 +112,7 @@ int run_cdist(Handle* h, const T* X, int64_t m, int f, int64_t ldx, const T* Y, 
         const unsigned gy = (unsigned)((gy_total - y0) < 65535 ? (gy_total - y0) : 65535);
         const int64_t r0 = y0 * BM;
         dim3 grid(gx, gy);
+        prof_begin(h, st);
         if (quad)
             cdist_simt_kernel<T, true><<<grid, 256, 0, st>>>(X + r0 * ldx, m - r0, f, ldx, Y, n, ldy,
                                                              out + r0 * ldo, ldo, xn + r0, yn, sqrt_flag);
@@ -119,6 +120,7 @@ int run_cdist(Handle* h, const T* X, int64_t m, int f, int64_t ldx, const T* Y, 
             cdist_simt_kernel<T, false><<<grid, 256, 0, st>>>(X + r0 * ldx, m - r0, f, ldx, Y, n, ldy,
                                                               out + r0 * ldo, ldo, nullptr, nullptr,
                                                               sqrt_flag);
+        prof_end(h, st);
         HK_CUDA(cudaGetLastError());
         h->launches++;
     }

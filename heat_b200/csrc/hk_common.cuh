@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/hkmeans.h"
 
@@ -48,7 +50,24 @@ struct Handle {
     int rank = 0;
     int64_t launches = 0;
     std::string variant;
+    // optional event timing of the dominant kernel
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
+
+// RAII-less helpers: bracket the dominant kernel with events when profiling is on
+inline void prof_begin(Handle* h, cudaStream_t st) {
+    if (!h->profile) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+    h->prof_events.emplace_back(a, b);
+}
+inline void prof_end(Handle* h, cudaStream_t st) {
+    if (!h->profile || h->prof_events.empty()) return;
+    cudaEventRecord(h->prof_events.back().second, st);
+}
 
 int ensure_part(Handle* h, size_t bytes);
 int ensure_red(Handle* h, size_t bytes);

@@ -480,7 +480,9 @@ int run_variant(Handle* h, SimtParams p, size_t smem, const LloydArgs& a, int le
         }
     }
     p.fv_part = fv_part;
+    prof_begin(h, a.stream);
     kern<<<grid, NT, smem, a.stream>>>(p);
+    prof_end(h, a.stream);
     HK_CUDA(cudaGetLastError());
     h->launches++;
     if (SM == SUMS_SMEM) {

@@ -133,6 +133,15 @@ class CudaEngine:
     def last_variant(self) -> str:
         return self.lib.hk_last_variant(self.h).decode()
 
+    def profile(self, enable: bool) -> None:
+        check(self.lib.hk_profile_enable(self.h, int(enable)), "hk_profile_enable")
+
+    def profile_read(self):
+        """(summed device ms of the dominant kernel, launches measured) since the last read."""
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        check(self.lib.hk_profile_read(self.h, ctypes.byref(ms), ctypes.byref(n)), "hk_profile_read")
+        return ms.value, n.value
+
 
 _ENGINES = {}
 

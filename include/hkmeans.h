@@ -120,6 +120,11 @@ int hk_allreduce_f64(hk_handle_t h, double* buf, int64_t count, void* stream);
 int64_t hk_launch_count(hk_handle_t h);
 /* name of the kernel variant the last hk_lloyd_accumulate / hk_assign call selected */
 const char* hk_last_variant(hk_handle_t h);
+/* CUDA-event timing of the dominant kernel (the Lloyd pass / the cdist kernel) on its own stream:
+ * enable != 0 brackets every such launch with an event pair; hk_profile_read synchronises, returns the
+ * summed device time in ms and the number of launches measured, and clears the list. */
+int hk_profile_enable(hk_handle_t h, int enable);
+int hk_profile_read(hk_handle_t h, double* total_ms, int64_t* launches);
 
 #ifdef __cplusplus
 }
