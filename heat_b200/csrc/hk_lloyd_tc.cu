@@ -1,0 +1,642 @@
+// Tensor-core Lloyd pass (fp32 data) for sm_100a: TMA-streamed row tiles, tcgen05 TF32 distance filter with
+// fp32 accumulators in TMEM, exact-FMA refinement of the rows the filter cannot decide, and the same
+// deterministic in-tile counting sort + segmented column sums as the exact-FMA kernel.
+//
+// Why a filter: at k=64, d=32 the distance contraction costs 2*k = 128 FLOP per 4-byte element, three
+// times what the FP32 pipes can sustain at HBM speed, so x.c^T runs on the 5th-gen tensor cores
+// (tcgen05.mma kind::tf32 reads the fp32 tile in shared memory directly and ignores the low 13 mantissa
+// bits).  The TF32 result has a rigorous error bound  |s_j - (|c_j|^2 - 2 x.c_j)| <= E(x)  with
+//      E = 2*beta*|x|*max_j|c_j| + (d+3)*2^-23*(|x|^2 + max_j|c_j|^2),   beta = 1.05 * 2^-9,
+// so a row whose runner-up is more than 2E above the minimum has a certain label (identical to what the
+// exact fp32 formula of heat/spatial/distance.py:59-64 + first-index argmin would give); every other row
+// (near-ties, NaN/Inf) is re-evaluated with that exact formula over all centroids.  Labels are therefore
+// those of the exact-FMA path, the tensor cores only remove work.
+//
+// Roles per CTA (1 CTA per SM, persistent, static tile -> CTA map):
+//   warp 0   : TMA producer (cp.async.bulk.tensor, 128B swizzle, EVICT_FIRST) into an S-stage ring
+//   warp 1   : tcgen05.mma issuer (one lane), accumulator buffer g = tile % G in TMEM
+//   warp 2   : TMEM allocation / release
+//   G groups of 4 warps: tcgen05.ld epilogue (thread == row == TMEM lane) -> label -> sort -> sums
+// Replaces _assign_to_cluster + KMeans._update_centroids for one shard
+// (heat/cluster/_kcluster.py:352-370, heat/cluster/kmeans.py:76-103).
+#include <math.h>
+
+#include "hk_tma.cuh"
+
+namespace hk {
+namespace {
+
+constexpr int TM = 128;    // rows per tile (UMMA M)
+constexpr int GT = 128;    // threads per consumer group
+constexpr int MISC = 128;  // warps 0-3
+constexpr int GW = 4;      // warps per consumer group
+
+struct TcParams {
+    int64_t n;
+    int d;
+    int k;
+    int nk;  // k rounded up to a multiple of 32 (UMMA N, TMEM columns per accumulator)
+    const float* C;
+    void* labels;
+    int label_kind;
+    double* part;     // [grid*G][k*(d+1)] or nullptr (assign only)
+    double* fv_part;  // [grid*G] or nullptr
+    int S;            // smem stages
+    int nsub;
+    int64_t num_tiles;
+    const int32_t* state;
+    uint32_t tmem_cols;
+};
+
+struct TcLayout {
+    size_t stages, B, cn, grp, grp_stride, sums, cnts, wcnt, wpre, tcnt, seg, perm, bars, misc, total;
+};
+
+__host__ __device__ inline size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ inline TcLayout tc_layout(int d, int k, int nk, int S, int G, int nsub, bool sums) {
+    TcLayout L;
+    size_t o = 0;
+    L.stages = o;
+    o += (size_t)S * TM * d * 4;
+    L.B = o;
+    o += up((size_t)nk * d * 4, 1024);
+    L.cn = o;
+    o += up((size_t)nk * 4, 16);
+    // per-group region (offsets relative to the group base)
+    size_t g = 0;
+    L.sums = g;
+    if (sums) g += up((size_t)nsub * k * d * 8, 16);
+    L.cnts = g;
+    if (sums) g += up((size_t)k * 8, 16);
+    L.wcnt = g;
+    if (sums) g += up((size_t)GW * (k + 1) * 4, 16);
+    L.wpre = g;
+    if (sums) g += up((size_t)GW * (k + 1) * 4, 16);
+    L.tcnt = g;
+    if (sums) g += up((size_t)(k + 1) * 4, 16);
+    L.seg = g;
+    if (sums) g += up((size_t)(k + 2) * 4, 16);
+    L.perm = g;
+    g += up((size_t)GT * 2, 16);
+    L.grp_stride = up(g, 16);
+    L.grp = o;
+    o += L.grp_stride * G;
+    L.bars = o;
+    o += 8 * 64;  // up to 64 mbarriers
+    L.misc = o;
+    o += 256;
+    L.total = o + 1024;  // slack for manual 1024-byte alignment of the base
+    return L;
+}
+
+__device__ __forceinline__ void store_label_tc(void* labels, int kind, int64_t row, int lab) {
+    if (kind == HK_LABEL_I64)
+        reinterpret_cast<long long*>(labels)[row] = lab;
+    else if (kind == HK_LABEL_I32)
+        reinterpret_cast<int*>(labels)[row] = lab;
+    else if (kind == HK_LABEL_U8)
+        reinterpret_cast<unsigned char*>(labels)[row] = (unsigned char)lab;
+}
+
+// exact fp32 squared distance of the reference formula for (row, centroid j), operands read from the
+// swizzled tiles in shared memory, features accumulated in ascending order
+__device__ __forceinline__ float exact_d2(const unsigned char* xt, int row, const unsigned char* Bt, int nk, int j,
+                                          int d, float xn, float cnj) {
+    float dot = 0.f;
+    for (int f = 0; f < d; f += 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(xt + sw128_off(TM, row, f));
+        const float4 cv = *reinterpret_cast<const float4*>(Bt + sw128_off(nk, j, f));
+        dot = fmaf(xv.x, cv.x, dot);
+        dot = fmaf(xv.y, cv.y, dot);
+        dot = fmaf(xv.z, cv.z, dot);
+        dot = fmaf(xv.w, cv.w, dot);
+    }
+    return (xn + cnj) - 2.f * dot;
+}
+
+template <int G, bool SUMS>
+__global__ void __launch_bounds__(MISC + G * GT, 1)
+    lloyd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    if (p.state != nullptr && p.state[0] != 0) return;  // uniform across the grid
+    unsigned char* smem =
+        reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int d = p.d, k = p.k, nk = p.nk, S = p.S;
+    const int nkb = d >> 5;
+    const TcLayout L = tc_layout(d, k, nk, S, G, p.nsub, SUMS);
+    unsigned char* stages = smem + L.stages;
+    unsigned char* Bt = smem + L.B;
+    float* cn = reinterpret_cast<float*>(smem + L.cn);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+    uint64_t* full = bars;             // [S]  TMA -> MMA, consumers
+    uint64_t* empty = bars + 16;       // [S]  consumers -> TMA
+    uint64_t* tfull = bars + 32;       // [G]  MMA -> consumers
+    uint64_t* tempty = bars + 40;      // [G]  consumers -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.misc);
+    float* cmax_s = reinterpret_cast<float*>(smem + L.misc + 16);
+    int* force_exact_s = reinterpret_cast<int*>(smem + L.misc + 32);
+    double* fvred = reinterpret_cast<double*>(smem + L.misc + 64);  // [G*GW] <= 16 doubles
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const uint32_t stage_bytes = (uint32_t)TM * d * 4;
+
+    // ---------------- one-time setup -------------------------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int g = 0; g < G; ++g) {
+            mbar_init(&tfull[g], 1);
+            mbar_init(&tempty[g], GW);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&xmap);
+        *cmax_s = 0.f;
+        *force_exact_s = 0;
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+    // centroid tile B: K-blocked, 128B-swizzled, rows >= k zero
+    for (int e = tid; e < nk * (d >> 2); e += blockDim.x) {
+        const int j = e / (d >> 2), f = (e - j * (d >> 2)) << 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < k) v = *reinterpret_cast<const float4*>(p.C + (size_t)j * d + f);
+        *reinterpret_cast<float4*>(Bt + sw128_off(nk, j, f)) = v;
+    }
+    if (SUMS) {
+        for (int g = 0; g < G; ++g) {
+            unsigned char* gb = smem + L.grp + (size_t)g * L.grp_stride;
+            double* sums = reinterpret_cast<double*>(gb + L.sums);
+            for (int i = tid; i < p.nsub * k * d; i += blockDim.x) sums[i] = 0.0;
+            unsigned long long* cnts = reinterpret_cast<unsigned long long*>(gb + L.cnts);
+            for (int i = tid; i < k; i += blockDim.x) cnts[i] = 0ull;
+            int* wcnt = reinterpret_cast<int*>(gb + L.wcnt);
+            for (int i = tid; i < GW * (k + 1); i += blockDim.x) wcnt[i] = 0;
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < nk; j += blockDim.x) {
+        float s = INFINITY;  // padded centroids can never win
+        if (j < k) {
+            s = 0.f;
+            for (int f = 0; f < d; ++f) {
+                const float c = p.C[(size_t)j * d + f];
+                s = fmaf(c, c, s);
+            }
+            if (!(s < INFINITY)) atomicExch(force_exact_s, 1);  // NaN/Inf centroid: exact path decides
+            atomicMax(reinterpret_cast<int*>(cmax_s), __float_as_int(sqrtf(s)));  // s >= 0: int order == float order
+        }
+        cn[j] = s;
+    }
+    fence_proxy_async();  // B was written with st.shared, tcgen05.mma reads it through the async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const float cmax = *cmax_s;
+    const bool force_exact = *force_exact_s != 0;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            for (int64_t i = 0;; ++i) {
+                const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
+                if (tile >= p.num_tiles) break;
+                const int s = (int)(i % S);
+                const uint32_t u = (uint32_t)(i / S);
+                mbar_wait(&empty[s], (u & 1) ^ 1);
+                mbar_expect_tx(&full[s], stage_bytes);
+                unsigned char* dst = stages + (size_t)s * stage_bytes;
+                for (int kb = 0; kb < nkb; ++kb)
+                    tma_load_2d(dst + (size_t)kb * TM * 128, &xmap, &full[s], kb * 32, (int)(tile * TM),
+                                kEvictFirst);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(TM, nk);
+            const uint32_t b_base = smem_u32(Bt);
+            for (int64_t i = 0;; ++i) {
+                const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
+                if (tile >= p.num_tiles) break;
+                const int s = (int)(i % S);
+                const uint32_t u = (uint32_t)(i / S);
+                const int g = (int)(i % G);
+                const uint32_t v = (uint32_t)(i / G);
+                mbar_wait(&tempty[g], (v & 1) ^ 1);
+                mbar_wait(&full[s], u & 1);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(stages + (size_t)s * stage_bytes);
+                for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t ad = umma_desc_k_sw128(a_base + kb * TM * 128 + ks * 32);
+                        const uint64_t bd = umma_desc_k_sw128(b_base + kb * nk * 128 + ks * 32);
+                        umma_tf32(tmem_base + (uint32_t)(g * nk), ad, bd, idesc, (kb | ks) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(&tfull[g]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= consumer groups =================
+        const int g = (warp - 4) / GW;
+        const int gt = tid - MISC - g * GT;  // 0..127 == row in tile == TMEM lane
+        const int q = gt >> 5;               // warp within the group == warp % 4 (TMEM lane quarter)
+        unsigned char* gb = smem + L.grp + (size_t)g * L.grp_stride;
+        double* sums = reinterpret_cast<double*>(gb + L.sums);
+        unsigned long long* cnts = reinterpret_cast<unsigned long long*>(gb + L.cnts);
+        int* wcnt = reinterpret_cast<int*>(gb + L.wcnt);
+        int* wpre = reinterpret_cast<int*>(gb + L.wpre);
+        int* tcnt = reinterpret_cast<int*>(gb + L.tcnt);
+        int* seg = reinterpret_cast<int*>(gb + L.seg);
+        unsigned short* perm = reinterpret_cast<unsigned short*>(gb + L.perm);
+        const int bar_id = 1 + g;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * nk);
+        double fv_acc = 0.0;
+
+        for (int64_t i = g;; i += G) {
+            const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
+            if (tile >= p.num_tiles) break;
+            const int s = (int)(i % S);
+            const uint32_t u = (uint32_t)(i / S);
+            const uint32_t v = (uint32_t)(i / G);
+            const unsigned char* xt = stages + (size_t)s * stage_bytes;
+            const int64_t row0 = tile * TM;
+            const int rows = (int)((p.n - row0) < (int64_t)TM ? (p.n - row0) : (int64_t)TM);
+            const bool active = gt < rows;
+
+            mbar_wait(&full[s], u & 1);  // x tile visible to this thread
+            // |x|^2 in ascending feature order (same order as the exact path)
+            float xn = 0.f;
+            for (int f = 0; f < d; f += 4) {
+                const float4 xv = *reinterpret_cast<const float4*>(xt + sw128_off(TM, gt, f));
+                xn = fmaf(xv.x, xv.x, xn);
+                xn = fmaf(xv.y, xv.y, xn);
+                xn = fmaf(xv.z, xv.z, xn);
+                xn = fmaf(xv.w, xv.w, xn);
+            }
+            mbar_wait(&tfull[g], v & 1);  // accumulator ready
+            tc_fence_after();
+
+            // pass 1: m = min_j (|c_j|^2 - 2 x.c_j)   (TF32 dots)
+            float m = INFINITY;
+            for (int c0 = 0; c0 < nk; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(taddr + (uint32_t)c0, acc);
+                tmem_wait_ld();
+#pragma unroll
+                for (int jj = 0; jj < 32; jj += 4) {
+                    const float4 c4 = *reinterpret_cast<const float4*>(cn + c0 + jj);
+                    m = fminf(m, fmaf(-2.f, __uint_as_float(acc[jj + 0]), c4.x));
+                    m = fminf(m, fmaf(-2.f, __uint_as_float(acc[jj + 1]), c4.y));
+                    m = fminf(m, fmaf(-2.f, __uint_as_float(acc[jj + 2]), c4.z));
+                    m = fminf(m, fmaf(-2.f, __uint_as_float(acc[jj + 3]), c4.w));
+                }
+            }
+            // rigorous bound on |TF32 estimate - exact fp32 formula| for this row (see file header)
+            const float beta2 = 2.f * 1.05f * 0.001953125f;
+            const float E = (beta2 * sqrtf(xn) * cmax + (float)(d + 3) * 1.1920929e-7f * (xn + cmax * cmax)) * 1.001f;
+            const float thr = m + 2.f * E;
+            // pass 2: candidates within the bound of the minimum
+            int cnt = 0, idx = 0;
+            for (int c0 = 0; c0 < nk; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(taddr + (uint32_t)c0, acc);
+                tmem_wait_ld();
+#pragma unroll
+                for (int jj = 0; jj < 32; jj += 4) {
+                    const float4 c4 = *reinterpret_cast<const float4*>(cn + c0 + jj);
+                    const float s0 = fmaf(-2.f, __uint_as_float(acc[jj + 0]), c4.x);
+                    const float s1 = fmaf(-2.f, __uint_as_float(acc[jj + 1]), c4.y);
+                    const float s2 = fmaf(-2.f, __uint_as_float(acc[jj + 2]), c4.z);
+                    const float s3 = fmaf(-2.f, __uint_as_float(acc[jj + 3]), c4.w);
+                    if (s0 <= thr) { ++cnt; idx = c0 + jj + 0; }
+                    if (s1 <= thr) { ++cnt; idx = c0 + jj + 1; }
+                    if (s2 <= thr) { ++cnt; idx = c0 + jj + 2; }
+                    if (s3 <= thr) { ++cnt; idx = c0 + jj + 3; }
+                }
+            }
+            // accumulator buffer g may be overwritten by the next MMA of this group
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[g]);
+
+            int lab = k;
+            float best = INFINITY;
+            bool have_best = false;
+            if (active) {
+                if (cnt == 1 && !force_exact && xn < INFINITY) {
+                    lab = idx;
+                } else {
+                    // undecided (near-tie within the TF32 bound, NaN/Inf): exact formula, torch.min semantics
+                    int bl = 0;
+                    for (int j = 0; j < k; ++j) {
+                        float d2 = exact_d2(xt, gt, Bt, nk, j, d, xn, cn[j]);
+                        d2 = d2 < 0.f ? 0.f : d2;
+                        if (d2 < best || (d2 != d2 && best == best)) {
+                            best = d2;
+                            bl = j;
+                        }
+                    }
+                    lab = bl;
+                    have_best = true;
+                }
+                if (p.label_kind != HK_LABEL_NONE) store_label_tc(p.labels, p.label_kind, row0 + gt, lab);
+                if (p.fv_part != nullptr) {
+                    if (!have_best) {
+                        best = exact_d2(xt, gt, Bt, nk, lab, d, xn, cn[lab]);
+                        best = best < 0.f ? 0.f : best;
+                    }
+                    const float sq = sqrtf(best);
+                    fv_acc += (double)(sq * sq);
+                }
+            }
+
+            if (SUMS) {
+                // ---- deterministic counting sort of the tile's rows by label (group-local) ----
+                const unsigned peers = __match_any_sync(0xffffffffu, lab);
+                const int rank = __popc(peers & lanemask_lt());
+                const int leader = __ffs(peers) - 1;
+                if (lane == leader) wcnt[q * (k + 1) + lab] = __popc(peers);
+                named_bar_sync(bar_id, GT);
+                for (int c = gt; c <= k; c += GT) {
+                    int run = 0;
+#pragma unroll
+                    for (int w = 0; w < GW; ++w) {
+                        const int vv = wcnt[w * (k + 1) + c];
+                        wcnt[w * (k + 1) + c] = 0;
+                        wpre[w * (k + 1) + c] = run;
+                        run += vv;
+                    }
+                    tcnt[c] = run;
+                    if (c < k) cnts[c] += (unsigned long long)run;
+                }
+                named_bar_sync(bar_id, GT);
+                if (q == 0) {
+                    const int per = (k + 1 + 31) / 32;
+                    const int b0 = lane * per;
+                    int local = 0;
+                    for (int ii = 0; ii < per; ++ii)
+                        if (b0 + ii <= k) local += tcnt[b0 + ii];
+                    int incl = local;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int vv = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += vv;
+                    }
+                    int run = incl - local;
+                    for (int ii = 0; ii < per; ++ii)
+                        if (b0 + ii <= k) {
+                            seg[b0 + ii] = run;
+                            run += tcnt[b0 + ii];
+                        }
+                    if (lane == 31) seg[k + 1] = incl;
+                }
+                named_bar_sync(bar_id, GT);
+                perm[seg[lab] + wpre[q * (k + 1) + lab] + rank] = (unsigned short)gt;
+                named_bar_sync(bar_id, GT);
+                // ---- segmented column sums: thread == (feature, slice) ----
+                const int FW = d < GT ? d : GT;
+                const int SL = GT / FW;
+                const int f0 = gt % FW;
+                const int sl = gt / FW;
+                if (sl < SL) {
+                    const int nslots = p.nsub * k;
+                    for (int vs = sl; vs < nslots; vs += SL) {
+                        const int c = vs / p.nsub;
+                        const int sub = vs - c * p.nsub;
+                        const int b = seg[c], e = seg[c + 1];
+                        if (b + sub >= e) continue;
+                        for (int f = f0; f < d; f += FW) {
+                            // a tile holds <= 128 rows: fp32 partial sums stay short, then widen
+                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                            int ii = b + sub;
+                            for (; ii + 3 * p.nsub < e; ii += 4 * p.nsub) {
+                                a0 += *reinterpret_cast<const float*>(xt + sw128_off(TM, perm[ii], f));
+                                a1 += *reinterpret_cast<const float*>(xt + sw128_off(TM, perm[ii + p.nsub], f));
+                                a2 += *reinterpret_cast<const float*>(xt + sw128_off(TM, perm[ii + 2 * p.nsub], f));
+                                a3 += *reinterpret_cast<const float*>(xt + sw128_off(TM, perm[ii + 3 * p.nsub], f));
+                            }
+                            for (; ii < e; ii += p.nsub)
+                                a0 += *reinterpret_cast<const float*>(xt + sw128_off(TM, perm[ii], f));
+                            sums[((size_t)sub * k + c) * d + f] += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+                        }
+                    }
+                }
+            }
+            // every thread of the group is done with stage s (and with perm/seg of this tile)
+            named_bar_sync(bar_id, GT);
+            if (gt == 0) mbar_arrive(&empty[s]);
+        }
+
+        if (SUMS) {
+            double* out = p.part + ((size_t)blockIdx.x * G + g) * k * (d + 1);
+            for (int ii = gt; ii < k * d; ii += GT) {
+                const int c = ii / d, f = ii - c * d;
+                double t = 0.0;
+                for (int sub = 0; sub < p.nsub; ++sub) t += sums[((size_t)sub * k + c) * d + f];
+                out[(size_t)c * (d + 1) + f] = t;
+            }
+            for (int c = gt; c < k; c += GT) out[(size_t)c * (d + 1) + d] = (double)cnts[c];
+        }
+        if (p.fv_part != nullptr) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) fv_acc += __shfl_xor_sync(0xffffffffu, fv_acc, o);
+            if (lane == 0) fvred[g * GW + q] = fv_acc;
+            named_bar_sync(bar_id, GT);
+            if (gt == 0) {
+                double t = 0.0;
+                for (int w = 0; w < GW; ++w) t += fvred[g * GW + w];
+                p.fv_part[(size_t)blockIdx.x * G + g] = t;
+            }
+        }
+    }
+
+    // ---------------- teardown ---------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+__global__ void reduce_partials_tc_kernel(const double* __restrict__ part, int nb, int len,
+                                          double* __restrict__ out, const int32_t* state) {
+    if (state != nullptr && state[0] != 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    double t = 0.0;
+    for (int b = 0; b < nb; ++b) t += part[(size_t)b * len + i];
+    out[i] = t;
+}
+
+struct TcPlan {
+    int G, S, nk, nsub;
+    uint32_t tmem_cols;
+    size_t smem;
+    bool ok;
+};
+
+TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
+    TcPlan pl{};
+    pl.ok = false;
+    pl.nk = (k + 31) / 32 * 32;
+    const int FW = d < GT ? d : GT;
+    const int SL = GT / FW;
+    pl.nsub = SL / k;
+    if (pl.nsub < 1) pl.nsub = 1;
+    const size_t budget = (size_t)h->smem_optin;
+    for (int G = 4; G >= 1; --G) {
+        if (G * pl.nk > 512) continue;
+        for (int S = 8; S >= 2; --S) {
+            if (S < G && S < 3) continue;
+            TcLayout L = tc_layout(d, k, pl.nk, S, G, pl.nsub, sums);
+            if (L.total <= budget && (S >= G + 1 || S >= 4)) {
+                pl.G = G;
+                pl.S = S;
+                pl.smem = L.total;
+                uint32_t cols = 32;
+                while (cols < (uint32_t)(G * pl.nk)) cols <<= 1;
+                pl.tmem_cols = cols;
+                pl.ok = true;
+                return pl;
+            }
+        }
+    }
+    return pl;
+}
+
+template <int G, bool SUMS>
+int launch_g(Handle* h, const CUtensorMap& map, TcParams& p, size_t smem, int grid, cudaStream_t st) {
+    auto kern = lloyd_tc_kernel<G, SUMS>;
+    HK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin(h, st);
+    kern<<<grid, MISC + G * GT, smem, st>>>(map, p);
+    prof_end(h, st);
+    HK_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+}  // namespace
+
+bool tc_supported(const Handle* h, const LloydArgs& a) {
+    if (a.dtype != HK_F32) return false;
+    if (a.d % 32 != 0 || a.d < 32 || a.d > 256) return false;
+    if (a.k < 1 || a.k > 256) return false;
+    if (a.ldx % 4 != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(a.X) & 15) != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15) != 0) return false;
+    if (a.n >= (int64_t)1 << 31) return false;  // TMA coordinates are int32
+    TcPlan pl = plan_tc(h, a.d, a.k, a.partials != nullptr);
+    return pl.ok;
+}
+
+int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
+    const bool sums = a.partials != nullptr;
+    TcPlan pl = plan_tc(h, a.d, a.k, sums);
+    if (!pl.ok) {
+        set_error("lloyd_tc: no feasible plan for d=%d k=%d", a.d, a.k);
+        return -2;
+    }
+    CUtensorMap map;
+    int rc = make_tensor_map_2d(&map, a.X, 4, (uint64_t)a.n, (uint64_t)a.d, (uint64_t)a.ldx, 32, TM, 128);
+    if (rc) return rc;
+    const int len = a.k * (a.d + 1);
+    TcParams p{};
+    p.n = a.n;
+    p.d = a.d;
+    p.k = a.k;
+    p.nk = pl.nk;
+    p.C = reinterpret_cast<const float*>(a.C);
+    p.labels = a.labels;
+    p.label_kind = a.labels ? a.label_kind : HK_LABEL_NONE;
+    p.S = pl.S;
+    p.nsub = pl.nsub;
+    p.num_tiles = (a.n + TM - 1) / TM;
+    p.state = a.state;
+    p.tmem_cols = pl.tmem_cols;
+    int64_t grid64 = h->num_sms;
+    if (grid64 > p.num_tiles) grid64 = p.num_tiles;
+    const int grid = (int)grid64;
+    const int nb = grid * pl.G;
+    rc = ensure_part(h, ((size_t)nb * len + nb) * sizeof(double));
+    if (rc) return rc;
+    p.part = sums ? h->part : nullptr;
+    p.fv_part = a.fv_out ? h->part + (size_t)nb * len : nullptr;
+
+    char name[96];
+    snprintf(name, sizeof(name), "tc<f32,d=%d,k=%d,G=%d,S=%d,%s>", a.d, a.k, pl.G, pl.S, sums ? "sums" : "assign");
+    h->variant = name;
+
+#define HK_TC(GV)                                                                          \
+    case GV:                                                                               \
+        rc = sums ? launch_g<GV, true>(h, map, p, pl.smem, grid, a.stream)                 \
+                  : launch_g<GV, false>(h, map, p, pl.smem, grid, a.stream);               \
+        break;
+    switch (pl.G) {
+        HK_TC(1)
+        HK_TC(2)
+        HK_TC(3)
+        HK_TC(4)
+        default:
+            rc = -2;
+    }
+#undef HK_TC
+    if (rc) return rc;
+    if (sums) {
+        reduce_partials_tc_kernel<<<(len + 255) / 256, 256, 0, a.stream>>>(h->part, nb, len, a.partials, a.state);
+        HK_CUDA(cudaGetLastError());
+        h->launches++;
+    }
+    if (a.fv_out) {
+        reduce_partials_tc_kernel<<<1, 32, 0, a.stream>>>(p.fv_part, nb, 1, a.fv_out, nullptr);
+        HK_CUDA(cudaGetLastError());
+        h->launches++;
+    }
+    return 0;
+}
+
+// ---- tensor map encoding (driver entry point fetched through the runtime) ---------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tensor_map_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
+                       uint64_t ld, uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        HK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+        if (!sym || qres != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return -5;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {ld * (uint64_t)elem_bytes};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                        : CU_TENSOR_MAP_SWIZZLE_NONE;
+    const CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows);
+        return 3000 + (int)r;
+    }
+    return 0;
+}
+
+}  // namespace hk
