@@ -52,6 +52,7 @@ SIGNATURES = {
     "hk_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "hk_comm_destroy": (c_int, [c_void_p]),
     "hk_allreduce_f64": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "hk_cache_reset": (c_int, [c_void_p]),
     "hk_launch_count": (c_int64, [c_void_p]),
     "hk_last_variant": (c_char_p, [c_void_p]),
     "hk_profile_enable": (c_int, [c_void_p, c_int]),

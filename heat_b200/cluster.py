@@ -138,6 +138,7 @@ class KMeans(BaseEstimator):
         distributed = x.split is not None and x.comm.is_distributed()
         if distributed:
             eng.init_comm(x.comm)
+        eng.cache_reset()  # per-matrix bounds are recomputed in the first pass of every fit
 
         centers0 = self._cluster_centers.larray.to(dev)
         c_dtype = centers0.dtype if centers0.dtype in _FLOATS else cdtype

@@ -98,6 +98,7 @@ int hk_destroy(hk_handle_t hh) {
     if (h->part) cudaFree(h->part);
     if (h->red) cudaFree(h->red);
     if (h->tc_scratch) cudaFree(h->tc_scratch);
+    if (h->xb) cudaFree(h->xb);
     delete h;
     return 0;
 }
@@ -225,6 +226,12 @@ int hk_allreduce_f64(hk_handle_t hh, double* buf, int64_t count, void* stream) {
 int64_t hk_launch_count(hk_handle_t hh) { return hh ? reinterpret_cast<Handle*>(hh)->launches : 0; }
 const char* hk_last_variant(hk_handle_t hh) {
     return hh ? reinterpret_cast<Handle*>(hh)->variant.c_str() : "";
+}
+
+int hk_cache_reset(hk_handle_t hh) {
+    HK_ARG(hh != nullptr, "hk_cache_reset: null handle");
+    reinterpret_cast<Handle*>(hh)->xb_X = nullptr;
+    return 0;
 }
 
 int hk_profile_enable(hk_handle_t hh, int enable) {

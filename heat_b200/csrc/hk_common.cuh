@@ -44,6 +44,13 @@ struct Handle {
     // tensor-core path scratch (TMA descriptors etc.)
     void* tc_scratch = nullptr;
     size_t tc_scratch_bytes = 0;
+    // per-tile |x|^2 bound cache of the tensor-core path, keyed by the matrix it was computed from
+    float* xb = nullptr;
+    size_t xb_bytes = 0;
+    const void* xb_X = nullptr;
+    int64_t xb_n = 0;
+    int xb_d = 0;
+    int64_t xb_ld = 0;
     // communicator
     void* nccl_comm = nullptr;
     int nranks = 1;

@@ -17,6 +17,10 @@
 //   warp 1   : tcgen05.mma issuer (one lane), accumulator buffer g = tile % G in TMEM
 //   warp 2   : TMEM allocation / release
 //   G groups of 4 warps: tcgen05.ld epilogue (thread == row == TMEM lane) -> label -> sort -> sums
+// The accumulator is seeded with |c_j|^2 by one extra k-step (ones x three exact TF32 pieces of |c_j|^2)
+// and B holds -2*c, so TMEM already contains s_j = |c_j|^2 - 2 x.c_j and the epilogue is min + sign-mask.
+// |x|^2 (needed only for the bound E) is computed per row in the first pass over a matrix and cached as a
+// per-tile maximum in the handle (like sklearn's x_squared_norms), later passes read one float per tile.
 // Replaces _assign_to_cluster + KMeans._update_centroids for one shard
 // (heat/cluster/_kcluster.py:352-370, heat/cluster/kmeans.py:76-103).
 #include <math.h>
@@ -46,10 +50,13 @@ struct TcParams {
     int64_t num_tiles;
     const int32_t* state;
     uint32_t tmem_cols;
+    float* bounds;   // [num_tiles] per-tile max |x|^2, followed by one int "filled" flag
+    int want_write;  // 1: this launch fills `bounds`
 };
 
 struct TcLayout {
-    size_t stages, B, cn, grp, grp_stride, sums, cnts, wcnt, wpre, tcnt, seg, perm, bars, misc, total;
+    size_t stages, B, Aext, Bext, cn, grp, grp_stride, sums, cnts, wcnt, wpre, tcnt, seg, perm, gxn, bars, misc,
+        total;
 };
 
 __host__ __device__ inline size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -61,6 +68,10 @@ __host__ __device__ inline TcLayout tc_layout(int d, int k, int nk, int S, int G
     o += (size_t)S * TM * d * 4;
     L.B = o;
     o += up((size_t)nk * d * 4, 1024);
+    L.Aext = o;
+    o += (size_t)TM * 128;
+    L.Bext = o;
+    o += up((size_t)nk * 128, 1024);
     L.cn = o;
     o += up((size_t)nk * 4, 16);
     // per-group region (offsets relative to the group base)
@@ -79,6 +90,8 @@ __host__ __device__ inline TcLayout tc_layout(int d, int k, int nk, int S, int G
     if (sums) g += up((size_t)(k + 2) * 4, 16);
     L.perm = g;
     g += up((size_t)GT * 2, 16);
+    L.gxn = g;
+    g += 2 * GW * 4;
     L.grp_stride = up(g, 16);
     L.grp = o;
     o += L.grp_stride * G;
@@ -99,23 +112,67 @@ __device__ __forceinline__ void store_label_tc(void* labels, int kind, int64_t r
         reinterpret_cast<unsigned char*>(labels)[row] = (unsigned char)lab;
 }
 
-// exact fp32 squared distance of the reference formula for (row, centroid j), operands read from the
-// swizzled tiles in shared memory, features accumulated in ascending order
+// exact fp32 squared distance of the reference formula for (row, centroid j): operands come from the
+// swizzled tiles in shared memory (Bt holds -2*c, so the dot already carries the factor), features are
+// accumulated in ascending order.  fl(-2*dot) == -2*fl(dot): scaling by two is exact.
 __device__ __forceinline__ float exact_d2(const unsigned char* xt, int row, const unsigned char* Bt, int nk, int j,
                                           int d, float xn, float cnj) {
-    float dot = 0.f;
+    float dotm2 = 0.f;
     for (int f = 0; f < d; f += 4) {
         const float4 xv = *reinterpret_cast<const float4*>(xt + sw128_off(TM, row, f));
         const float4 cv = *reinterpret_cast<const float4*>(Bt + sw128_off(nk, j, f));
-        dot = fmaf(xv.x, cv.x, dot);
-        dot = fmaf(xv.y, cv.y, dot);
-        dot = fmaf(xv.z, cv.z, dot);
-        dot = fmaf(xv.w, cv.w, dot);
+        dotm2 = fmaf(xv.x, cv.x, dotm2);
+        dotm2 = fmaf(xv.y, cv.y, dotm2);
+        dotm2 = fmaf(xv.z, cv.z, dotm2);
+        dotm2 = fmaf(xv.w, cv.w, dotm2);
     }
-    return (xn + cnj) - 2.f * dot;
+    return (xn + cnj) + dotm2;
 }
 
-template <int G, bool SUMS>
+__device__ __forceinline__ float row_norm2(const unsigned char* xt, int row, int d) {
+    float xn = 0.f;
+    for (int f = 0; f < d; f += 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(xt + sw128_off(TM, row, f));
+        xn = fmaf(xv.x, xv.x, xn);
+        xn = fmaf(xv.y, xv.y, xn);
+        xn = fmaf(xv.z, xv.z, xn);
+        xn = fmaf(xv.w, xv.w, xn);
+    }
+    return xn;
+}
+
+// wait on an mbarrier with one lane per warp, then release the warp (keeps 31 lanes out of the spin loop)
+__device__ __forceinline__ void warp_mbar_wait(uint64_t* bar, uint32_t parity, int lane) {
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
+
+// sign-bit mask of (s_j < thr) for 32 accumulator columns: bit j <-> column j
+__device__ __forceinline__ unsigned below_mask32(const uint32_t* a, float thr) {
+    unsigned m = 0;
+#pragma unroll
+    for (int j = 31; j >= 0; --j) m = __funnelshift_l(__float_as_uint(__uint_as_float(a[j]) - thr), m, 1);
+    return m;
+}
+__device__ __forceinline__ float min32(const uint32_t* a) {
+    float m0 = __uint_as_float(a[0]), m1 = __uint_as_float(a[1]), m2 = __uint_as_float(a[2]),
+          m3 = __uint_as_float(a[3]);
+#pragma unroll
+    for (int j = 4; j < 32; j += 4) {
+        m0 = fminf(m0, __uint_as_float(a[j]));
+        m1 = fminf(m1, __uint_as_float(a[j + 1]));
+        m2 = fminf(m2, __uint_as_float(a[j + 2]));
+        m3 = fminf(m3, __uint_as_float(a[j + 3]));
+    }
+    return fminf(fminf(m0, m1), fminf(m2, m3));
+}
+
+enum { XN_COMPUTE = 0, XN_WRITE = 1, XN_READ = 2 };
+
+// G consumer groups; SUMS: accumulate per-cluster sums; NCH: 32-column chunks of the accumulator kept in
+// registers (1, 2; 0 = generic two-pass loop for nk > 64); CPS: clusters per slice held in register
+// accumulators in the sums phase (0 = generic shared-memory read-modify-write path)
+template <int G, bool SUMS, int NCH, int CPS>
 __global__ void __launch_bounds__(MISC + G * GT, 1)
     lloyd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -127,12 +184,14 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
     const TcLayout L = tc_layout(d, k, nk, S, G, p.nsub, SUMS);
     unsigned char* stages = smem + L.stages;
     unsigned char* Bt = smem + L.B;
+    unsigned char* Aext = smem + L.Aext;
+    unsigned char* Bext = smem + L.Bext;
     float* cn = reinterpret_cast<float*>(smem + L.cn);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
-    uint64_t* full = bars;             // [S]  TMA -> MMA, consumers
-    uint64_t* empty = bars + 16;       // [S]  consumers -> TMA
-    uint64_t* tfull = bars + 32;       // [G]  MMA -> consumers
-    uint64_t* tempty = bars + 40;      // [G]  consumers -> MMA
+    uint64_t* full = bars;         // [S]  TMA -> MMA, consumers
+    uint64_t* empty = bars + 16;   // [S]  consumers -> TMA
+    uint64_t* tfull = bars + 32;   // [G]  MMA -> consumers
+    uint64_t* tempty = bars + 40;  // [G]  consumers -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.misc);
     float* cmax_s = reinterpret_cast<float*>(smem + L.misc + 16);
     int* force_exact_s = reinterpret_cast<int*>(smem + L.misc + 32);
@@ -142,6 +201,8 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const uint32_t stage_bytes = (uint32_t)TM * d * 4;
+    const int xn_mode = p.want_write ? XN_WRITE
+                                     : (reinterpret_cast<const int*>(p.bounds)[p.num_tiles] != 0 ? XN_READ : XN_COMPUTE);
 
     // ---------------- one-time setup -------------------------------------------------------------------
     if (tid == 0) {
@@ -159,12 +220,25 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
         *force_exact_s = 0;
     }
     if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
-    // centroid tile B: K-blocked, 128B-swizzled, rows >= k zero
+    // operand B = -2*C: K-blocked, 128B-swizzled, rows >= k zero
     for (int e = tid; e < nk * (d >> 2); e += blockDim.x) {
         const int j = e / (d >> 2), f = (e - j * (d >> 2)) << 2;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < k) v = *reinterpret_cast<const float4*>(p.C + (size_t)j * d + f);
+        if (j < k) {
+            v = *reinterpret_cast<const float4*>(p.C + (size_t)j * d + f);
+            v.x *= -2.f;
+            v.y *= -2.f;
+            v.z *= -2.f;
+            v.w *= -2.f;
+        }
         *reinterpret_cast<float4*>(Bt + sw128_off(nk, j, f)) = v;
+    }
+    // seed operands: A_ext[r] = (1,1,1,0,...), B_ext[j] = three exact TF32 pieces of |c_j|^2
+    for (int e = tid; e < TM * 8; e += blockDim.x) {
+        const int r = e >> 3, ch = e & 7;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ch == 0) v = make_float4(1.f, 1.f, 1.f, 0.f);
+        *reinterpret_cast<float4*>(Aext + sw128_off(TM, r, ch << 2)) = v;
     }
     if (SUMS) {
         for (int g = 0; g < G; ++g) {
@@ -179,7 +253,7 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
     }
     __syncthreads();
     for (int j = tid; j < nk; j += blockDim.x) {
-        float s = INFINITY;  // padded centroids can never win
+        float s = 3.0e38f;  // padded centroids can never win
         if (j < k) {
             s = 0.f;
             for (int f = 0; f < d; ++f) {
@@ -190,8 +264,17 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
             atomicMax(reinterpret_cast<int*>(cmax_s), __float_as_int(sqrtf(s)));  // s >= 0: int order == float order
         }
         cn[j] = s;
+        const float p1 = __uint_as_float(__float_as_uint(s) & 0xFFFFE000u);
+        const float r1 = s - p1;
+        const float p2 = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
+        const float p3 = r1 - p2;
+        for (int ch = 0; ch < 8; ++ch) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ch == 0) v = make_float4(p1, p2, p3, 0.f);
+            *reinterpret_cast<float4*>(Bext + sw128_off(nk, j, ch << 2)) = v;
+        }
     }
-    fence_proxy_async();  // B was written with st.shared, tcgen05.mma reads it through the async proxy
+    fence_proxy_async();  // operands were written with st.shared, tcgen05.mma reads them through the async proxy
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -220,6 +303,8 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(TM, nk);
             const uint32_t b_base = smem_u32(Bt);
+            const uint64_t aext_d = umma_desc_k_sw128(smem_u32(Aext));
+            const uint64_t bext_d = umma_desc_k_sw128(smem_u32(Bext));
             for (int64_t i = 0;; ++i) {
                 const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
                 if (tile >= p.num_tiles) break;
@@ -231,12 +316,14 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
                 mbar_wait(&full[s], u & 1);
                 tc_fence_after();
                 const uint32_t a_base = smem_u32(stages + (size_t)s * stage_bytes);
+                const uint32_t dcol = tmem_base + (uint32_t)(g * nk);
+                umma_tf32(dcol, aext_d, bext_d, idesc, 0u);  // D = |c_j|^2
                 for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint64_t ad = umma_desc_k_sw128(a_base + kb * TM * 128 + ks * 32);
                         const uint64_t bd = umma_desc_k_sw128(b_base + kb * nk * 128 + ks * 32);
-                        umma_tf32(tmem_base + (uint32_t)(g * nk), ad, bd, idesc, (kb | ks) != 0 ? 1u : 0u);
+                        umma_tf32(dcol, ad, bd, idesc, 1u);  // D += x . (-2 c_j)
                     }
                 }
                 umma_commit(&tfull[g]);
@@ -255,9 +342,55 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
         int* tcnt = reinterpret_cast<int*>(gb + L.tcnt);
         int* seg = reinterpret_cast<int*>(gb + L.seg);
         unsigned short* perm = reinterpret_cast<unsigned short*>(gb + L.perm);
+        float* gxn = reinterpret_cast<float*>(gb + L.gxn);  // [2][GW]
         const int bar_id = 1 + g;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * nk);
         double fv_acc = 0.0;
+        const float beta2 = 2.f * 1.05f * 0.001953125f;
+        const float gam = (float)(d + 3) * 1.1920929e-7f;
+
+        // sums phase geometry: thread == (feature quad fq, slice sl)
+        const int FQ = d >> 2;
+        const int SL = GT / (FQ < GT ? FQ : GT);
+        const int fq = gt % FQ;  // FQ <= 64 for d <= 256
+        const int sl = gt / FQ;
+        const uint32_t kboff = (uint32_t)((fq >> 3) * TM * 128);
+        const uint32_t cx = (uint32_t)((fq & 7) << 4);
+        constexpr int NACC = CPS > 0 ? CPS : 1;
+        float4 acc[NACC];
+#pragma unroll
+        for (int cc = 0; cc < NACC; ++cc) acc[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int rows_since = 0;
+        int c_base, sub, stride;
+        if (p.nsub > 1) {
+            c_base = sl / p.nsub;
+            sub = sl - c_base * p.nsub;
+            stride = p.nsub;
+        } else {
+            c_base = sl * NACC;
+            sub = 0;
+            stride = 1;
+        }
+
+        auto flush_acc = [&]() {
+#pragma unroll
+            for (int cc = 0; cc < NACC; ++cc) {
+                const int c = c_base + cc;
+                if (c < k) {
+                    double* sp = sums + ((size_t)sub * k + c) * d + (fq << 2);
+                    double2 lo = *reinterpret_cast<double2*>(sp);
+                    double2 hi = *reinterpret_cast<double2*>(sp + 2);
+                    lo.x += (double)acc[cc].x;
+                    lo.y += (double)acc[cc].y;
+                    hi.x += (double)acc[cc].z;
+                    hi.y += (double)acc[cc].w;
+                    *reinterpret_cast<double2*>(sp) = lo;
+                    *reinterpret_cast<double2*>(sp + 2) = hi;
+                }
+                acc[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            rows_since = 0;
+        };
 
         for (int64_t i = g;; i += G) {
             const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
@@ -270,73 +403,86 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
             const int rows = (int)((p.n - row0) < (int64_t)TM ? (p.n - row0) : (int64_t)TM);
             const bool active = gt < rows;
 
-            mbar_wait(&full[s], u & 1);  // x tile visible to this thread
-            // |x|^2 in ascending feature order (same order as the exact path)
-            float xn = 0.f;
-            for (int f = 0; f < d; f += 4) {
-                const float4 xv = *reinterpret_cast<const float4*>(xt + sw128_off(TM, gt, f));
-                xn = fmaf(xv.x, xv.x, xn);
-                xn = fmaf(xv.y, xv.y, xn);
-                xn = fmaf(xv.z, xv.z, xn);
-                xn = fmaf(xv.w, xv.w, xn);
+            warp_mbar_wait(&full[s], u & 1, lane);  // x tile landed (needed by |x|^2, exact path, sums)
+            float xn;  // |x|^2 of this row, or an upper bound for every row of the tile
+            if (xn_mode == XN_READ) {
+                xn = __ldg(p.bounds + tile);
+            } else {
+                xn = row_norm2(xt, gt, d);
+                if (xn_mode == XN_WRITE) {
+                    float wm = xn;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+                    if (!(wm == wm)) wm = INFINITY;  // NaN rows: make the cached bound useless, not wrong
+                    if (lane == 0) gxn[(v & 1) * GW + q] = wm;
+                }
             }
-            mbar_wait(&tfull[g], v & 1);  // accumulator ready
-            tc_fence_after();
+            const float E2 = 2.f * ((beta2 * sqrtf(xn) * cmax + gam * (xn + cmax * cmax)) * 1.001f);
 
-            // pass 1: m = min_j (|c_j|^2 - 2 x.c_j)   (TF32 dots)
-            float m = INFINITY;
-            for (int c0 = 0; c0 < nk; c0 += 32) {
-                uint32_t acc[32];
-                tmem_ld32(taddr + (uint32_t)c0, acc);
+            warp_mbar_wait(&tfull[g], v & 1, lane);  // accumulator ready: s_j = |c_j|^2 - 2 x.c_j (TF32)
+            tc_fence_after();
+            int cnt, idx;
+            if constexpr (NCH == 1) {
+                uint32_t a[32];
+                tmem_ld32(taddr, a);
                 tmem_wait_ld();
-#pragma unroll
-                for (int jj = 0; jj < 32; jj += 4) {
-                    const float4 c4 = *reinterpret_cast<const float4*>(cn + c0 + jj);
-                    m = fminf(m, fmaf(-2.f, __uint_as_float(acc[jj + 0]), c4.x));
-                    m = fminf(m, fmaf(-2.f, __uint_as_float(acc[jj + 1]), c4.y));
-                    m = fminf(m, fmaf(-2.f, __uint_as_float(acc[jj + 2]), c4.z));
-                    m = fminf(m, fmaf(-2.f, __uint_as_float(acc[jj + 3]), c4.w));
-                }
-            }
-            // rigorous bound on |TF32 estimate - exact fp32 formula| for this row (see file header)
-            const float beta2 = 2.f * 1.05f * 0.001953125f;
-            const float E = (beta2 * sqrtf(xn) * cmax + (float)(d + 3) * 1.1920929e-7f * (xn + cmax * cmax)) * 1.001f;
-            const float thr = m + 2.f * E;
-            // pass 2: candidates within the bound of the minimum
-            int cnt = 0, idx = 0;
-            for (int c0 = 0; c0 < nk; c0 += 32) {
-                uint32_t acc[32];
-                tmem_ld32(taddr + (uint32_t)c0, acc);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[g]);  // values are in registers: release the accumulator
+                const float thr = min32(a) + E2;
+                const unsigned lo = below_mask32(a, thr);
+                cnt = __popc(lo);
+                idx = __ffs(lo) - 1;
+            } else if constexpr (NCH == 2) {
+                uint32_t a[32], b[32];
+                tmem_ld32(taddr, a);
+                tmem_ld32(taddr + 32u, b);
                 tmem_wait_ld();
-#pragma unroll
-                for (int jj = 0; jj < 32; jj += 4) {
-                    const float4 c4 = *reinterpret_cast<const float4*>(cn + c0 + jj);
-                    const float s0 = fmaf(-2.f, __uint_as_float(acc[jj + 0]), c4.x);
-                    const float s1 = fmaf(-2.f, __uint_as_float(acc[jj + 1]), c4.y);
-                    const float s2 = fmaf(-2.f, __uint_as_float(acc[jj + 2]), c4.z);
-                    const float s3 = fmaf(-2.f, __uint_as_float(acc[jj + 3]), c4.w);
-                    if (s0 <= thr) { ++cnt; idx = c0 + jj + 0; }
-                    if (s1 <= thr) { ++cnt; idx = c0 + jj + 1; }
-                    if (s2 <= thr) { ++cnt; idx = c0 + jj + 2; }
-                    if (s3 <= thr) { ++cnt; idx = c0 + jj + 3; }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[g]);
+                const float thr = fminf(min32(a), min32(b)) + E2;
+                const unsigned lo = below_mask32(a, thr);
+                const unsigned hi = below_mask32(b, thr);
+                cnt = __popc(lo) + __popc(hi);
+                idx = lo ? (__ffs(lo) - 1) : (31 + __ffs(hi));
+            } else {
+                float m = INFINITY;
+                for (int c0 = 0; c0 < nk; c0 += 32) {
+                    uint32_t a[32];
+                    tmem_ld32(taddr + (uint32_t)c0, a);
+                    tmem_wait_ld();
+                    m = fminf(m, min32(a));
                 }
+                const float thr = m + E2;
+                cnt = 0;
+                idx = 0;
+                for (int c0 = 0; c0 < nk; c0 += 32) {
+                    uint32_t a[32];
+                    tmem_ld32(taddr + (uint32_t)c0, a);
+                    tmem_wait_ld();
+                    const unsigned mk = below_mask32(a, thr);
+                    cnt += __popc(mk);
+                    if (mk) idx = c0 + __ffs(mk) - 1;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[g]);
             }
-            // accumulator buffer g may be overwritten by the next MMA of this group
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[g]);
 
             int lab = k;
-            float best = INFINITY;
-            bool have_best = false;
             if (active) {
+                float best = INFINITY;
+                bool have_best = false;
+                float xr = xn;  // exact |x|^2 of this row (the cached value is only a bound)
                 if (cnt == 1 && !force_exact && xn < INFINITY) {
                     lab = idx;
                 } else {
                     // undecided (near-tie within the TF32 bound, NaN/Inf): exact formula, torch.min semantics
+                    if (xn_mode == XN_READ) xr = row_norm2(xt, gt, d);
                     int bl = 0;
                     for (int j = 0; j < k; ++j) {
-                        float d2 = exact_d2(xt, gt, Bt, nk, j, d, xn, cn[j]);
+                        float d2 = exact_d2(xt, gt, Bt, nk, j, d, xr, cn[j]);
                         d2 = d2 < 0.f ? 0.f : d2;
                         if (d2 < best || (d2 != d2 && best == best)) {
                             best = d2;
@@ -349,7 +495,8 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
                 if (p.label_kind != HK_LABEL_NONE) store_label_tc(p.labels, p.label_kind, row0 + gt, lab);
                 if (p.fv_part != nullptr) {
                     if (!have_best) {
-                        best = exact_d2(xt, gt, Bt, nk, lab, d, xn, cn[lab]);
+                        if (xn_mode == XN_READ) xr = row_norm2(xt, gt, d);
+                        best = exact_d2(xt, gt, Bt, nk, lab, d, xr, cn[lab]);
                         best = best < 0.f ? 0.f : best;
                     }
                     const float sq = sqrtf(best);
@@ -376,6 +523,10 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
                     tcnt[c] = run;
                     if (c < k) cnts[c] += (unsigned long long)run;
                 }
+                if (xn_mode == XN_WRITE && gt == 0) {
+                    const float* gx = gxn + (v & 1) * GW;
+                    p.bounds[tile] = fmaxf(fmaxf(gx[0], gx[1]), fmaxf(gx[2], gx[3]));
+                }
                 named_bar_sync(bar_id, GT);
                 if (q == 0) {
                     const int per = (k + 1 + 31) / 32;
@@ -398,35 +549,61 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
                     if (lane == 31) seg[k + 1] = incl;
                 }
                 named_bar_sync(bar_id, GT);
-                perm[seg[lab] + wpre[q * (k + 1) + lab] + rank] = (unsigned short)gt;
+                // perm holds the swizzled byte offset of the row inside a K-block: (r << 7) | ((r & 7) << 4)
+                perm[seg[lab] + wpre[q * (k + 1) + lab] + rank] = (unsigned short)((gt << 7) | ((gt & 7) << 4));
                 named_bar_sync(bar_id, GT);
-                // ---- segmented column sums: thread == (feature, slice) ----
-                const int FW = d < GT ? d : GT;
-                const int SL = GT / FW;
-                const int f0 = gt % FW;
-                const int sl = gt / FW;
-                if (sl < SL) {
-                    const int nslots = p.nsub * k;
-                    for (int vs = sl; vs < nslots; vs += SL) {
-                        const int c = vs / p.nsub;
-                        const int sub = vs - c * p.nsub;
-                        const int b = seg[c], e = seg[c + 1];
-                        if (b + sub >= e) continue;
-                        for (int f = f0; f < d; f += FW) {
-                            // a tile holds <= 128 rows: fp32 partial sums stay short, then widen
-                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                            int ii = b + sub;
-                            for (; ii + 3 * p.nsub < e; ii += 4 * p.nsub) {
-                                a0 += *reinterpret_cast<const float*>(xt + sw128_off(TM, perm[ii], f));
-                                a1 += *reinterpret_cast<const float*>(xt + sw128_off(TM, perm[ii + p.nsub], f));
-                                a2 += *reinterpret_cast<const float*>(xt + sw128_off(TM, perm[ii + 2 * p.nsub], f));
-                                a3 += *reinterpret_cast<const float*>(xt + sw128_off(TM, perm[ii + 3 * p.nsub], f));
+                // ---- segmented column sums ----
+                const unsigned char* xk = xt + kboff;
+                if constexpr (CPS > 0) {
+                    // register accumulators: slice sl always owns clusters [c_base, c_base + CPS)
+                    if (sl < SL) {
+#pragma unroll
+                        for (int cc = 0; cc < NACC; ++cc) {
+                            const int c = c_base + cc;
+                            if (c < k) {
+                                const int b = seg[c], e = seg[c + 1];
+                                for (int ii = b + sub; ii < e; ii += stride) {
+                                    const float4 xv = *reinterpret_cast<const float4*>(xk + ((uint32_t)perm[ii] ^ cx));
+                                    acc[cc].x += xv.x;
+                                    acc[cc].y += xv.y;
+                                    acc[cc].z += xv.z;
+                                    acc[cc].w += xv.w;
+                                }
+                                rows_since += e - b;
                             }
-                            for (; ii < e; ii += p.nsub)
-                                a0 += *reinterpret_cast<const float*>(xt + sw128_off(TM, perm[ii], f));
-                            sums[((size_t)sub * k + c) * d + f] += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+                        }
+                        if (rows_since >= 32) flush_acc();  // keep fp32 partial sums short, then widen
+                    }
+                } else {
+                    if (sl < SL) {
+                        const int nslots = p.nsub * k;
+                        for (int vs = sl; vs < nslots; vs += SL) {
+                            const int c = vs / p.nsub;
+                            const int sb = vs - c * p.nsub;
+                            const int b = seg[c], e = seg[c + 1];
+                            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int ii = b + sb; ii < e; ii += p.nsub) {
+                                const float4 xv = *reinterpret_cast<const float4*>(xk + ((uint32_t)perm[ii] ^ cx));
+                                a4.x += xv.x;
+                                a4.y += xv.y;
+                                a4.z += xv.z;
+                                a4.w += xv.w;
+                            }
+                            if (b + sb < e) {
+                                double* sp = sums + ((size_t)sb * k + c) * d + (fq << 2);
+                                sp[0] += (double)a4.x;
+                                sp[1] += (double)a4.y;
+                                sp[2] += (double)a4.z;
+                                sp[3] += (double)a4.w;
+                            }
                         }
                     }
+                }
+            } else if (xn_mode == XN_WRITE) {
+                named_bar_sync(bar_id, GT);
+                if (gt == 0) {
+                    const float* gx = gxn + (v & 1) * GW;
+                    p.bounds[tile] = fmaxf(fmaxf(gx[0], gx[1]), fmaxf(gx[2], gx[3]));
                 }
             }
             // every thread of the group is done with stage s (and with perm/seg of this tile)
@@ -435,11 +612,15 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
         }
 
         if (SUMS) {
+            if constexpr (CPS > 0) {
+                if (sl < SL) flush_acc();
+            }
+            named_bar_sync(bar_id, GT);
             double* out = p.part + ((size_t)blockIdx.x * G + g) * k * (d + 1);
             for (int ii = gt; ii < k * d; ii += GT) {
                 const int c = ii / d, f = ii - c * d;
                 double t = 0.0;
-                for (int sub = 0; sub < p.nsub; ++sub) t += sums[((size_t)sub * k + c) * d + f];
+                for (int sb = 0; sb < p.nsub; ++sb) t += sums[((size_t)sb * k + c) * d + f];
                 out[(size_t)c * (d + 1) + f] = t;
             }
             for (int c = gt; c < k; c += GT) out[(size_t)c * (d + 1) + d] = (double)cnts[c];
@@ -464,6 +645,7 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
+    if (xn_mode == XN_WRITE && blockIdx.x == 0 && tid == 0) reinterpret_cast<int*>(p.bounds)[p.num_tiles] = 1;
 }
 
 __global__ void reduce_partials_tc_kernel(const double* __restrict__ part, int nb, int len,
@@ -477,7 +659,7 @@ __global__ void reduce_partials_tc_kernel(const double* __restrict__ part, int n
 }
 
 struct TcPlan {
-    int G, S, nk, nsub;
+    int G, S, nk, nsub, nch, cps;
     uint32_t tmem_cols;
     size_t smem;
     bool ok;
@@ -487,15 +669,20 @@ TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
     TcPlan pl{};
     pl.ok = false;
     pl.nk = (k + 31) / 32 * 32;
-    const int FW = d < GT ? d : GT;
-    const int SL = GT / FW;
+    pl.nch = pl.nk <= 64 ? pl.nk / 32 : 0;
+    const int FQ = d / 4;
+    const int SL = GT / (FQ < GT ? FQ : GT);
     pl.nsub = SL / k;
     if (pl.nsub < 1) pl.nsub = 1;
+    // clusters per slice for the register-accumulator sums phase (1, 2, 4, 8; 0 = generic)
+    int cps = pl.nsub > 1 ? 1 : (k + SL - 1) / SL;
+    pl.cps = cps <= 1 ? 1 : (cps <= 2 ? 2 : (cps <= 4 ? 4 : (cps <= 8 ? 8 : 0)));
+    if (!sums) pl.cps = 1;
     const size_t budget = (size_t)h->smem_optin;
-    for (int G = 4; G >= 1; --G) {
+    const int gmax = pl.nch == 2 ? 3 : 4;  // 64 accumulator registers per thread: keep 128 regs/thread
+    for (int G = gmax; G >= 2; --G) {
         if (G * pl.nk > 512) continue;
-        for (int S = 8; S >= 2; --S) {
-            if (S < G && S < 3) continue;
+        for (int S = 8; S >= 3; --S) {
             TcLayout L = tc_layout(d, k, pl.nk, S, G, pl.nsub, sums);
             if (L.total <= budget && (S >= G + 1 || S >= 4)) {
                 pl.G = G;
@@ -512,9 +699,9 @@ TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
     return pl;
 }
 
-template <int G, bool SUMS>
-int launch_g(Handle* h, const CUtensorMap& map, TcParams& p, size_t smem, int grid, cudaStream_t st) {
-    auto kern = lloyd_tc_kernel<G, SUMS>;
+template <int G, bool SUMS, int NCH, int CPS>
+int launch_inst(Handle* h, const CUtensorMap& map, TcParams& p, size_t smem, int grid, cudaStream_t st) {
+    auto kern = lloyd_tc_kernel<G, SUMS, NCH, CPS>;
     HK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(h, st);
     kern<<<grid, MISC + G * GT, smem, st>>>(map, p);
@@ -522,6 +709,29 @@ int launch_g(Handle* h, const CUtensorMap& map, TcParams& p, size_t smem, int gr
     HK_CUDA(cudaGetLastError());
     h->launches++;
     return 0;
+}
+
+template <int G, int NCH>
+int launch_gn(Handle* h, const CUtensorMap& map, TcParams& p, const TcPlan& pl, bool sums, int grid,
+              cudaStream_t st) {
+    if (!sums) return launch_inst<G, false, NCH, 1>(h, map, p, pl.smem, grid, st);
+    switch (pl.cps) {
+        case 1: return launch_inst<G, true, NCH, 1>(h, map, p, pl.smem, grid, st);
+        case 2: return launch_inst<G, true, NCH, 2>(h, map, p, pl.smem, grid, st);
+        case 4: return launch_inst<G, true, NCH, 4>(h, map, p, pl.smem, grid, st);
+        case 8: return launch_inst<G, true, NCH, 8>(h, map, p, pl.smem, grid, st);
+        default: return launch_inst<G, true, NCH, 0>(h, map, p, pl.smem, grid, st);
+    }
+}
+
+template <int G>
+int launch_g(Handle* h, const CUtensorMap& map, TcParams& p, const TcPlan& pl, bool sums, int grid,
+             cudaStream_t st) {
+    switch (pl.nch) {
+        case 1: return launch_gn<G, 1>(h, map, p, pl, sums, grid, st);
+        case 2: return launch_gn<G, 2>(h, map, p, pl, sums, grid, st);
+        default: return launch_gn<G, 0>(h, map, p, pl, sums, grid, st);
+    }
 }
 
 }  // namespace
@@ -561,6 +771,29 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
     p.num_tiles = (a.n + TM - 1) / TM;
     p.state = a.state;
     p.tmem_cols = pl.tmem_cols;
+
+    // per-tile |x|^2 bound cache, keyed by the matrix identity (reset with hk_cache_reset)
+    const size_t need = ((size_t)p.num_tiles + 4) * sizeof(float);
+    const bool same = h->xb != nullptr && h->xb_X == a.X && h->xb_n == a.n && h->xb_d == a.d && h->xb_ld == a.ldx;
+    if (!same) {
+        if (h->xb_bytes < need) {
+            if (h->xb) HK_CUDA(cudaFree(h->xb));
+            h->xb = nullptr;
+            h->xb_bytes = 0;
+            HK_CUDA(cudaMalloc(&h->xb, need));
+            h->xb_bytes = need;
+        }
+        HK_CUDA(cudaMemsetAsync(h->xb + p.num_tiles, 0, sizeof(int), a.stream));
+        h->xb_X = a.X;
+        h->xb_n = a.n;
+        h->xb_d = a.d;
+        h->xb_ld = a.ldx;
+        p.want_write = 1;
+    } else {
+        p.want_write = 0;
+    }
+    p.bounds = h->xb;
+
     int64_t grid64 = h->num_sms;
     if (grid64 > p.num_tiles) grid64 = p.num_tiles;
     const int grid = (int)grid64;
@@ -570,24 +803,17 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
     p.part = sums ? h->part : nullptr;
     p.fv_part = a.fv_out ? h->part + (size_t)nb * len : nullptr;
 
-    char name[96];
-    snprintf(name, sizeof(name), "tc<f32,d=%d,k=%d,G=%d,S=%d,%s>", a.d, a.k, pl.G, pl.S, sums ? "sums" : "assign");
+    char name[112];
+    snprintf(name, sizeof(name), "tc<f32,d=%d,k=%d,G=%d,S=%d,nch=%d,cps=%d,%s,%s>", a.d, a.k, pl.G, pl.S, pl.nch,
+             pl.cps, sums ? "sums" : "assign", p.want_write ? "xn-write" : "xn-cached");
     h->variant = name;
 
-#define HK_TC(GV)                                                                          \
-    case GV:                                                                               \
-        rc = sums ? launch_g<GV, true>(h, map, p, pl.smem, grid, a.stream)                 \
-                  : launch_g<GV, false>(h, map, p, pl.smem, grid, a.stream);               \
-        break;
     switch (pl.G) {
-        HK_TC(1)
-        HK_TC(2)
-        HK_TC(3)
-        HK_TC(4)
-        default:
-            rc = -2;
+        case 2: rc = launch_g<2>(h, map, p, pl, sums, grid, a.stream); break;
+        case 3: rc = launch_g<3>(h, map, p, pl, sums, grid, a.stream); break;
+        case 4: rc = launch_g<4>(h, map, p, pl, sums, grid, a.stream); break;
+        default: rc = -2;
     }
-#undef HK_TC
     if (rc) return rc;
     if (sums) {
         reduce_partials_tc_kernel<<<(len + 255) / 256, 256, 0, a.stream>>>(h->part, nb, len, a.partials, a.state);

@@ -126,6 +126,10 @@ class CudaEngine:
                                 _DT[x.dtype], int(quadratic_expansion), int(sqrt), _stream(self.device)),
               "hk_cdist")
 
+    def cache_reset(self) -> None:
+        """Forget cached per-matrix bounds (call when a matrix changes in place under the same pointer)."""
+        check(self.lib.hk_cache_reset(self.h), "hk_cache_reset")
+
     # -- introspection -------------------------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self.lib.hk_launch_count(self.h))

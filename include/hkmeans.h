@@ -98,6 +98,11 @@ int hk_lloyd_step(hk_handle_t h, const void* X, int64_t n_local, int d, int64_t 
                   double tol_cmp, void* shift2_out, int32_t* state, int allreduce, int path,
                   void* stream);
 
+/* The tensor-core path caches a per-tile upper bound of |x|^2 (it enters only the error bound that decides
+ * which rows need exact re-evaluation, never a result), keyed by (X, n, d, ldx).  Call this when the
+ * CONTENT of a matrix changes under the same pointer; KMeans.fit calls it once per fit. */
+int hk_cache_reset(hk_handle_t h);
+
 /* labels (+ optional sum over rows of min_j d^2, one double) — predict */
 int hk_assign(hk_handle_t h, const void* X, int64_t n_local, int d, int64_t ldx, int dtype,
               const void* C, int k, void* labels, int label_kind, double* min_d2_sum, int path,

@@ -16,6 +16,9 @@ class CheckerEngine:
     def init_comm(self, comm):
         self.comm = comm
 
+    def cache_reset(self):
+        pass
+
     def allreduce_f64(self, buf):
         if self.comm is not None and self.comm.is_distributed():
             self.comm.Allreduce("IN_PLACE", buf)
