@@ -52,6 +52,9 @@ struct TcParams {
     uint32_t tmem_cols;
     float* bounds;   // [num_tiles] per-tile max |x|^2, followed by one int "filled" flag
     int want_write;  // 1: this launch fills `bounds`
+    // shared-memory layout (byte offsets from the 1024-aligned base), computed on the host
+    uint32_t o_stages, o_B, o_Aext, o_Bext, o_cn, o_grp, grp_stride, o_bars, o_misc;
+    uint32_t g_sums, g_cnts, g_wcnt, g_seg, g_perm, g_gxn;  // relative to a group's base
 };
 
 struct TcLayout {
@@ -147,12 +150,17 @@ __device__ __forceinline__ void warp_mbar_wait(uint64_t* bar, uint32_t parity, i
     __syncwarp();
 }
 
-// sign-bit mask of (s_j < thr) for 32 accumulator columns: bit j <-> column j
+// sign-bit mask of (s_j < thr) for 32 accumulator columns: bit j <-> column j (4 independent shift chains)
 __device__ __forceinline__ unsigned below_mask32(const uint32_t* a, float thr) {
-    unsigned m = 0;
+    unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
 #pragma unroll
-    for (int j = 31; j >= 0; --j) m = __funnelshift_l(__float_as_uint(__uint_as_float(a[j]) - thr), m, 1);
-    return m;
+    for (int j = 7; j >= 0; --j) {
+        m0 = __funnelshift_l(__float_as_uint(__uint_as_float(a[j]) - thr), m0, 1);
+        m1 = __funnelshift_l(__float_as_uint(__uint_as_float(a[8 + j]) - thr), m1, 1);
+        m2 = __funnelshift_l(__float_as_uint(__uint_as_float(a[16 + j]) - thr), m2, 1);
+        m3 = __funnelshift_l(__float_as_uint(__uint_as_float(a[24 + j]) - thr), m3, 1);
+    }
+    return m0 | (m1 << 8) | (m2 << 16) | (m3 << 24);
 }
 __device__ __forceinline__ float min32(const uint32_t* a) {
     float m0 = __uint_as_float(a[0]), m1 = __uint_as_float(a[1]), m2 = __uint_as_float(a[2]),
@@ -169,10 +177,9 @@ __device__ __forceinline__ float min32(const uint32_t* a) {
 
 enum { XN_COMPUTE = 0, XN_WRITE = 1, XN_READ = 2 };
 
-// G consumer groups; SUMS: accumulate per-cluster sums; NCH: 32-column chunks of the accumulator kept in
-// registers (1, 2; 0 = generic two-pass loop for nk > 64); CPS: clusters per slice held in register
-// accumulators in the sums phase (0 = generic shared-memory read-modify-write path)
-template <int G, bool SUMS, int NCH, int CPS>
+// G consumer groups; SUMS: accumulate per-cluster sums; CPS: clusters per slice held in register accumulators
+// in the sums phase (0 = generic shared-memory read-modify-write path)
+template <int G, bool SUMS, int CPS>
 __global__ void __launch_bounds__(MISC + G * GT, 1)
     lloyd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -181,34 +188,34 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
         reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int d = p.d, k = p.k, nk = p.nk, S = p.S;
     const int nkb = d >> 5;
-    const TcLayout L = tc_layout(d, k, nk, S, G, p.nsub, SUMS);
-    unsigned char* stages = smem + L.stages;
-    unsigned char* Bt = smem + L.B;
-    unsigned char* Aext = smem + L.Aext;
-    unsigned char* Bext = smem + L.Bext;
-    float* cn = reinterpret_cast<float*>(smem + L.cn);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+    unsigned char* stages = smem + p.o_stages;
+    unsigned char* Bt = smem + p.o_B;
+    unsigned char* Aext = smem + p.o_Aext;
+    unsigned char* Bext = smem + p.o_Bext;
+    float* cn = reinterpret_cast<float*>(smem + p.o_cn);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.o_bars);
     uint64_t* full = bars;         // [S]  TMA -> MMA, consumers
-    uint64_t* empty = bars + 16;   // [S]  consumers -> TMA
+    uint64_t* empty = bars + 16;   // [S]  consumers (one arrival per warp) -> TMA
     uint64_t* tfull = bars + 32;   // [G]  MMA -> consumers
-    uint64_t* tempty = bars + 40;  // [G]  consumers -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.misc);
-    float* cmax_s = reinterpret_cast<float*>(smem + L.misc + 16);
-    int* force_exact_s = reinterpret_cast<int*>(smem + L.misc + 32);
-    double* fvred = reinterpret_cast<double*>(smem + L.misc + 64);  // [G*GW] <= 16 doubles
+    uint64_t* tempty = bars + 40;  // [G]  consumers (one arrival per warp) -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.o_misc);
+    float* cmax_s = reinterpret_cast<float*>(smem + p.o_misc + 16);
+    int* force_exact_s = reinterpret_cast<int*>(smem + p.o_misc + 32);
+    double* fvred = reinterpret_cast<double*>(smem + p.o_misc + 64);  // [G*GW] <= 16 doubles
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const uint32_t stage_bytes = (uint32_t)TM * d * 4;
-    const int xn_mode = p.want_write ? XN_WRITE
-                                     : (reinterpret_cast<const int*>(p.bounds)[p.num_tiles] != 0 ? XN_READ : XN_COMPUTE);
+    const int ntiles = (int)p.num_tiles;
+    const int xn_mode =
+        p.want_write ? XN_WRITE : (reinterpret_cast<const int*>(p.bounds)[p.num_tiles] != 0 ? XN_READ : XN_COMPUTE);
 
     // ---------------- one-time setup -------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], GW);
         }
         for (int g = 0; g < G; ++g) {
             mbar_init(&tfull[g], 1);
@@ -242,12 +249,12 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
     }
     if (SUMS) {
         for (int g = 0; g < G; ++g) {
-            unsigned char* gb = smem + L.grp + (size_t)g * L.grp_stride;
-            double* sums = reinterpret_cast<double*>(gb + L.sums);
+            unsigned char* gb = smem + p.o_grp + g * p.grp_stride;
+            double* sums = reinterpret_cast<double*>(gb + p.g_sums);
             for (int i = tid; i < p.nsub * k * d; i += blockDim.x) sums[i] = 0.0;
-            unsigned long long* cnts = reinterpret_cast<unsigned long long*>(gb + L.cnts);
+            unsigned long long* cnts = reinterpret_cast<unsigned long long*>(gb + p.g_cnts);
             for (int i = tid; i < k; i += blockDim.x) cnts[i] = 0ull;
-            int* wcnt = reinterpret_cast<int*>(gb + L.wcnt);
+            int* wcnt = reinterpret_cast<int*>(gb + p.g_wcnt);
             for (int i = tid; i < GW * (k + 1); i += blockDim.x) wcnt[i] = 0;
         }
     }
@@ -285,17 +292,18 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            for (int64_t i = 0;; ++i) {
-                const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
-                if (tile >= p.num_tiles) break;
-                const int s = (int)(i % S);
-                const uint32_t u = (uint32_t)(i / S);
-                mbar_wait(&empty[s], (u & 1) ^ 1);
+            int s = 0;
+            uint32_t ph = 0;  // phase parity of stage ring pass
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], stage_bytes);
                 unsigned char* dst = stages + (size_t)s * stage_bytes;
                 for (int kb = 0; kb < nkb; ++kb)
-                    tma_load_2d(dst + (size_t)kb * TM * 128, &xmap, &full[s], kb * 32, (int)(tile * TM),
-                                kEvictFirst);
+                    tma_load_2d(dst + (size_t)kb * TM * 128, &xmap, &full[s], kb * 32, tile * TM, kEvictFirst);
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
         }
     } else if (warp == 1) {
@@ -305,15 +313,11 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
             const uint32_t b_base = smem_u32(Bt);
             const uint64_t aext_d = umma_desc_k_sw128(smem_u32(Aext));
             const uint64_t bext_d = umma_desc_k_sw128(smem_u32(Bext));
-            for (int64_t i = 0;; ++i) {
-                const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
-                if (tile >= p.num_tiles) break;
-                const int s = (int)(i % S);
-                const uint32_t u = (uint32_t)(i / S);
-                const int g = (int)(i % G);
-                const uint32_t v = (uint32_t)(i / G);
-                mbar_wait(&tempty[g], (v & 1) ^ 1);
-                mbar_wait(&full[s], u & 1);
+            int s = 0, g = 0;
+            uint32_t ph = 0, gph = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                mbar_wait(&tempty[g], gph ^ 1);
+                mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t a_base = smem_u32(stages + (size_t)s * stage_bytes);
                 const uint32_t dcol = tmem_base + (uint32_t)(g * nk);
@@ -327,6 +331,14 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
                     }
                 }
                 umma_commit(&tfull[g]);
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1;
+                }
+                if (++g == G) {
+                    g = 0;
+                    gph ^= 1;
+                }
             }
         }
     } else if (warp >= 4) {
@@ -334,20 +346,20 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
         const int g = (warp - 4) / GW;
         const int gt = tid - MISC - g * GT;  // 0..127 == row in tile == TMEM lane
         const int q = gt >> 5;               // warp within the group == warp % 4 (TMEM lane quarter)
-        unsigned char* gb = smem + L.grp + (size_t)g * L.grp_stride;
-        double* sums = reinterpret_cast<double*>(gb + L.sums);
-        unsigned long long* cnts = reinterpret_cast<unsigned long long*>(gb + L.cnts);
-        int* wcnt = reinterpret_cast<int*>(gb + L.wcnt);
-        int* wpre = reinterpret_cast<int*>(gb + L.wpre);
-        int* tcnt = reinterpret_cast<int*>(gb + L.tcnt);
-        int* seg = reinterpret_cast<int*>(gb + L.seg);
-        unsigned short* perm = reinterpret_cast<unsigned short*>(gb + L.perm);
-        float* gxn = reinterpret_cast<float*>(gb + L.gxn);  // [2][GW]
+        unsigned char* gb = smem + p.o_grp + g * p.grp_stride;
+        double* sums = reinterpret_cast<double*>(gb + p.g_sums);
+        unsigned long long* cnts = reinterpret_cast<unsigned long long*>(gb + p.g_cnts);
+        int4* wcnt4 = reinterpret_cast<int4*>(gb + p.g_wcnt);  // [k+1] x {warp 0..3}
+        int* wcnt = reinterpret_cast<int*>(gb + p.g_wcnt);
+        int* seg = reinterpret_cast<int*>(gb + p.g_seg);
+        unsigned short* perm = reinterpret_cast<unsigned short*>(gb + p.g_perm);
+        float* gxn = reinterpret_cast<float*>(gb + p.g_gxn);  // [2][GW]
         const int bar_id = 1 + g;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * nk);
         double fv_acc = 0.0;
         const float beta2 = 2.f * 1.05f * 0.001953125f;
         const float gam = (float)(d + 3) * 1.1920929e-7f;
+        const int kp1 = k + 1;
 
         // sums phase geometry: thread == (feature quad fq, slice sl)
         const int FQ = d >> 2;
@@ -392,18 +404,17 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
             rows_since = 0;
         };
 
-        for (int64_t i = g;; i += G) {
-            const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
-            if (tile >= p.num_tiles) break;
-            const int s = (int)(i % S);
-            const uint32_t u = (uint32_t)(i / S);
-            const uint32_t v = (uint32_t)(i / G);
-            const unsigned char* xt = stages + (size_t)s * stage_bytes;
-            const int64_t row0 = tile * TM;
-            const int rows = (int)((p.n - row0) < (int64_t)TM ? (p.n - row0) : (int64_t)TM);
+        // ring bookkeeping without divisions: stage s / its phase, accumulator phase, tile parity
+        int s = g % S;
+        uint32_t ph = (uint32_t)((g / S) & 1);
+        uint32_t gph = 0;
+        for (int tile = blockIdx.x + g * gridDim.x; tile < ntiles; tile += G * gridDim.x) {
+            const unsigned char* xt = stages + (uint32_t)s * stage_bytes;
+            const int row0 = tile * TM;
+            const int rows = (p.n - row0) < (int64_t)TM ? (int)(p.n - row0) : TM;
             const bool active = gt < rows;
 
-            warp_mbar_wait(&full[s], u & 1, lane);  // x tile landed (needed by |x|^2, exact path, sums)
+            warp_mbar_wait(&full[s], ph, lane);  // x tile landed (needed by |x|^2, exact path, sums)
             float xn;  // |x|^2 of this row, or an upper bound for every row of the tile
             if (xn_mode == XN_READ) {
                 xn = __ldg(p.bounds + tile);
@@ -414,61 +425,34 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
                     if (!(wm == wm)) wm = INFINITY;  // NaN rows: make the cached bound useless, not wrong
-                    if (lane == 0) gxn[(v & 1) * GW + q] = wm;
+                    if (lane == 0) gxn[gph * GW + q] = wm;
                 }
             }
             const float E2 = 2.f * ((beta2 * sqrtf(xn) * cmax + gam * (xn + cmax * cmax)) * 1.001f);
 
-            warp_mbar_wait(&tfull[g], v & 1, lane);  // accumulator ready: s_j = |c_j|^2 - 2 x.c_j (TF32)
+            warp_mbar_wait(&tfull[g], gph, lane);  // accumulator ready: s_j = |c_j|^2 - 2 x.c_j (TF32)
             tc_fence_after();
-            int cnt, idx;
-            if constexpr (NCH == 1) {
+            // two sweeps over the accumulator, 32 columns in registers at a time: min, then sign mask
+            float m = INFINITY;
+            for (int c0 = 0; c0 < nk; c0 += 32) {
                 uint32_t a[32];
-                tmem_ld32(taddr, a);
+                tmem_ld32(taddr + (uint32_t)c0, a);
                 tmem_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[g]);  // values are in registers: release the accumulator
-                const float thr = min32(a) + E2;
-                const unsigned lo = below_mask32(a, thr);
-                cnt = __popc(lo);
-                idx = __ffs(lo) - 1;
-            } else if constexpr (NCH == 2) {
-                uint32_t a[32], b[32];
-                tmem_ld32(taddr, a);
-                tmem_ld32(taddr + 32u, b);
-                tmem_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[g]);
-                const float thr = fminf(min32(a), min32(b)) + E2;
-                const unsigned lo = below_mask32(a, thr);
-                const unsigned hi = below_mask32(b, thr);
-                cnt = __popc(lo) + __popc(hi);
-                idx = lo ? (__ffs(lo) - 1) : (31 + __ffs(hi));
-            } else {
-                float m = INFINITY;
-                for (int c0 = 0; c0 < nk; c0 += 32) {
-                    uint32_t a[32];
-                    tmem_ld32(taddr + (uint32_t)c0, a);
-                    tmem_wait_ld();
-                    m = fminf(m, min32(a));
-                }
-                const float thr = m + E2;
-                cnt = 0;
-                idx = 0;
-                for (int c0 = 0; c0 < nk; c0 += 32) {
-                    uint32_t a[32];
-                    tmem_ld32(taddr + (uint32_t)c0, a);
-                    tmem_wait_ld();
-                    const unsigned mk = below_mask32(a, thr);
-                    cnt += __popc(mk);
-                    if (mk) idx = c0 + __ffs(mk) - 1;
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[g]);
+                m = fminf(m, min32(a));
             }
+            const float thr = m + E2;
+            int cnt = 0, idx = 0;
+            for (int c0 = 0; c0 < nk; c0 += 32) {
+                uint32_t a[32];
+                tmem_ld32(taddr + (uint32_t)c0, a);
+                tmem_wait_ld();
+                const unsigned mk = below_mask32(a, thr);
+                cnt += __popc(mk);
+                if (mk) idx = c0 + __ffs(mk) - 1;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[g]);  // accumulator g may be overwritten
 
             int lab = k;
             if (active) {
@@ -492,7 +476,7 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
                     lab = bl;
                     have_best = true;
                 }
-                if (p.label_kind != HK_LABEL_NONE) store_label_tc(p.labels, p.label_kind, row0 + gt, lab);
+                if (p.label_kind != HK_LABEL_NONE) store_label_tc(p.labels, p.label_kind, (int64_t)row0 + gt, lab);
                 if (p.fv_part != nullptr) {
                     if (!have_best) {
                         if (xn_mode == XN_READ) xr = row_norm2(xt, gt, d);
@@ -505,35 +489,28 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
             }
 
             if (SUMS) {
-                // ---- deterministic counting sort of the tile's rows by label (group-local) ----
+                // ---- deterministic counting sort of the tile's rows by label: two group barriers ----
                 const unsigned peers = __match_any_sync(0xffffffffu, lab);
                 const int rank = __popc(peers & lanemask_lt());
-                const int leader = __ffs(peers) - 1;
-                if (lane == leader) wcnt[q * (k + 1) + lab] = __popc(peers);
-                named_bar_sync(bar_id, GT);
-                for (int c = gt; c <= k; c += GT) {
-                    int run = 0;
-#pragma unroll
-                    for (int w = 0; w < GW; ++w) {
-                        const int vv = wcnt[w * (k + 1) + c];
-                        wcnt[w * (k + 1) + c] = 0;
-                        wpre[w * (k + 1) + c] = run;
-                        run += vv;
-                    }
-                    tcnt[c] = run;
-                    if (c < k) cnts[c] += (unsigned long long)run;
-                }
+                const bool leader = lane == __ffs(peers) - 1;
+                if (leader) wcnt[lab * 4 + q] = __popc(peers);
+                named_bar_sync(bar_id, GT);  // (1) per-warp label counts visible; previous tile fully consumed
                 if (xn_mode == XN_WRITE && gt == 0) {
-                    const float* gx = gxn + (v & 1) * GW;
+                    const float* gx = gxn + gph * GW;
                     p.bounds[tile] = fmaxf(fmaxf(gx[0], gx[1]), fmaxf(gx[2], gx[3]));
                 }
-                named_bar_sync(bar_id, GT);
-                if (q == 0) {
-                    const int per = (k + 1 + 31) / 32;
+                {
+                    // every warp redundantly scans the (k+1) cluster totals: lane owns `per` consecutive clusters
+                    const int per = (kp1 + 31) >> 5;
                     const int b0 = lane * per;
                     int local = 0;
-                    for (int ii = 0; ii < per; ++ii)
-                        if (b0 + ii <= k) local += tcnt[b0 + ii];
+                    for (int ii = 0; ii < per; ++ii) {
+                        const int c = b0 + ii;
+                        if (c <= k) {
+                            const int4 w4 = wcnt4[c];
+                            local += (w4.x + w4.y) + (w4.z + w4.w);
+                        }
+                    }
                     int incl = local;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -541,33 +518,48 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
                         if (lane >= o) incl += vv;
                     }
                     int run = incl - local;
-                    for (int ii = 0; ii < per; ++ii)
-                        if (b0 + ii <= k) {
-                            seg[b0 + ii] = run;
-                            run += tcnt[b0 + ii];
+                    for (int ii = 0; ii < per; ++ii) {
+                        const int c = b0 + ii;
+                        if (c <= k) {
+                            const int4 w4 = wcnt4[c];
+                            const int t = (w4.x + w4.y) + (w4.z + w4.w);
+                            seg[c] = run;  // all four warps store identical values
+                            if (q == 0 && c < k) cnts[c] += (unsigned long long)t;
+                            run += t;
                         }
-                    if (lane == 31) seg[k + 1] = incl;
+                    }
+                    if (lane == 31) seg[kp1] = incl;
                 }
-                named_bar_sync(bar_id, GT);
-                // perm holds the swizzled byte offset of the row inside a K-block: (r << 7) | ((r & 7) << 4)
-                perm[seg[lab] + wpre[q * (k + 1) + lab] + rank] = (unsigned short)((gt << 7) | ((gt & 7) << 4));
-                named_bar_sync(bar_id, GT);
+                __syncwarp();
+                {
+                    const int4 w4 = wcnt4[lab];
+                    int pos = seg[lab] + rank;
+                    if (q > 0) pos += w4.x;
+                    if (q > 1) pos += w4.y;
+                    if (q > 2) pos += w4.z;
+                    // perm holds the swizzled byte offset of the row inside a K-block: (r << 7) | ((r & 7) << 4)
+                    perm[pos] = (unsigned short)((gt << 7) | ((gt & 7) << 4));
+                }
+                named_bar_sync(bar_id, GT);  // (2) perm/seg complete; wcnt reads done
+                if (leader) wcnt[lab * 4 + q] = 0;  // clean table for the next tile
                 // ---- segmented column sums ----
                 const unsigned char* xk = xt + kboff;
                 if constexpr (CPS > 0) {
                     // register accumulators: slice sl always owns clusters [c_base, c_base + CPS)
                     if (sl < SL) {
+                        int e = seg[c_base < kp1 ? c_base : kp1];
 #pragma unroll
                         for (int cc = 0; cc < NACC; ++cc) {
-                            const int c = c_base + cc;
-                            if (c < k) {
-                                const int b = seg[c], e = seg[c + 1];
+                            const int b = e;
+                            const int cn1 = c_base + cc + 1;
+                            e = seg[cn1 < kp1 ? cn1 : kp1];
+                            if (c_base + cc < k) {
                                 for (int ii = b + sub; ii < e; ii += stride) {
-                                    const float4 xv = *reinterpret_cast<const float4*>(xk + ((uint32_t)perm[ii] ^ cx));
-                                    acc[cc].x += xv.x;
-                                    acc[cc].y += xv.y;
-                                    acc[cc].z += xv.z;
-                                    acc[cc].w += xv.w;
+                                    const float4 x4 = *reinterpret_cast<const float4*>(xk + ((uint32_t)perm[ii] ^ cx));
+                                    acc[cc].x += x4.x;
+                                    acc[cc].y += x4.y;
+                                    acc[cc].z += x4.z;
+                                    acc[cc].w += x4.w;
                                 }
                                 rows_since += e - b;
                             }
@@ -583,11 +575,11 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
                             const int b = seg[c], e = seg[c + 1];
                             float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
                             for (int ii = b + sb; ii < e; ii += p.nsub) {
-                                const float4 xv = *reinterpret_cast<const float4*>(xk + ((uint32_t)perm[ii] ^ cx));
-                                a4.x += xv.x;
-                                a4.y += xv.y;
-                                a4.z += xv.z;
-                                a4.w += xv.w;
+                                const float4 x4 = *reinterpret_cast<const float4*>(xk + ((uint32_t)perm[ii] ^ cx));
+                                a4.x += x4.x;
+                                a4.y += x4.y;
+                                a4.z += x4.z;
+                                a4.w += x4.w;
                             }
                             if (b + sb < e) {
                                 double* sp = sums + ((size_t)sb * k + c) * d + (fq << 2);
@@ -602,13 +594,19 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
             } else if (xn_mode == XN_WRITE) {
                 named_bar_sync(bar_id, GT);
                 if (gt == 0) {
-                    const float* gx = gxn + (v & 1) * GW;
+                    const float* gx = gxn + gph * GW;
                     p.bounds[tile] = fmaxf(fmaxf(gx[0], gx[1]), fmaxf(gx[2], gx[3]));
                 }
             }
-            // every thread of the group is done with stage s (and with perm/seg of this tile)
-            named_bar_sync(bar_id, GT);
-            if (gt == 0) mbar_arrive(&empty[s]);
+            // this warp is done with stage s (the next tile's barrier (1) separates perm/seg reuse)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            s += G;
+            if (s >= S) {
+                s -= S;
+                ph ^= 1;
+            }
+            gph ^= 1;
         }
 
         if (SUMS) {
@@ -659,7 +657,7 @@ __global__ void reduce_partials_tc_kernel(const double* __restrict__ part, int n
 }
 
 struct TcPlan {
-    int G, S, nk, nsub, nch, cps;
+    int G, S, nk, nsub, cps;
     uint32_t tmem_cols;
     size_t smem;
     bool ok;
@@ -669,7 +667,6 @@ TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
     TcPlan pl{};
     pl.ok = false;
     pl.nk = (k + 31) / 32 * 32;
-    pl.nch = pl.nk <= 64 ? pl.nk / 32 : 0;
     const int FQ = d / 4;
     const int SL = GT / (FQ < GT ? FQ : GT);
     pl.nsub = SL / k;
@@ -679,8 +676,7 @@ TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
     pl.cps = cps <= 1 ? 1 : (cps <= 2 ? 2 : (cps <= 4 ? 4 : (cps <= 8 ? 8 : 0)));
     if (!sums) pl.cps = 1;
     const size_t budget = (size_t)h->smem_optin;
-    const int gmax = pl.nch == 2 ? 3 : 4;  // 64 accumulator registers per thread: keep 128 regs/thread
-    for (int G = gmax; G >= 2; --G) {
+    for (int G = 4; G >= 2; --G) {
         if (G * pl.nk > 512) continue;
         for (int S = 8; S >= 3; --S) {
             TcLayout L = tc_layout(d, k, pl.nk, S, G, pl.nsub, sums);
@@ -699,9 +695,9 @@ TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
     return pl;
 }
 
-template <int G, bool SUMS, int NCH, int CPS>
+template <int G, bool SUMS, int CPS>
 int launch_inst(Handle* h, const CUtensorMap& map, TcParams& p, size_t smem, int grid, cudaStream_t st) {
-    auto kern = lloyd_tc_kernel<G, SUMS, NCH, CPS>;
+    auto kern = lloyd_tc_kernel<G, SUMS, CPS>;
     HK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(h, st);
     kern<<<grid, MISC + G * GT, smem, st>>>(map, p);
@@ -711,26 +707,16 @@ int launch_inst(Handle* h, const CUtensorMap& map, TcParams& p, size_t smem, int
     return 0;
 }
 
-template <int G, int NCH>
-int launch_gn(Handle* h, const CUtensorMap& map, TcParams& p, const TcPlan& pl, bool sums, int grid,
-              cudaStream_t st) {
-    if (!sums) return launch_inst<G, false, NCH, 1>(h, map, p, pl.smem, grid, st);
-    switch (pl.cps) {
-        case 1: return launch_inst<G, true, NCH, 1>(h, map, p, pl.smem, grid, st);
-        case 2: return launch_inst<G, true, NCH, 2>(h, map, p, pl.smem, grid, st);
-        case 4: return launch_inst<G, true, NCH, 4>(h, map, p, pl.smem, grid, st);
-        case 8: return launch_inst<G, true, NCH, 8>(h, map, p, pl.smem, grid, st);
-        default: return launch_inst<G, true, NCH, 0>(h, map, p, pl.smem, grid, st);
-    }
-}
-
 template <int G>
 int launch_g(Handle* h, const CUtensorMap& map, TcParams& p, const TcPlan& pl, bool sums, int grid,
              cudaStream_t st) {
-    switch (pl.nch) {
-        case 1: return launch_gn<G, 1>(h, map, p, pl, sums, grid, st);
-        case 2: return launch_gn<G, 2>(h, map, p, pl, sums, grid, st);
-        default: return launch_gn<G, 0>(h, map, p, pl, sums, grid, st);
+    if (!sums) return launch_inst<G, false, 1>(h, map, p, pl.smem, grid, st);
+    switch (pl.cps) {
+        case 1: return launch_inst<G, true, 1>(h, map, p, pl.smem, grid, st);
+        case 2: return launch_inst<G, true, 2>(h, map, p, pl.smem, grid, st);
+        case 4: return launch_inst<G, true, 4>(h, map, p, pl.smem, grid, st);
+        case 8: return launch_inst<G, true, 8>(h, map, p, pl.smem, grid, st);
+        default: return launch_inst<G, true, 0>(h, map, p, pl.smem, grid, st);
     }
 }
 
@@ -771,6 +757,24 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
     p.num_tiles = (a.n + TM - 1) / TM;
     p.state = a.state;
     p.tmem_cols = pl.tmem_cols;
+    {
+        const TcLayout L = tc_layout(a.d, a.k, pl.nk, pl.S, pl.G, pl.nsub, sums);
+        p.o_stages = (uint32_t)L.stages;
+        p.o_B = (uint32_t)L.B;
+        p.o_Aext = (uint32_t)L.Aext;
+        p.o_Bext = (uint32_t)L.Bext;
+        p.o_cn = (uint32_t)L.cn;
+        p.o_grp = (uint32_t)L.grp;
+        p.grp_stride = (uint32_t)L.grp_stride;
+        p.o_bars = (uint32_t)L.bars;
+        p.o_misc = (uint32_t)L.misc;
+        p.g_sums = (uint32_t)L.sums;
+        p.g_cnts = (uint32_t)L.cnts;
+        p.g_wcnt = (uint32_t)L.wcnt;
+        p.g_seg = (uint32_t)L.seg;
+        p.g_perm = (uint32_t)L.perm;
+        p.g_gxn = (uint32_t)L.gxn;
+    }
 
     // per-tile |x|^2 bound cache, keyed by the matrix identity (reset with hk_cache_reset)
     const size_t need = ((size_t)p.num_tiles + 4) * sizeof(float);
@@ -804,8 +808,8 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
     p.fv_part = a.fv_out ? h->part + (size_t)nb * len : nullptr;
 
     char name[112];
-    snprintf(name, sizeof(name), "tc<f32,d=%d,k=%d,G=%d,S=%d,nch=%d,cps=%d,%s,%s>", a.d, a.k, pl.G, pl.S, pl.nch,
-             pl.cps, sums ? "sums" : "assign", p.want_write ? "xn-write" : "xn-cached");
+    snprintf(name, sizeof(name), "tc<f32,d=%d,k=%d,G=%d,S=%d,cps=%d,%s,%s>", a.d, a.k, pl.G, pl.S, pl.cps,
+             sums ? "sums" : "assign", p.want_write ? "xn-write" : "xn-cached");
     h->variant = name;
 
     switch (pl.G) {
