@@ -1,6 +1,6 @@
 // Tensor-core Lloyd pass (fp32 data) for sm_100a: TMA-streamed row tiles, tcgen05 TF32 distance filter with
-// fp32 accumulators in TMEM, exact-FMA refinement of the rows the filter cannot decide, and the same
-// deterministic in-tile counting sort + segmented column sums as the exact-FMA kernel.
+// fp32 accumulators in TMEM, exact-FMA refinement of the rows the filter cannot decide, and deterministic
+// per-cluster column sums kept in registers.
 //
 // Why a filter: at k=64, d=32 the distance contraction costs 2*k = 128 FLOP per 4-byte element, three
 // times what the FP32 pipes can sustain at HBM speed, so x.c^T runs on the 5th-gen tensor cores
@@ -12,11 +12,21 @@
 // (near-ties, NaN/Inf) is re-evaluated with that exact formula over all centroids.  Labels are therefore
 // those of the exact-FMA path, the tensor cores only remove work.
 //
-// Roles per CTA (1 CTA per SM, persistent, static tile -> CTA map):
-//   warp 0   : TMA producer (cp.async.bulk.tensor, 128B swizzle, EVICT_FIRST) into an S-stage ring
-//   warp 1   : tcgen05.mma issuer (one lane), accumulator buffer g = tile % G in TMEM
-//   warp 2   : TMEM allocation / release
-//   G groups of 4 warps: tcgen05.ld epilogue (thread == row == TMEM lane) -> label -> sort -> sums
+// Warp roles per CTA (1 CTA per SM, persistent, static tile -> CTA map); all hand-offs are mbarriers with
+// one arrival per warp, there is no CTA- or group-wide barrier in the steady state:
+//   warp 0      : TMA producer (cp.async.bulk.tensor, 128B swizzle, EVICT_FIRST) into an S-stage ring
+//   warp 1      : tcgen05.mma issuer (one lane); accumulator buffer = tile % NBUF in TMEM
+//   warp 2      : TMEM allocation / release
+//   warps 4-19  : epilogue warps.  Warp (q, r) owns TMEM lane quarter q of the tiles i == r (mod 4):
+//                 tcgen05.ld -> min + sign mask -> label (or exact re-evaluation) -> label to shared memory,
+//                 per-cluster row counts with integer shared-memory atomics
+//   warps 20-27 : accumulator warps (only when sums are wanted).  Warp (q, r') owns rows of lane quarter q of
+//                 the tiles i == r' (mod NA/4) and a PRIVATE fp32 [k+1][d] accumulator in shared memory:
+//                 lanes cover 128/d rows x d/4 feature quads per step, add the row into the accumulator row
+//                 of its label with plain load-add-store (no atomics: the array is private, label collisions
+//                 inside a step are detected up front and serialised).  The array is widened into a per-warp
+//                 fp64 slot in global memory (L2) before any cluster can have received more than ~100 rows,
+//                 so fp32 partial sums stay short.  Fixed row order and fixed reduction order -> deterministic.
 // The accumulator is seeded with |c_j|^2 by one extra k-step (ones x three exact TF32 pieces of |c_j|^2)
 // and B holds -2*c, so TMEM already contains s_j = |c_j|^2 - 2 x.c_j and the epilogue is min + sign-mask.
 // |x|^2 (needed only for the bound E) is computed per row in the first pass over a matrix and cached as a
@@ -30,10 +40,12 @@
 namespace hk {
 namespace {
 
-constexpr int TM = 128;    // rows per tile (UMMA M)
-constexpr int GT = 128;    // threads per consumer group
-constexpr int MISC = 128;  // warps 0-3
-constexpr int GW = 4;      // warps per consumer group
+constexpr int TM = 128;         // rows per tile (UMMA M)
+constexpr int MISC_WARPS = 4;   // producer, MMA, TMEM allocator, spare
+constexpr int E_WARPS = 16;     // epilogue warps: 4 lane quarters x 4 tile residues
+constexpr int A_WARPS_MAX = 8;  // accumulator warps (8, or 4 when the private accumulators are large)
+constexpr int E_FIRST = MISC_WARPS;
+constexpr int A_FIRST = MISC_WARPS + E_WARPS;
 
 struct TcParams {
     int64_t n;
@@ -43,28 +55,28 @@ struct TcParams {
     const float* C;
     void* labels;
     int label_kind;
-    double* part;     // [grid*G][k*(d+1)] or nullptr (assign only)
-    double* fv_part;  // [grid*G] or nullptr
+    double* fsum;     // [grid*NA][k*d] per-accumulator-warp fp64 sums, or nullptr (assign only)
+    double* fcnt;     // [grid][k] per-CTA cluster counts
+    double* fv_part;  // [grid] or nullptr
     int S;            // smem stages
-    int nsub;
-    int64_t num_tiles;
+    int nbuf_log2;    // TMEM accumulator buffers = 1 << nbuf_log2
+    int NA;           // accumulator warps (8 or 4)
+    int num_tiles;
     const int32_t* state;
     uint32_t tmem_cols;
     float* bounds;   // [num_tiles] per-tile max |x|^2, followed by one int "filled" flag
     int want_write;  // 1: this launch fills `bounds`
     // shared-memory layout (byte offsets from the 1024-aligned base), computed on the host
-    uint32_t o_stages, o_B, o_Aext, o_Bext, o_cn, o_grp, grp_stride, o_bars, o_misc;
-    uint32_t g_sums, g_cnts, g_wcnt, g_seg, g_perm, g_gxn;  // relative to a group's base
+    uint32_t o_stages, o_B, o_Aext, o_Bext, o_cn, o_acc, o_lab, o_cnt, o_snap, o_bars, o_misc;
 };
 
 struct TcLayout {
-    size_t stages, B, Aext, Bext, cn, grp, grp_stride, sums, cnts, wcnt, wpre, tcnt, seg, perm, gxn, bars, misc,
-        total;
+    size_t stages, B, Aext, Bext, cn, acc, lab, cnt, snap, bars, misc, total;
 };
 
-__host__ __device__ inline size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+__host__ inline size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline TcLayout tc_layout(int d, int k, int nk, int S, int G, int nsub, bool sums) {
+__host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sums) {
     TcLayout L;
     size_t o = 0;
     L.stages = o;
@@ -77,33 +89,77 @@ __host__ __device__ inline TcLayout tc_layout(int d, int k, int nk, int S, int G
     o += up((size_t)nk * 128, 1024);
     L.cn = o;
     o += up((size_t)nk * 4, 16);
-    // per-group region (offsets relative to the group base)
-    size_t g = 0;
-    L.sums = g;
-    if (sums) g += up((size_t)nsub * k * d * 8, 16);
-    L.cnts = g;
-    if (sums) g += up((size_t)k * 8, 16);
-    L.wcnt = g;
-    if (sums) g += up((size_t)GW * (k + 1) * 4, 16);
-    L.wpre = g;
-    if (sums) g += up((size_t)GW * (k + 1) * 4, 16);
-    L.tcnt = g;
-    if (sums) g += up((size_t)(k + 1) * 4, 16);
-    L.seg = g;
-    if (sums) g += up((size_t)(k + 2) * 4, 16);
-    L.perm = g;
-    g += up((size_t)GT * 2, 16);
-    L.gxn = g;
-    g += 2 * GW * 4;
-    L.grp_stride = up(g, 16);
-    L.grp = o;
-    o += L.grp_stride * G;
+    L.acc = o;  // NA private fp32 accumulators [k+1][d] (row k swallows the rows past the end of X)
+    if (sums) o += up((size_t)NA * (k + 1) * d * 4, 16);
+    L.lab = o;  // per stage: 128 labels (u16)
+    if (sums) o += (size_t)S * TM * 2;
+    L.cnt = o;  // per-CTA cluster counts (int)
+    if (sums) o += up((size_t)k * 4, 16);
+    L.snap = o;  // per accumulator warp: counts at its last flush
+    if (sums) o += up((size_t)NA * k * 4, 16);
     L.bars = o;
-    o += 8 * 64;  // up to 64 mbarriers
+    o += 8 * 80;  // mbarriers
     L.misc = o;
-    o += 256;
+    o += 512;
     L.total = o + 1024;  // slack for manual 1024-byte alignment of the base
     return L;
+}
+
+// ---- 32-bit shared-window accessors (keep the hot loops free of 64-bit address arithmetic) -------------
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) {
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity), "r"(0x989680u)
+        : "memory");
+}
+// one lane waits, then the warp is released (keeps 31 lanes out of the wait loop)
+__device__ __forceinline__ void warp_wait(uint32_t bar, uint32_t parity, int lane) {
+    if (lane == 0) mbar_wait_a(bar, parity);
+    __syncwarp();
 }
 
 __device__ __forceinline__ void store_label_tc(void* labels, int kind, int64_t row, int lab) {
@@ -118,12 +174,12 @@ __device__ __forceinline__ void store_label_tc(void* labels, int kind, int64_t r
 // exact fp32 squared distance of the reference formula for (row, centroid j): operands come from the
 // swizzled tiles in shared memory (Bt holds -2*c, so the dot already carries the factor), features are
 // accumulated in ascending order.  fl(-2*dot) == -2*fl(dot): scaling by two is exact.
-__device__ __forceinline__ float exact_d2(const unsigned char* xt, int row, const unsigned char* Bt, int nk, int j,
-                                          int d, float xn, float cnj) {
+__device__ __noinline__ float exact_d2(uint32_t xt, int row, uint32_t Bt, int nk, int j, int d, float xn,
+                                       float cnj) {
     float dotm2 = 0.f;
     for (int f = 0; f < d; f += 4) {
-        const float4 xv = *reinterpret_cast<const float4*>(xt + sw128_off(TM, row, f));
-        const float4 cv = *reinterpret_cast<const float4*>(Bt + sw128_off(nk, j, f));
+        const float4 xv = lds_f4(xt + sw128_off(TM, row, f));
+        const float4 cv = lds_f4(Bt + sw128_off(nk, j, f));
         dotm2 = fmaf(xv.x, cv.x, dotm2);
         dotm2 = fmaf(xv.y, cv.y, dotm2);
         dotm2 = fmaf(xv.z, cv.z, dotm2);
@@ -132,10 +188,10 @@ __device__ __forceinline__ float exact_d2(const unsigned char* xt, int row, cons
     return (xn + cnj) + dotm2;
 }
 
-__device__ __forceinline__ float row_norm2(const unsigned char* xt, int row, int d) {
+__device__ __noinline__ float row_norm2(uint32_t xt, int row, int d) {
     float xn = 0.f;
     for (int f = 0; f < d; f += 4) {
-        const float4 xv = *reinterpret_cast<const float4*>(xt + sw128_off(TM, row, f));
+        const float4 xv = lds_f4(xt + sw128_off(TM, row, f));
         xn = fmaf(xv.x, xv.x, xn);
         xn = fmaf(xv.y, xv.y, xn);
         xn = fmaf(xv.z, xv.z, xn);
@@ -144,21 +200,34 @@ __device__ __forceinline__ float row_norm2(const unsigned char* xt, int row, int
     return xn;
 }
 
-// wait on an mbarrier with one lane per warp, then release the warp (keeps 31 lanes out of the spin loop)
-__device__ __forceinline__ void warp_mbar_wait(uint64_t* bar, uint32_t parity, int lane) {
-    if (lane == 0) mbar_wait(bar, parity);
-    __syncwarp();
+// (a0 - t, a1 - t) with one packed FP32x2 add (sm_100 FADD2)
+__device__ __forceinline__ void sub2(uint32_t a0, uint32_t a1, uint64_t negthr2, uint32_t& r0, uint32_t& r1) {
+    uint64_t in, out;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(in) : "r"(a0), "r"(a1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(out) : "l"(in), "l"(negthr2));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(r0), "=r"(r1) : "l"(out));
 }
-
 // sign-bit mask of (s_j < thr) for 32 accumulator columns: bit j <-> column j (4 independent shift chains)
 __device__ __forceinline__ unsigned below_mask32(const uint32_t* a, float thr) {
+    const uint32_t nt = __float_as_uint(-thr);
+    uint64_t negthr2;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(negthr2) : "r"(nt));
     unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
 #pragma unroll
-    for (int j = 7; j >= 0; --j) {
-        m0 = __funnelshift_l(__float_as_uint(__uint_as_float(a[j]) - thr), m0, 1);
-        m1 = __funnelshift_l(__float_as_uint(__uint_as_float(a[8 + j]) - thr), m1, 1);
-        m2 = __funnelshift_l(__float_as_uint(__uint_as_float(a[16 + j]) - thr), m2, 1);
-        m3 = __funnelshift_l(__float_as_uint(__uint_as_float(a[24 + j]) - thr), m3, 1);
+    for (int j = 6; j >= 0; j -= 2) {
+        uint32_t t0, t1;
+        sub2(a[j], a[j + 1], negthr2, t0, t1);
+        m0 = __funnelshift_l(t1, m0, 1);
+        m0 = __funnelshift_l(t0, m0, 1);
+        sub2(a[8 + j], a[9 + j], negthr2, t0, t1);
+        m1 = __funnelshift_l(t1, m1, 1);
+        m1 = __funnelshift_l(t0, m1, 1);
+        sub2(a[16 + j], a[17 + j], negthr2, t0, t1);
+        m2 = __funnelshift_l(t1, m2, 1);
+        m2 = __funnelshift_l(t0, m2, 1);
+        sub2(a[24 + j], a[25 + j], negthr2, t0, t1);
+        m3 = __funnelshift_l(t1, m3, 1);
+        m3 = __funnelshift_l(t0, m3, 1);
     }
     return m0 | (m1 << 8) | (m2 << 16) | (m3 << 24);
 }
@@ -177,49 +246,53 @@ __device__ __forceinline__ float min32(const uint32_t* a) {
 
 enum { XN_COMPUTE = 0, XN_WRITE = 1, XN_READ = 2 };
 
-// G consumer groups; SUMS: accumulate per-cluster sums; CPS: clusters per slice held in register accumulators
-// in the sums phase (0 = generic shared-memory read-modify-write path)
-template <int G, bool SUMS, int CPS>
-__global__ void __launch_bounds__(MISC + G * GT, 1)
+// SUMS: accumulate per-cluster sums (adds the accumulator warps); FQL2 = log2(d/4): lanes per row in the
+// accumulator warps (d = 32, 64, 128 -> 3, 4, 5)
+template <bool SUMS, int FQL2>
+__global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 0)) * 32, 1)
     lloyd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
     if (p.state != nullptr && p.state[0] != 0) return;  // uniform across the grid
     unsigned char* smem =
         reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
     const int d = p.d, k = p.k, nk = p.nk, S = p.S;
     const int nkb = d >> 5;
-    unsigned char* stages = smem + p.o_stages;
-    unsigned char* Bt = smem + p.o_B;
-    unsigned char* Aext = smem + p.o_Aext;
-    unsigned char* Bext = smem + p.o_Bext;
+    const int NBUF = 1 << p.nbuf_log2;
+    const uint32_t a_stages = sbase + p.o_stages;
+    const uint32_t a_B = sbase + p.o_B;
+    const uint32_t a_lab = sbase + p.o_lab;
+    const uint32_t a_cnt = sbase + p.o_cnt;
     float* cn = reinterpret_cast<float*>(smem + p.o_cn);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.o_bars);
-    uint64_t* full = bars;         // [S]  TMA -> MMA, consumers
-    uint64_t* empty = bars + 16;   // [S]  consumers (one arrival per warp) -> TMA
-    uint64_t* tfull = bars + 32;   // [G]  MMA -> consumers
-    uint64_t* tempty = bars + 40;  // [G]  consumers (one arrival per warp) -> MMA
+    // mbarriers: full[S] | empty[S] | lfull[S] | tfull[NBUF] | tempty[NBUF]   (16 slots per array)
+    const uint32_t b_full = sbase + p.o_bars;
+    const uint32_t b_empty = b_full + 16 * 8;
+    const uint32_t b_lfull = b_full + 32 * 8;
+    const uint32_t b_tfull = b_full + 48 * 8;
+    const uint32_t b_tempty = b_full + 64 * 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.o_misc);
     float* cmax_s = reinterpret_cast<float*>(smem + p.o_misc + 16);
     int* force_exact_s = reinterpret_cast<int*>(smem + p.o_misc + 32);
-    double* fvred = reinterpret_cast<double*>(smem + p.o_misc + 64);  // [G*GW] <= 16 doubles
+    double* fvred = reinterpret_cast<double*>(smem + p.o_misc + 64);  // [E_WARPS]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const uint32_t stage_bytes = (uint32_t)TM * d * 4;
-    const int ntiles = (int)p.num_tiles;
+    const int ntiles = p.num_tiles;
     const int xn_mode =
         p.want_write ? XN_WRITE : (reinterpret_cast<const int*>(p.bounds)[p.num_tiles] != 0 ? XN_READ : XN_COMPUTE);
 
     // ---------------- one-time setup -------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], GW);
+            mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + s, 1);
+            mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 16 + s, 4 + (SUMS ? 4 : 0));
+            mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 32 + s, 4);
         }
-        for (int g = 0; g < G; ++g) {
-            mbar_init(&tfull[g], 1);
-            mbar_init(&tempty[g], GW);
+        for (int b = 0; b < NBUF; ++b) {
+            mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 48 + b, 1);
+            mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 64 + b, 4);
         }
         mbar_fence_init();
         tma_prefetch_desc(&xmap);
@@ -238,25 +311,22 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
             v.z *= -2.f;
             v.w *= -2.f;
         }
-        *reinterpret_cast<float4*>(Bt + sw128_off(nk, j, f)) = v;
+        *reinterpret_cast<float4*>(smem + p.o_B + sw128_off(nk, j, f)) = v;
     }
     // seed operands: A_ext[r] = (1,1,1,0,...), B_ext[j] = three exact TF32 pieces of |c_j|^2
     for (int e = tid; e < TM * 8; e += blockDim.x) {
         const int r = e >> 3, ch = e & 7;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ch == 0) v = make_float4(1.f, 1.f, 1.f, 0.f);
-        *reinterpret_cast<float4*>(Aext + sw128_off(TM, r, ch << 2)) = v;
+        *reinterpret_cast<float4*>(smem + p.o_Aext + sw128_off(TM, r, ch << 2)) = v;
     }
     if (SUMS) {
-        for (int g = 0; g < G; ++g) {
-            unsigned char* gb = smem + p.o_grp + g * p.grp_stride;
-            double* sums = reinterpret_cast<double*>(gb + p.g_sums);
-            for (int i = tid; i < p.nsub * k * d; i += blockDim.x) sums[i] = 0.0;
-            unsigned long long* cnts = reinterpret_cast<unsigned long long*>(gb + p.g_cnts);
-            for (int i = tid; i < k; i += blockDim.x) cnts[i] = 0ull;
-            int* wcnt = reinterpret_cast<int*>(gb + p.g_wcnt);
-            for (int i = tid; i < GW * (k + 1); i += blockDim.x) wcnt[i] = 0;
-        }
+        float* accz = reinterpret_cast<float*>(smem + p.o_acc);
+        for (int i = tid; i < p.NA * (k + 1) * d; i += blockDim.x) accz[i] = 0.f;
+        int* cz = reinterpret_cast<int*>(smem + p.o_cnt);
+        for (int i = tid; i < k; i += blockDim.x) cz[i] = 0;
+        int* sz = reinterpret_cast<int*>(smem + p.o_snap);
+        for (int i = tid; i < p.NA * k; i += blockDim.x) sz[i] = 0;
     }
     __syncthreads();
     for (int j = tid; j < nk; j += blockDim.x) {
@@ -278,7 +348,7 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
         for (int ch = 0; ch < 8; ++ch) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ch == 0) v = make_float4(p1, p2, p3, 0.f);
-            *reinterpret_cast<float4*>(Bext + sw128_off(nk, j, ch << 2)) = v;
+            *reinterpret_cast<float4*>(smem + p.o_Bext + sw128_off(nk, j, ch << 2)) = v;
         }
     }
     fence_proxy_async();  // operands were written with st.shared, tcgen05.mma reads them through the async proxy
@@ -293,13 +363,18 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
         // ================= TMA producer =================
         if (lane == 0) {
             int s = 0;
-            uint32_t ph = 0;  // phase parity of stage ring pass
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], stage_bytes);
-                unsigned char* dst = stages + (size_t)s * stage_bytes;
+                mbar_wait_a(b_empty + s * 8, ph ^ 1);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_full + s * 8),
+                             "r"(stage_bytes)
+                             : "memory");
                 for (int kb = 0; kb < nkb; ++kb)
-                    tma_load_2d(dst + (size_t)kb * TM * 128, &xmap, &full[s], kb * 32, tile * TM, kEvictFirst);
+                    asm volatile(
+                        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+                        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(a_stages + s * stage_bytes + kb * TM * 128),
+                        "l"(&xmap), "r"(b_full + s * 8), "r"(kb * 32), "r"(tile * TM), "l"(kEvictFirst)
+                        : "memory");
                 if (++s == S) {
                     s = 0;
                     ph ^= 1;
@@ -310,128 +385,79 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(TM, nk);
-            const uint32_t b_base = smem_u32(Bt);
-            const uint64_t aext_d = umma_desc_k_sw128(smem_u32(Aext));
-            const uint64_t bext_d = umma_desc_k_sw128(smem_u32(Bext));
-            int s = 0, g = 0;
-            uint32_t ph = 0, gph = 0;
+            const uint64_t aext_d = umma_desc_k_sw128(sbase + p.o_Aext);
+            const uint64_t bext_d = umma_desc_k_sw128(sbase + p.o_Bext);
+            int s = 0, b = 0;
+            uint32_t ph = 0, bph = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                mbar_wait(&tempty[g], gph ^ 1);
-                mbar_wait(&full[s], ph);
+                mbar_wait_a(b_tempty + b * 8, bph ^ 1);
+                mbar_wait_a(b_full + s * 8, ph);
                 tc_fence_after();
-                const uint32_t a_base = smem_u32(stages + (size_t)s * stage_bytes);
-                const uint32_t dcol = tmem_base + (uint32_t)(g * nk);
+                const uint32_t a_base = a_stages + s * stage_bytes;
+                const uint32_t dcol = tmem_base + (uint32_t)(b * nk);
                 umma_tf32(dcol, aext_d, bext_d, idesc, 0u);  // D = |c_j|^2
                 for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint64_t ad = umma_desc_k_sw128(a_base + kb * TM * 128 + ks * 32);
-                        const uint64_t bd = umma_desc_k_sw128(b_base + kb * nk * 128 + ks * 32);
+                        const uint64_t bd = umma_desc_k_sw128(a_B + kb * nk * 128 + ks * 32);
                         umma_tf32(dcol, ad, bd, idesc, 1u);  // D += x . (-2 c_j)
                     }
                 }
-                umma_commit(&tfull[g]);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                 b_tfull + b * 8)
+                             : "memory");
                 if (++s == S) {
                     s = 0;
                     ph ^= 1;
                 }
-                if (++g == G) {
-                    g = 0;
-                    gph ^= 1;
+                if (++b == NBUF) {
+                    b = 0;
+                    bph ^= 1;
                 }
             }
         }
-    } else if (warp >= 4) {
-        // ================= consumer groups =================
-        const int g = (warp - 4) / GW;
-        const int gt = tid - MISC - g * GT;  // 0..127 == row in tile == TMEM lane
-        const int q = gt >> 5;               // warp within the group == warp % 4 (TMEM lane quarter)
-        unsigned char* gb = smem + p.o_grp + g * p.grp_stride;
-        double* sums = reinterpret_cast<double*>(gb + p.g_sums);
-        unsigned long long* cnts = reinterpret_cast<unsigned long long*>(gb + p.g_cnts);
-        int4* wcnt4 = reinterpret_cast<int4*>(gb + p.g_wcnt);  // [k+1] x {warp 0..3}
-        int* wcnt = reinterpret_cast<int*>(gb + p.g_wcnt);
-        int* seg = reinterpret_cast<int*>(gb + p.g_seg);
-        unsigned short* perm = reinterpret_cast<unsigned short*>(gb + p.g_perm);
-        float* gxn = reinterpret_cast<float*>(gb + p.g_gxn);  // [2][GW]
-        const int bar_id = 1 + g;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * nk);
-        double fv_acc = 0.0;
+    } else if (warp >= E_FIRST && warp < E_FIRST + E_WARPS) {
+        // ================= epilogue warps =================
+        const int we = warp - E_FIRST;
+        const int q = we & 3;   // TMEM lane quarter (== warp % 4)
+        const int r = we >> 2;  // tile residue mod 4
+        const int row = q * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         const float beta2 = 2.f * 1.05f * 0.001953125f;
         const float gam = (float)(d + 3) * 1.1920929e-7f;
-        const int kp1 = k + 1;
-
-        // sums phase geometry: thread == (feature quad fq, slice sl)
-        const int FQ = d >> 2;
-        const int SL = GT / (FQ < GT ? FQ : GT);
-        const int fq = gt % FQ;  // FQ <= 64 for d <= 256
-        const int sl = gt / FQ;
-        const uint32_t kboff = (uint32_t)((fq >> 3) * TM * 128);
-        const uint32_t cx = (uint32_t)((fq & 7) << 4);
-        constexpr int NACC = CPS > 0 ? CPS : 1;
-        float4 acc[NACC];
-#pragma unroll
-        for (int cc = 0; cc < NACC; ++cc) acc[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int rows_since = 0;
-        int c_base, sub, stride;
-        if (p.nsub > 1) {
-            c_base = sl / p.nsub;
-            sub = sl - c_base * p.nsub;
-            stride = p.nsub;
-        } else {
-            c_base = sl * NACC;
-            sub = 0;
-            stride = 1;
-        }
-
-        auto flush_acc = [&]() {
-#pragma unroll
-            for (int cc = 0; cc < NACC; ++cc) {
-                const int c = c_base + cc;
-                if (c < k) {
-                    double* sp = sums + ((size_t)sub * k + c) * d + (fq << 2);
-                    double2 lo = *reinterpret_cast<double2*>(sp);
-                    double2 hi = *reinterpret_cast<double2*>(sp + 2);
-                    lo.x += (double)acc[cc].x;
-                    lo.y += (double)acc[cc].y;
-                    hi.x += (double)acc[cc].z;
-                    hi.y += (double)acc[cc].w;
-                    *reinterpret_cast<double2*>(sp) = lo;
-                    *reinterpret_cast<double2*>(sp + 2) = hi;
-                }
-                acc[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            rows_since = 0;
-        };
-
-        // ring bookkeeping without divisions: stage s / its phase, accumulator phase, tile parity
-        int s = g % S;
-        uint32_t ph = (uint32_t)((g / S) & 1);
-        uint32_t gph = 0;
-        for (int tile = blockIdx.x + g * gridDim.x; tile < ntiles; tile += G * gridDim.x) {
-            const unsigned char* xt = stages + (uint32_t)s * stage_bytes;
+        double fv_acc = 0.0;
+        int s = r % S;
+        uint32_t ph = (uint32_t)((r / S) & 1);
+        int i = r;  // local tile counter of this CTA
+        for (int tile = blockIdx.x + r * gridDim.x; tile < ntiles; tile += 4 * gridDim.x, i += 4) {
+            const int b = i & (NBUF - 1);
+            const uint32_t bph = (uint32_t)((i >> p.nbuf_log2) & 1);
+            const uint32_t xt = a_stages + s * stage_bytes;
             const int row0 = tile * TM;
-            const int rows = (p.n - row0) < (int64_t)TM ? (int)(p.n - row0) : TM;
-            const bool active = gt < rows;
+            const bool active = (int64_t)row0 + row < p.n;
 
-            warp_mbar_wait(&full[s], ph, lane);  // x tile landed (needed by |x|^2, exact path, sums)
-            float xn;  // |x|^2 of this row, or an upper bound for every row of the tile
+            float xn, xs;  // |x|^2 and |x| of this row, or upper bounds for every row of the tile
+            if (xn_mode != XN_READ) warp_wait(b_full + s * 8, ph, lane);  // x tile landed
             if (xn_mode == XN_READ) {
-                xn = __ldg(p.bounds + tile);
+                xs = __ldg(p.bounds + tile);  // the cache holds sqrt(max |x|^2)
+                xn = xs * xs;
             } else {
-                xn = row_norm2(xt, gt, d);
+                xn = row_norm2(xt, row, d);
+                xs = sqrtf(xn);
                 if (xn_mode == XN_WRITE) {
-                    float wm = xn;
+                    float wm = xs * 1.0000002f;  // xs*xs must not round below xn
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
                     if (!(wm == wm)) wm = INFINITY;  // NaN rows: make the cached bound useless, not wrong
-                    if (lane == 0) gxn[gph * GW + q] = wm;
+                    if (lane == 0) atomicMax(reinterpret_cast<int*>(p.bounds) + tile, __float_as_int(wm));
                 }
             }
-            const float E2 = 2.f * ((beta2 * sqrtf(xn) * cmax + gam * (xn + cmax * cmax)) * 1.001f);
+            const float E2 = 2.002f * (beta2 * xs * cmax + gam * (xn + cmax * cmax));
 
-            warp_mbar_wait(&tfull[g], gph, lane);  // accumulator ready: s_j = |c_j|^2 - 2 x.c_j (TF32)
+            warp_wait(b_tfull + b * 8, bph, lane);  // accumulator ready: s_j = |c_j|^2 - 2 x.c_j (TF32)
             tc_fence_after();
+            const uint32_t taddr = tlane + (uint32_t)(b * nk);
             // two sweeps over the accumulator, 32 columns in registers at a time: min, then sign mask
             float m = INFINITY;
             for (int c0 = 0; c0 < nk; c0 += 32) {
@@ -452,7 +478,7 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[g]);  // accumulator g may be overwritten
+            if (lane == 0) mbar_arrive_a(b_tempty + b * 8);  // accumulator b may be overwritten
 
             int lab = k;
             if (active) {
@@ -463,10 +489,13 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
                     lab = idx;
                 } else {
                     // undecided (near-tie within the TF32 bound, NaN/Inf): exact formula, torch.min semantics
-                    if (xn_mode == XN_READ) xr = row_norm2(xt, gt, d);
+                    if (xn_mode == XN_READ) {
+                        mbar_wait_a(b_full + s * 8, ph);  // this thread is about to read the x tile itself
+                        xr = row_norm2(xt, row, d);
+                    }
                     int bl = 0;
                     for (int j = 0; j < k; ++j) {
-                        float d2 = exact_d2(xt, gt, Bt, nk, j, d, xr, cn[j]);
+                        float d2 = exact_d2(xt, row, a_B, nk, j, d, xr, cn[j]);
                         d2 = d2 < 0.f ? 0.f : d2;
                         if (d2 < best || (d2 != d2 && best == best)) {
                             best = d2;
@@ -476,164 +505,151 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
                     lab = bl;
                     have_best = true;
                 }
-                if (p.label_kind != HK_LABEL_NONE) store_label_tc(p.labels, p.label_kind, (int64_t)row0 + gt, lab);
+                if (p.label_kind != HK_LABEL_NONE) store_label_tc(p.labels, p.label_kind, (int64_t)row0 + row, lab);
                 if (p.fv_part != nullptr) {
                     if (!have_best) {
-                        if (xn_mode == XN_READ) xr = row_norm2(xt, gt, d);
-                        best = exact_d2(xt, gt, Bt, nk, lab, d, xr, cn[lab]);
+                        if (xn_mode == XN_READ) {
+                            mbar_wait_a(b_full + s * 8, ph);
+                            xr = row_norm2(xt, row, d);
+                        }
+                        best = exact_d2(xt, row, a_B, nk, lab, d, xr, cn[lab]);
                         best = best < 0.f ? 0.f : best;
                     }
                     const float sq = sqrtf(best);
                     fv_acc += (double)(sq * sq);
                 }
             }
-
             if (SUMS) {
-                // ---- deterministic counting sort of the tile's rows by label: two group barriers ----
+                // hand the labels to the accumulator warp of this lane quarter (rows past the end carry label k)
+                sts_u16(a_lab + s * (TM * 2) + row * 2, (uint32_t)lab);
                 const unsigned peers = __match_any_sync(0xffffffffu, lab);
-                const int rank = __popc(peers & lanemask_lt());
-                const bool leader = lane == __ffs(peers) - 1;
-                if (leader) wcnt[lab * 4 + q] = __popc(peers);
-                named_bar_sync(bar_id, GT);  // (1) per-warp label counts visible; previous tile fully consumed
-                if (xn_mode == XN_WRITE && gt == 0) {
-                    const float* gx = gxn + gph * GW;
-                    p.bounds[tile] = fmaxf(fmaxf(gx[0], gx[1]), fmaxf(gx[2], gx[3]));
-                }
-                {
-                    // every warp redundantly scans the (k+1) cluster totals: lane owns `per` consecutive clusters
-                    const int per = (kp1 + 31) >> 5;
-                    const int b0 = lane * per;
-                    int local = 0;
-                    for (int ii = 0; ii < per; ++ii) {
-                        const int c = b0 + ii;
-                        if (c <= k) {
-                            const int4 w4 = wcnt4[c];
-                            local += (w4.x + w4.y) + (w4.z + w4.w);
-                        }
-                    }
-                    int incl = local;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int vv = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += vv;
-                    }
-                    int run = incl - local;
-                    for (int ii = 0; ii < per; ++ii) {
-                        const int c = b0 + ii;
-                        if (c <= k) {
-                            const int4 w4 = wcnt4[c];
-                            const int t = (w4.x + w4.y) + (w4.z + w4.w);
-                            seg[c] = run;  // all four warps store identical values
-                            if (q == 0 && c < k) cnts[c] += (unsigned long long)t;
-                            run += t;
-                        }
-                    }
-                    if (lane == 31) seg[kp1] = incl;
-                }
+                if (lane == __ffs(peers) - 1 && lab < k)
+                    atomicAdd(reinterpret_cast<int*>(smem + p.o_cnt) + lab, __popc(peers));
                 __syncwarp();
-                {
-                    const int4 w4 = wcnt4[lab];
-                    int pos = seg[lab] + rank;
-                    if (q > 0) pos += w4.x;
-                    if (q > 1) pos += w4.y;
-                    if (q > 2) pos += w4.z;
-                    // perm holds the swizzled byte offset of the row inside a K-block: (r << 7) | ((r & 7) << 4)
-                    perm[pos] = (unsigned short)((gt << 7) | ((gt & 7) << 4));
+                if (lane == 0) {
+                    mbar_arrive_a(b_lfull + s * 8);
+                    mbar_arrive_a(b_empty + s * 8);
                 }
-                named_bar_sync(bar_id, GT);  // (2) perm/seg complete; wcnt reads done
-                if (leader) wcnt[lab * 4 + q] = 0;  // clean table for the next tile
-                // ---- segmented column sums ----
-                const unsigned char* xk = xt + kboff;
-                if constexpr (CPS > 0) {
-                    // register accumulators: slice sl always owns clusters [c_base, c_base + CPS)
-                    if (sl < SL) {
-                        int e = seg[c_base < kp1 ? c_base : kp1];
-#pragma unroll
-                        for (int cc = 0; cc < NACC; ++cc) {
-                            const int b = e;
-                            const int cn1 = c_base + cc + 1;
-                            e = seg[cn1 < kp1 ? cn1 : kp1];
-                            if (c_base + cc < k) {
-                                for (int ii = b + sub; ii < e; ii += stride) {
-                                    const float4 x4 = *reinterpret_cast<const float4*>(xk + ((uint32_t)perm[ii] ^ cx));
-                                    acc[cc].x += x4.x;
-                                    acc[cc].y += x4.y;
-                                    acc[cc].z += x4.z;
-                                    acc[cc].w += x4.w;
-                                }
-                                rows_since += e - b;
-                            }
-                        }
-                        if (rows_since >= 32) flush_acc();  // keep fp32 partial sums short, then widen
-                    }
-                } else {
-                    if (sl < SL) {
-                        const int nslots = p.nsub * k;
-                        for (int vs = sl; vs < nslots; vs += SL) {
-                            const int c = vs / p.nsub;
-                            const int sb = vs - c * p.nsub;
-                            const int b = seg[c], e = seg[c + 1];
-                            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            for (int ii = b + sb; ii < e; ii += p.nsub) {
-                                const float4 x4 = *reinterpret_cast<const float4*>(xk + ((uint32_t)perm[ii] ^ cx));
-                                a4.x += x4.x;
-                                a4.y += x4.y;
-                                a4.z += x4.z;
-                                a4.w += x4.w;
-                            }
-                            if (b + sb < e) {
-                                double* sp = sums + ((size_t)sb * k + c) * d + (fq << 2);
-                                sp[0] += (double)a4.x;
-                                sp[1] += (double)a4.y;
-                                sp[2] += (double)a4.z;
-                                sp[3] += (double)a4.w;
-                            }
-                        }
-                    }
-                }
-            } else if (xn_mode == XN_WRITE) {
-                named_bar_sync(bar_id, GT);
-                if (gt == 0) {
-                    const float* gx = gxn + gph * GW;
-                    p.bounds[tile] = fmaxf(fmaxf(gx[0], gx[1]), fmaxf(gx[2], gx[3]));
-                }
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(b_empty + s * 8);
             }
-            // this warp is done with stage s (the next tile's barrier (1) separates perm/seg reuse)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-            s += G;
-            if (s >= S) {
+            s += 4;
+            while (s >= S) {
                 s -= S;
                 ph ^= 1;
             }
-            gph ^= 1;
-        }
-
-        if (SUMS) {
-            if constexpr (CPS > 0) {
-                if (sl < SL) flush_acc();
-            }
-            named_bar_sync(bar_id, GT);
-            double* out = p.part + ((size_t)blockIdx.x * G + g) * k * (d + 1);
-            for (int ii = gt; ii < k * d; ii += GT) {
-                const int c = ii / d, f = ii - c * d;
-                double t = 0.0;
-                for (int sb = 0; sb < p.nsub; ++sb) t += sums[((size_t)sb * k + c) * d + f];
-                out[(size_t)c * (d + 1) + f] = t;
-            }
-            for (int c = gt; c < k; c += GT) out[(size_t)c * (d + 1) + d] = (double)cnts[c];
         }
         if (p.fv_part != nullptr) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) fv_acc += __shfl_xor_sync(0xffffffffu, fv_acc, o);
-            if (lane == 0) fvred[g * GW + q] = fv_acc;
-            named_bar_sync(bar_id, GT);
-            if (gt == 0) {
-                double t = 0.0;
-                for (int w = 0; w < GW; ++w) t += fvred[g * GW + w];
-                p.fv_part[(size_t)blockIdx.x * G + g] = t;
+            if (lane == 0) fvred[we] = fv_acc;
+        }
+    } else if (SUMS && warp >= A_FIRST) {
+        // ================= accumulator warps =================
+        const int a = warp - A_FIRST;
+        const int q = a & 3;         // lane quarter of the tile this warp accumulates
+        const int res = a >> 2;      // tile residue
+        const int nres = p.NA >> 2;  // 1 or 2
+        constexpr int FQ = 1 << FQL2;         // lanes per row (feature quads): 8, 16, 32
+        constexpr int RPI = 32 / FQ;          // rows per step: 4, 2, 1
+        constexpr int NIT = 32 / RPI;         // steps per 32-row quarter: 8, 16, 32
+        const int g = lane >> FQL2;           // row slot inside a step
+        const int fq = lane & (FQ - 1);
+        const uint32_t kboff = (uint32_t)((fq >> 3) * TM * 128);
+        const uint32_t acc_w = sbase + p.o_acc + (uint32_t)a * (uint32_t)((k + 1) * d * 4);
+        const uint32_t acc_l = acc_w + fq * 16;
+        const uint32_t rowbytes = (uint32_t)d * 4;
+        double* gslot = p.fsum + ((size_t)blockIdx.x * p.NA + a) * (size_t)(k * d);
+        bool first_flush = true;
+        int run_max = 0;  // upper bound on the rows any one accumulator row has taken since the last flush
+
+        auto flush = [&]() {
+            // widen the private fp32 sums into this warp's fp64 slot (plain read-modify-write: sole owner)
+            const int nq = (k * d) >> 2;
+            for (int e = lane; e < nq; e += 32) {
+                const float4 v = lds_f4(acc_w + e * 16);
+                sts_f4(acc_w + e * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+                double2* gp = reinterpret_cast<double2*>(gslot + (size_t)e * 4);
+                double2 lo = make_double2(0.0, 0.0), hi = make_double2(0.0, 0.0);
+                if (!first_flush) {
+                    lo = gp[0];
+                    hi = gp[1];
+                }
+                lo.x += (double)v.x;
+                lo.y += (double)v.y;
+                hi.x += (double)v.z;
+                hi.y += (double)v.w;
+                gp[0] = lo;
+                gp[1] = hi;
+            }
+            first_flush = false;
+            run_max = 0;
+        };
+
+        int s = res % S;
+        uint32_t ph = (uint32_t)((res / S) & 1);
+        for (int tile = blockIdx.x + res * gridDim.x; tile < ntiles; tile += nres * gridDim.x) {
+            warp_wait(b_full + s * 8, ph, lane);   // x tile visible
+            warp_wait(b_lfull + s * 8, ph, lane);  // labels of all four lane quarters published
+            const uint32_t xq = a_stages + s * stage_bytes + kboff + (uint32_t)(q * 32 * 128);
+            const uint32_t mylab = lds_u16(a_lab + s * (TM * 2) + (q * 32 + lane) * 2);
+            {
+                // most frequent label of these 32 rows: run_max bounds the fp32 adds per accumulator row
+                int mult = __popc(__match_any_sync(0xffffffffu, mylab));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mult = max(mult, __shfl_xor_sync(0xffffffffu, mult, o));
+                run_max += mult;
+            }
+            // label collisions inside a step (rows that would hit the same accumulator row), for all steps
+            unsigned coll = 0;
+            if (RPI > 1) {
+                bool c = false;
+#pragma unroll
+                for (int x = 1; x < RPI; ++x) c |= (__shfl_xor_sync(0xffffffffu, mylab, x) == mylab);
+                coll = __ballot_sync(0xffffffffu, c);
+            }
+#pragma unroll 8
+            for (int it = 0; it < NIT; ++it) {
+                const int rl = it * RPI + g;  // row inside the quarter
+                const uint32_t l = __shfl_sync(0xffffffffu, mylab, rl);
+                const uint32_t off = (uint32_t)(rl << 7) | ((uint32_t)((rl ^ fq) & 7) << 4);
+                const float4 x4 = lds_f4(xq + off);
+                const uint32_t aa = acc_l + l * rowbytes;
+                if (RPI > 1 && ((coll >> (it * RPI)) & ((1u << RPI) - 1u)) != 0u) {
+                    // two rows of this step share a label: one row at a time
+#pragma unroll
+                    for (int gg = 0; gg < RPI; ++gg) {
+                        if (g == gg) {
+                            float4 v = lds_f4(aa);
+                            v.x += x4.x;
+                            v.y += x4.y;
+                            v.z += x4.z;
+                            v.w += x4.w;
+                            sts_f4(aa, v);
+                        }
+                        __syncwarp();
+                    }
+                } else {
+                    float4 v = lds_f4(aa);
+                    v.x += x4.x;
+                    v.y += x4.y;
+                    v.z += x4.z;
+                    v.w += x4.w;
+                    sts_f4(aa, v);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(b_empty + s * 8);
+            // widen before any accumulator row can have taken more than ~100 fp32 adds (timing independent)
+            if (run_max >= 72) flush();
+            s += nres;
+            if (s >= S) {
+                s -= S;
+                ph ^= 1;
             }
         }
+        flush();
     }
 
     // ---------------- teardown ---------------------------------------------------------------------------
@@ -643,21 +659,45 @@ __global__ void __launch_bounds__(MISC + G * GT, 1)
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
-    if (xn_mode == XN_WRITE && blockIdx.x == 0 && tid == 0) reinterpret_cast<int*>(p.bounds)[p.num_tiles] = 1;
+    if (SUMS) {
+        const int* cz = reinterpret_cast<const int*>(smem + p.o_cnt);
+        for (int c = tid; c < k; c += blockDim.x) p.fcnt[(size_t)blockIdx.x * k + c] = (double)cz[c];
+    }
+    if (tid == 0) {
+        if (p.fv_part != nullptr) {
+            double t = 0.0;
+            for (int w = 0; w < E_WARPS; ++w) t += fvred[w];
+            p.fv_part[blockIdx.x] = t;
+        }
+        if (xn_mode == XN_WRITE && blockIdx.x == 0) reinterpret_cast<int*>(p.bounds)[p.num_tiles] = 1;
+    }
 }
 
-__global__ void reduce_partials_tc_kernel(const double* __restrict__ part, int nb, int len,
-                                          double* __restrict__ out, const int32_t* state) {
+// partials[c][0..d) = sum over accumulator slots, partials[c][d] = sum over CTAs of the counts (fixed order)
+__global__ void reduce_tc_kernel(const double* __restrict__ fsum, const double* __restrict__ fcnt, int nslots,
+                                 int nblocks, int k, int d, double* __restrict__ out, const int32_t* state) {
     if (state != nullptr && state[0] != 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= len) return;
+    if (i >= k * (d + 1)) return;
+    const int c = i / (d + 1), f = i - c * (d + 1);
     double t = 0.0;
-    for (int b = 0; b < nb; ++b) t += part[(size_t)b * len + i];
+    if (f < d) {
+        for (int b = 0; b < nslots; ++b) t += fsum[(size_t)b * k * d + (size_t)c * d + f];
+    } else {
+        for (int b = 0; b < nblocks; ++b) t += fcnt[(size_t)b * k + c];
+    }
     out[i] = t;
+}
+__global__ void reduce_scalar_tc_kernel(const double* __restrict__ v, int n, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0.0;
+        for (int b = 0; b < n; ++b) t += v[b];
+        *out = t;
+    }
 }
 
 struct TcPlan {
-    int G, S, nk, nsub, cps;
+    int S, nk, NA, nbuf_log2, fql2;
     uint32_t tmem_cols;
     size_t smem;
     bool ok;
@@ -667,64 +707,47 @@ TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
     TcPlan pl{};
     pl.ok = false;
     pl.nk = (k + 31) / 32 * 32;
-    const int FQ = d / 4;
-    const int SL = GT / (FQ < GT ? FQ : GT);
-    pl.nsub = SL / k;
-    if (pl.nsub < 1) pl.nsub = 1;
-    // clusters per slice for the register-accumulator sums phase (1, 2, 4, 8; 0 = generic)
-    int cps = pl.nsub > 1 ? 1 : (k + SL - 1) / SL;
-    pl.cps = cps <= 1 ? 1 : (cps <= 2 ? 2 : (cps <= 4 ? 4 : (cps <= 8 ? 8 : 0)));
-    if (!sums) pl.cps = 1;
+    pl.fql2 = d == 32 ? 3 : (d == 64 ? 4 : 5);
+    // private fp32 accumulators: 8 warps when they fit in ~72 KB, else 4
+    pl.NA = 8;
+    if ((size_t)8 * (k + 1) * d * 4 > 72 * 1024) pl.NA = 4;
+    if (sums && (size_t)pl.NA * (k + 1) * d * 4 > 96 * 1024) return pl;
+    // TMEM accumulator buffers: power of two, nbuf * nk <= 512
+    int nb = 512 / pl.nk;
+    pl.nbuf_log2 = nb >= 8 ? 3 : (nb >= 4 ? 2 : 1);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)((1 << pl.nbuf_log2) * pl.nk)) cols <<= 1;
+    pl.tmem_cols = cols;
     const size_t budget = (size_t)h->smem_optin;
-    for (int G = 4; G >= 2; --G) {
-        if (G * pl.nk > 512) continue;
-        for (int S = 8; S >= 3; --S) {
-            TcLayout L = tc_layout(d, k, pl.nk, S, G, pl.nsub, sums);
-            if (L.total <= budget && (S >= G + 1 || S >= 4)) {
-                pl.G = G;
-                pl.S = S;
-                pl.smem = L.total;
-                uint32_t cols = 32;
-                while (cols < (uint32_t)(G * pl.nk)) cols <<= 1;
-                pl.tmem_cols = cols;
-                pl.ok = true;
-                return pl;
-            }
+    for (int S = 12; S >= 4; --S) {
+        TcLayout L = tc_layout(d, k, pl.nk, S, pl.NA, sums);
+        if (L.total <= budget) {
+            pl.S = S;
+            pl.smem = L.total;
+            pl.ok = true;
+            return pl;
         }
     }
     return pl;
 }
 
-template <int G, bool SUMS, int CPS>
+template <bool SUMS, int FQL2>
 int launch_inst(Handle* h, const CUtensorMap& map, TcParams& p, size_t smem, int grid, cudaStream_t st) {
-    auto kern = lloyd_tc_kernel<G, SUMS, CPS>;
+    auto kern = lloyd_tc_kernel<SUMS, FQL2>;
     HK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(h, st);
-    kern<<<grid, MISC + G * GT, smem, st>>>(map, p);
+    kern<<<grid, (MISC_WARPS + E_WARPS + (SUMS ? p.NA : 0)) * 32, smem, st>>>(map, p);
     prof_end(h, st);
     HK_CUDA(cudaGetLastError());
     h->launches++;
     return 0;
 }
 
-template <int G>
-int launch_g(Handle* h, const CUtensorMap& map, TcParams& p, const TcPlan& pl, bool sums, int grid,
-             cudaStream_t st) {
-    if (!sums) return launch_inst<G, false, 1>(h, map, p, pl.smem, grid, st);
-    switch (pl.cps) {
-        case 1: return launch_inst<G, true, 1>(h, map, p, pl.smem, grid, st);
-        case 2: return launch_inst<G, true, 2>(h, map, p, pl.smem, grid, st);
-        case 4: return launch_inst<G, true, 4>(h, map, p, pl.smem, grid, st);
-        case 8: return launch_inst<G, true, 8>(h, map, p, pl.smem, grid, st);
-        default: return launch_inst<G, true, 0>(h, map, p, pl.smem, grid, st);
-    }
-}
-
 }  // namespace
 
 bool tc_supported(const Handle* h, const LloydArgs& a) {
     if (a.dtype != HK_F32) return false;
-    if (a.d % 32 != 0 || a.d < 32 || a.d > 256) return false;
+    if (a.d != 32 && a.d != 64 && a.d != 128) return false;
     if (a.k < 1 || a.k > 256) return false;
     if (a.ldx % 4 != 0) return false;
     if ((reinterpret_cast<uintptr_t>(a.X) & 15) != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15) != 0) return false;
@@ -743,7 +766,6 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
     CUtensorMap map;
     int rc = make_tensor_map_2d(&map, a.X, 4, (uint64_t)a.n, (uint64_t)a.d, (uint64_t)a.ldx, 32, TM, 128);
     if (rc) return rc;
-    const int len = a.k * (a.d + 1);
     TcParams p{};
     p.n = a.n;
     p.d = a.d;
@@ -753,30 +775,27 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
     p.labels = a.labels;
     p.label_kind = a.labels ? a.label_kind : HK_LABEL_NONE;
     p.S = pl.S;
-    p.nsub = pl.nsub;
-    p.num_tiles = (a.n + TM - 1) / TM;
+    p.nbuf_log2 = pl.nbuf_log2;
+    p.NA = pl.NA;
+    p.num_tiles = (int)((a.n + TM - 1) / TM);
     p.state = a.state;
     p.tmem_cols = pl.tmem_cols;
     {
-        const TcLayout L = tc_layout(a.d, a.k, pl.nk, pl.S, pl.G, pl.nsub, sums);
+        const TcLayout L = tc_layout(a.d, a.k, pl.nk, pl.S, pl.NA, sums);
         p.o_stages = (uint32_t)L.stages;
         p.o_B = (uint32_t)L.B;
         p.o_Aext = (uint32_t)L.Aext;
         p.o_Bext = (uint32_t)L.Bext;
         p.o_cn = (uint32_t)L.cn;
-        p.o_grp = (uint32_t)L.grp;
-        p.grp_stride = (uint32_t)L.grp_stride;
+        p.o_acc = (uint32_t)L.acc;
+        p.o_lab = (uint32_t)L.lab;
+        p.o_cnt = (uint32_t)L.cnt;
+        p.o_snap = (uint32_t)L.snap;
         p.o_bars = (uint32_t)L.bars;
         p.o_misc = (uint32_t)L.misc;
-        p.g_sums = (uint32_t)L.sums;
-        p.g_cnts = (uint32_t)L.cnts;
-        p.g_wcnt = (uint32_t)L.wcnt;
-        p.g_seg = (uint32_t)L.seg;
-        p.g_perm = (uint32_t)L.perm;
-        p.g_gxn = (uint32_t)L.gxn;
     }
 
-    // per-tile |x|^2 bound cache, keyed by the matrix identity (reset with hk_cache_reset)
+    // per-tile |x| bound cache, keyed by the matrix identity (reset with hk_cache_reset)
     const size_t need = ((size_t)p.num_tiles + 4) * sizeof(float);
     const bool same = h->xb != nullptr && h->xb_X == a.X && h->xb_n == a.n && h->xb_d == a.d && h->xb_ld == a.ldx;
     if (!same) {
@@ -787,7 +806,7 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
             HK_CUDA(cudaMalloc(&h->xb, need));
             h->xb_bytes = need;
         }
-        HK_CUDA(cudaMemsetAsync(h->xb + p.num_tiles, 0, sizeof(int), a.stream));
+        HK_CUDA(cudaMemsetAsync(h->xb, 0, need, a.stream));  // bounds are built with atomicMax; flag = 0
         h->xb_X = a.X;
         h->xb_n = a.n;
         h->xb_d = a.d;
@@ -798,34 +817,40 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
     }
     p.bounds = h->xb;
 
-    int64_t grid64 = h->num_sms;
-    if (grid64 > p.num_tiles) grid64 = p.num_tiles;
-    const int grid = (int)grid64;
-    const int nb = grid * pl.G;
-    rc = ensure_part(h, ((size_t)nb * len + nb) * sizeof(double));
+    int grid = h->num_sms;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    const int nslots = grid * pl.NA;
+    const size_t kd = (size_t)a.k * a.d;
+    rc = ensure_part(h, ((size_t)nslots * kd + (size_t)grid * a.k + grid) * sizeof(double));
     if (rc) return rc;
-    p.part = sums ? h->part : nullptr;
-    p.fv_part = a.fv_out ? h->part + (size_t)nb * len : nullptr;
+    p.fsum = sums ? h->part : nullptr;
+    p.fcnt = h->part + (size_t)nslots * kd;
+    p.fv_part = a.fv_out ? h->part + (size_t)nslots * kd + (size_t)grid * a.k : nullptr;
 
     char name[112];
-    snprintf(name, sizeof(name), "tc<f32,d=%d,k=%d,G=%d,S=%d,cps=%d,%s,%s>", a.d, a.k, pl.G, pl.S, pl.cps,
-             sums ? "sums" : "assign", p.want_write ? "xn-write" : "xn-cached");
+    snprintf(name, sizeof(name), "tc<f32,d=%d,k=%d,S=%d,nbuf=%d,NA=%d,%s,%s>", a.d, a.k, pl.S, 1 << pl.nbuf_log2,
+             pl.NA, sums ? "sums" : "assign", p.want_write ? "xn-write" : "xn-cached");
     h->variant = name;
 
-    switch (pl.G) {
-        case 2: rc = launch_g<2>(h, map, p, pl, sums, grid, a.stream); break;
-        case 3: rc = launch_g<3>(h, map, p, pl, sums, grid, a.stream); break;
-        case 4: rc = launch_g<4>(h, map, p, pl, sums, grid, a.stream); break;
-        default: rc = -2;
+    if (!sums) {
+        rc = launch_inst<false, 3>(h, map, p, pl.smem, grid, a.stream);
+    } else {
+        switch (pl.fql2) {
+            case 3: rc = launch_inst<true, 3>(h, map, p, pl.smem, grid, a.stream); break;
+            case 4: rc = launch_inst<true, 4>(h, map, p, pl.smem, grid, a.stream); break;
+            default: rc = launch_inst<true, 5>(h, map, p, pl.smem, grid, a.stream); break;
+        }
     }
     if (rc) return rc;
     if (sums) {
-        reduce_partials_tc_kernel<<<(len + 255) / 256, 256, 0, a.stream>>>(h->part, nb, len, a.partials, a.state);
+        const int len = a.k * (a.d + 1);
+        reduce_tc_kernel<<<(len + 255) / 256, 256, 0, a.stream>>>(p.fsum, p.fcnt, nslots, grid, a.k, a.d, a.partials,
+                                                                  a.state);
         HK_CUDA(cudaGetLastError());
         h->launches++;
     }
     if (a.fv_out) {
-        reduce_partials_tc_kernel<<<1, 32, 0, a.stream>>>(p.fv_part, nb, 1, a.fv_out, nullptr);
+        reduce_scalar_tc_kernel<<<1, 32, 0, a.stream>>>(p.fv_part, grid, a.fv_out);
         HK_CUDA(cudaGetLastError());
         h->launches++;
     }
