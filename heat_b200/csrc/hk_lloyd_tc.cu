@@ -18,8 +18,7 @@
 //   warp 1      : tcgen05.mma issuer (one lane); accumulator buffer = tile % NBUF in TMEM
 //   warp 2      : TMEM allocation / release
 //   warps 4-19  : epilogue warps.  Warp (q, r) owns TMEM lane quarter q of the tiles i == r (mod 4):
-//                 tcgen05.ld -> min + sign mask -> label (or exact re-evaluation) -> label to shared memory,
-//                 per-cluster row counts with integer shared-memory atomics
+//                 tcgen05.ld -> min + sign mask -> label (or exact re-evaluation) -> label to shared memory
 //   warps 20-27 : accumulator warps (only when sums are wanted).  Warp (q, r') owns rows of lane quarter q of
 //                 the tiles i == r' (mod NA/4) and a PRIVATE fp32 [k+1][d] accumulator in shared memory:
 //                 lanes cover 128/d rows x d/4 feature quads per step, add the row into the accumulator row
@@ -34,6 +33,9 @@
 // Replaces _assign_to_cluster + KMeans._update_centroids for one shard
 // (heat/cluster/_kcluster.py:352-370, heat/cluster/kmeans.py:76-103).
 #include <math.h>
+#include <stdlib.h>
+
+#include <vector>
 
 #include "hk_tma.cuh"
 
@@ -68,6 +70,7 @@ struct TcParams {
     int want_write;  // 1: this launch fills `bounds`
     // shared-memory layout (byte offsets from the 1024-aligned base), computed on the host
     uint32_t o_stages, o_B, o_Aext, o_Bext, o_cn, o_acc, o_lab, o_cnt, o_snap, o_bars, o_misc;
+    unsigned long long* dbg;  // optional [grid][32 warps][8] cycle counters (HK_TC_DEBUG=1)
 };
 
 struct TcLayout {
@@ -123,6 +126,10 @@ __device__ __forceinline__ void sts_u4(uint32_t a, uint4 v) {
 __device__ __forceinline__ void sts_f4(uint32_t a, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
+}
+// (volatile asm statements keep their relative order; the private-accumulator traffic needs no more than that)
+__device__ __forceinline__ void sts_f4_nc(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
 }
 __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
@@ -262,7 +269,6 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     const uint32_t a_stages = sbase + p.o_stages;
     const uint32_t a_B = sbase + p.o_B;
     const uint32_t a_lab = sbase + p.o_lab;
-    const uint32_t a_cnt = sbase + p.o_cnt;
     float* cn = reinterpret_cast<float*>(smem + p.o_cn);
     // mbarriers: full[S] | empty[S] | lfull[S] | tfull[NBUF] | tempty[NBUF]   (16 slots per array)
     const uint32_t b_full = sbase + p.o_bars;
@@ -364,8 +370,12 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
+            long long tw = 0;
+            const long long tstart = clock64();
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const long long ta = p.dbg ? clock64() : 0;
                 mbar_wait_a(b_empty + s * 8, ph ^ 1);
+                if (p.dbg) tw += clock64() - ta;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_full + s * 8),
                              "r"(stage_bytes)
                              : "memory");
@@ -380,6 +390,11 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                     ph ^= 1;
                 }
             }
+            if (p.dbg) {
+                unsigned long long* o = p.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;
+                o[0] = (unsigned long long)tw;
+                o[1] = (unsigned long long)(clock64() - tstart);
+            }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -389,9 +404,16 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             const uint64_t bext_d = umma_desc_k_sw128(sbase + p.o_Bext);
             int s = 0, b = 0;
             uint32_t ph = 0, bph = 0;
+            long long tw1 = 0, tw2 = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const long long ta = p.dbg ? clock64() : 0;
                 mbar_wait_a(b_tempty + b * 8, bph ^ 1);
+                const long long tb = p.dbg ? clock64() : 0;
                 mbar_wait_a(b_full + s * 8, ph);
+                if (p.dbg) {
+                    tw1 += tb - ta;
+                    tw2 += clock64() - tb;
+                }
                 tc_fence_after();
                 const uint32_t a_base = a_stages + s * stage_bytes;
                 const uint32_t dcol = tmem_base + (uint32_t)(b * nk);
@@ -416,6 +438,11 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                     bph ^= 1;
                 }
             }
+            if (p.dbg) {
+                unsigned long long* o = p.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;
+                o[0] = (unsigned long long)tw1;
+                o[1] = (unsigned long long)tw2;
+            }
         }
     } else if (warp >= E_FIRST && warp < E_FIRST + E_WARPS) {
         // ================= epilogue warps =================
@@ -430,7 +457,9 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         int s = r % S;
         uint32_t ph = (uint32_t)((r / S) & 1);
         int i = r;  // local tile counter of this CTA
+        long long t_wait = 0, t_work = 0, t_pub = 0, t0 = 0, t1 = 0, t2 = 0;
         for (int tile = blockIdx.x + r * gridDim.x; tile < ntiles; tile += 4 * gridDim.x, i += 4) {
+            if (p.dbg) t0 = clock64();
             const int b = i & (NBUF - 1);
             const uint32_t bph = (uint32_t)((i >> p.nbuf_log2) & 1);
             const uint32_t xt = a_stages + s * stage_bytes;
@@ -456,6 +485,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             const float E2 = 2.002f * (beta2 * xs * cmax + gam * (xn + cmax * cmax));
 
             warp_wait(b_tfull + b * 8, bph, lane);  // accumulator ready: s_j = |c_j|^2 - 2 x.c_j (TF32)
+            if (p.dbg) t1 = clock64();
             tc_fence_after();
             const uint32_t taddr = tlane + (uint32_t)(b * nk);
             // two sweeps over the accumulator, 32 columns in registers at a time: min, then sign mask
@@ -480,6 +510,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             __syncwarp();
             if (lane == 0) mbar_arrive_a(b_tempty + b * 8);  // accumulator b may be overwritten
 
+            if (p.dbg) t2 = clock64();
             int lab = k;
             if (active) {
                 float best = INFINITY;
@@ -522,9 +553,6 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             if (SUMS) {
                 // hand the labels to the accumulator warp of this lane quarter (rows past the end carry label k)
                 sts_u16(a_lab + s * (TM * 2) + row * 2, (uint32_t)lab);
-                const unsigned peers = __match_any_sync(0xffffffffu, lab);
-                if (lane == __ffs(peers) - 1 && lab < k)
-                    atomicAdd(reinterpret_cast<int*>(smem + p.o_cnt) + lab, __popc(peers));
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive_a(b_lfull + s * 8);
@@ -539,6 +567,18 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 s -= S;
                 ph ^= 1;
             }
+            if (p.dbg) {
+                const long long t3 = clock64();
+                t_wait += t1 - t0;
+                t_work += t2 - t1;
+                t_pub += t3 - t2;
+            }
+        }
+        if (p.dbg && lane == 0) {
+            unsigned long long* o = p.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;
+            o[0] = (unsigned long long)t_wait;
+            o[1] = (unsigned long long)t_work;
+            o[2] = (unsigned long long)t_pub;
         }
         if (p.fv_part != nullptr) {
 #pragma unroll
@@ -560,6 +600,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         const uint32_t acc_w = sbase + p.o_acc + (uint32_t)a * (uint32_t)((k + 1) * d * 4);
         const uint32_t acc_l = acc_w + fq * 16;
         const uint32_t rowbytes = (uint32_t)d * 4;
+        const uint32_t a_cntw = sbase + p.o_snap + (uint32_t)a * (uint32_t)(k * 4);  // private cluster counts
         double* gslot = p.fsum + ((size_t)blockIdx.x * p.NA + a) * (size_t)(k * d);
         bool first_flush = true;
         int run_max = 0;  // upper bound on the rows any one accumulator row has taken since the last flush
@@ -589,17 +630,24 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
 
         int s = res % S;
         uint32_t ph = (uint32_t)((res / S) & 1);
+        long long t_wait = 0, t_work = 0, t_fl = 0, t0 = 0, t1 = 0, t2 = 0;
         for (int tile = blockIdx.x + res * gridDim.x; tile < ntiles; tile += nres * gridDim.x) {
+            if (p.dbg) t0 = clock64();
             warp_wait(b_full + s * 8, ph, lane);   // x tile visible
             warp_wait(b_lfull + s * 8, ph, lane);  // labels of all four lane quarters published
+            if (p.dbg) t1 = clock64();
             const uint32_t xq = a_stages + s * stage_bytes + kboff + (uint32_t)(q * 32 * 128);
             const uint32_t mylab = lds_u16(a_lab + s * (TM * 2) + (q * 32 + lane) * 2);
             {
-                // most frequent label of these 32 rows: run_max bounds the fp32 adds per accumulator row
-                int mult = __popc(__match_any_sync(0xffffffffu, mylab));
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mult = max(mult, __shfl_xor_sync(0xffffffffu, mult, o));
-                run_max += mult;
+                // rows per label among these 32 rows: private per-warp cluster counts (leaders hit distinct
+                // addresses) and the bound on fp32 adds per accumulator row since the last flush
+                const unsigned peers = __match_any_sync(0xffffffffu, mylab);
+                const int mult = __popc(peers);
+                if (lane == __ffs(peers) - 1 && mylab < (uint32_t)k) {
+                    const uint32_t ca = a_cntw + mylab * 4;
+                    sts_s32(ca, lds_s32(ca) + mult);
+                }
+                run_max += __reduce_max_sync(0xffffffffu, mult);
             }
             // label collisions inside a step (rows that would hit the same accumulator row), for all steps
             unsigned coll = 0;
@@ -609,40 +657,57 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 for (int x = 1; x < RPI; ++x) c |= (__shfl_xor_sync(0xffffffffu, mylab, x) == mylab);
                 coll = __ballot_sync(0xffffffffu, c);
             }
-#pragma unroll 8
-            for (int it = 0; it < NIT; ++it) {
-                const int rl = it * RPI + g;  // row inside the quarter
-                const uint32_t l = __shfl_sync(0xffffffffu, mylab, rl);
-                const uint32_t off = (uint32_t)(rl << 7) | ((uint32_t)((rl ^ fq) & 7) << 4);
-                const float4 x4 = lds_f4(xq + off);
-                const uint32_t aa = acc_l + l * rowbytes;
-                if (RPI > 1 && ((coll >> (it * RPI)) & ((1u << RPI) - 1u)) != 0u) {
-                    // two rows of this step share a label: one row at a time
+            constexpr int BATCH = NIT < 8 ? NIT : 8;
+#pragma unroll 1
+            for (int it0 = 0; it0 < NIT; it0 += BATCH) {
+                // fetch the rows and the accumulator addresses of a batch of steps, then run the
+                // load-add-store chains (steps may share a label, so the chains stay in order)
+                float4 xr[BATCH];
+                uint32_t aa[BATCH];
 #pragma unroll
-                    for (int gg = 0; gg < RPI; ++gg) {
-                        if (g == gg) {
-                            float4 v = lds_f4(aa);
-                            v.x += x4.x;
-                            v.y += x4.y;
-                            v.z += x4.z;
-                            v.w += x4.w;
-                            sts_f4(aa, v);
+                for (int j = 0; j < BATCH; ++j) {
+                    const int rl = (it0 + j) * RPI + g;  // row inside the quarter
+                    const uint32_t l = __shfl_sync(0xffffffffu, mylab, rl);
+                    aa[j] = acc_l + l * rowbytes;
+                    xr[j] = lds_f4(xq + ((uint32_t)(rl << 7) | ((uint32_t)((rl ^ fq) & 7) << 4)));
+                }
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    if (RPI > 1 && ((coll >> ((it0 + j) * RPI)) & ((1u << RPI) - 1u)) != 0u) {
+                        // two rows of this step share a label: one row at a time
+#pragma unroll
+                        for (int gg = 0; gg < RPI; ++gg) {
+                            if (g == gg) {
+                                float4 v = lds_f4(aa[j]);
+                                v.x += xr[j].x;
+                                v.y += xr[j].y;
+                                v.z += xr[j].z;
+                                v.w += xr[j].w;
+                                sts_f4_nc(aa[j], v);
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
+                    } else {
+                        float4 v = lds_f4(aa[j]);
+                        v.x += xr[j].x;
+                        v.y += xr[j].y;
+                        v.z += xr[j].z;
+                        v.w += xr[j].w;
+                        sts_f4_nc(aa[j], v);
                     }
-                } else {
-                    float4 v = lds_f4(aa);
-                    v.x += x4.x;
-                    v.y += x4.y;
-                    v.z += x4.z;
-                    v.w += x4.w;
-                    sts_f4(aa, v);
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive_a(b_empty + s * 8);
+            if (p.dbg) t2 = clock64();
             // widen before any accumulator row can have taken more than ~100 fp32 adds (timing independent)
             if (run_max >= 72) flush();
+            if (p.dbg) {
+                const long long t3 = clock64();
+                t_wait += t1 - t0;
+                t_work += t2 - t1;
+                t_fl += t3 - t2;
+            }
             s += nres;
             if (s >= S) {
                 s -= S;
@@ -650,6 +715,12 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             }
         }
         flush();
+        if (p.dbg && lane == 0) {
+            unsigned long long* o = p.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;
+            o[0] = (unsigned long long)t_wait;
+            o[1] = (unsigned long long)t_work;
+            o[2] = (unsigned long long)t_fl;
+        }
     }
 
     // ---------------- teardown ---------------------------------------------------------------------------
@@ -660,8 +731,12 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
     if (SUMS) {
-        const int* cz = reinterpret_cast<const int*>(smem + p.o_cnt);
-        for (int c = tid; c < k; c += blockDim.x) p.fcnt[(size_t)blockIdx.x * k + c] = (double)cz[c];
+        const int* cw = reinterpret_cast<const int*>(smem + p.o_snap);
+        for (int c = tid; c < k; c += blockDim.x) {
+            int t = 0;
+            for (int w = 0; w < p.NA; ++w) t += cw[w * k + c];
+            p.fcnt[(size_t)blockIdx.x * k + c] = (double)t;
+        }
     }
     if (tid == 0) {
         if (p.fv_part != nullptr) {
@@ -827,6 +902,14 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
     p.fcnt = h->part + (size_t)nslots * kd;
     p.fv_part = a.fv_out ? h->part + (size_t)nslots * kd + (size_t)grid * a.k : nullptr;
 
+    static const bool dbg_on = getenv("HK_TC_DEBUG") != nullptr;
+    unsigned long long* dbg = nullptr;
+    if (dbg_on) {
+        HK_CUDA(cudaMalloc(&dbg, (size_t)grid * 32 * 8 * sizeof(unsigned long long)));
+        HK_CUDA(cudaMemsetAsync(dbg, 0, (size_t)grid * 32 * 8 * sizeof(unsigned long long), a.stream));
+    }
+    p.dbg = dbg;
+
     char name[112];
     snprintf(name, sizeof(name), "tc<f32,d=%d,k=%d,S=%d,nbuf=%d,NA=%d,%s,%s>", a.d, a.k, pl.S, 1 << pl.nbuf_log2,
              pl.NA, sums ? "sums" : "assign", p.want_write ? "xn-write" : "xn-cached");
@@ -842,6 +925,30 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
         }
     }
     if (rc) return rc;
+    if (dbg_on) {
+        std::vector<unsigned long long> hbuf((size_t)grid * 32 * 8);
+        HK_CUDA(cudaStreamSynchronize(a.stream));
+        HK_CUDA(cudaMemcpy(hbuf.data(), dbg, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        cudaFree(dbg);
+        double acc[32][3] = {};
+        for (int b = 0; b < grid; ++b)
+            for (int w = 0; w < 32; ++w)
+                for (int j = 0; j < 3; ++j) acc[w][j] += (double)hbuf[((size_t)b * 32 + w) * 8 + j] / grid;
+        const double tiles_cta = (double)p.num_tiles / grid;
+        fprintf(stderr, "[hk tc debug] %s tiles/CTA %.0f; mean cycles per CTA (per tile in brackets)\n", name, tiles_cta);
+        fprintf(stderr, "  producer: wait-empty %.0f [%.0f]  total %.0f [%.0f]\n", acc[0][0], acc[0][0] / tiles_cta, acc[0][1],
+                acc[0][1] / tiles_cta);
+        fprintf(stderr, "  mma: wait-tempty %.0f [%.0f]  wait-full %.0f [%.0f]\n", acc[1][0], acc[1][0] / tiles_cta, acc[1][1],
+                acc[1][1] / tiles_cta);
+        for (int w = 4; w < 20; w += 5)
+            fprintf(stderr, "  E warp %2d: wait %.0f [%.0f per own tile]  tmem+scan %.0f [%.0f]  label+publish %.0f [%.0f]\n", w,
+                    acc[w][0], acc[w][0] / (tiles_cta / 4), acc[w][1], acc[w][1] / (tiles_cta / 4), acc[w][2],
+                    acc[w][2] / (tiles_cta / 4));
+        const double an = tiles_cta / (p.NA / 4);
+        for (int w = 20; w < 20 + p.NA; w += 3)
+            fprintf(stderr, "  A warp %2d: wait %.0f [%.0f per own tile]  rows %.0f [%.0f]  flush %.0f [%.0f]\n", w, acc[w][0],
+                    acc[w][0] / an, acc[w][1], acc[w][1] / an, acc[w][2], acc[w][2] / an);
+    }
     if (sums) {
         const int len = a.k * (a.d + 1);
         reduce_tc_kernel<<<(len + 255) / 256, 256, 0, a.stream>>>(p.fsum, p.fcnt, nslots, grid, a.k, a.d, a.partials,
