@@ -86,8 +86,8 @@ __host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sum
     o += (size_t)S * TM * d * 4;
     L.B = o;
     o += up((size_t)nk * d * 4, 1024);
-    L.Aext = o;
-    o += (size_t)TM * 128;
+    L.Aext = o;  // eight identical rows (1,1,1,0..): the descriptor's 8-row group stride is 0
+    o += 1024;
     L.Bext = o;
     o += up((size_t)nk * 128, 1024);
     L.cn = o;
@@ -96,10 +96,10 @@ __host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sum
     if (sums) o += up((size_t)NA * (k + 1) * d * 4, 16);
     L.lab = o;  // per stage: 128 labels (u16)
     if (sums) o += (size_t)S * TM * 2;
-    L.cnt = o;  // per-CTA cluster counts (int)
-    if (sums) o += up((size_t)k * 4, 16);
-    L.snap = o;  // per accumulator warp: counts at its last flush
-    if (sums) o += up((size_t)NA * k * 4, 16);
+    L.cnt = o;  // private cluster counts of the 16 epilogue warps (int)
+    if (sums) o += up((size_t)E_WARPS * k * 4, 16);
+    L.snap = o;  // per stage and lane quarter: largest label multiplicity among the 32 rows
+    if (sums) o += up((size_t)S * 4 * 4, 16);
     L.bars = o;
     o += 8 * 80;  // mbarriers
     L.misc = o;
@@ -251,6 +251,16 @@ __device__ __forceinline__ float min32(const uint32_t* a) {
     return fminf(fminf(m0, m1), fminf(m2, m3));
 }
 
+// K-major SWIZZLE_128B descriptor whose 8-row groups all alias the same 1 KB (stride byte offset 0)
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_bcast(uint32_t smem_addr) {
+    uint64_t dsc = 0;
+    dsc |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    dsc |= (uint64_t)1 << 16;
+    dsc |= (uint64_t)1 << 46;
+    dsc |= (uint64_t)2 << 61;
+    return dsc;
+}
+
 enum { XN_COMPUTE = 0, XN_WRITE = 1, XN_READ = 2 };
 
 // SUMS: accumulate per-cluster sums (adds the accumulator warps); FQL2 = log2(d/4): lanes per row in the
@@ -320,19 +330,17 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         *reinterpret_cast<float4*>(smem + p.o_B + sw128_off(nk, j, f)) = v;
     }
     // seed operands: A_ext[r] = (1,1,1,0,...), B_ext[j] = three exact TF32 pieces of |c_j|^2
-    for (int e = tid; e < TM * 8; e += blockDim.x) {
+    for (int e = tid; e < 8 * 8; e += blockDim.x) {
         const int r = e >> 3, ch = e & 7;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ch == 0) v = make_float4(1.f, 1.f, 1.f, 0.f);
-        *reinterpret_cast<float4*>(smem + p.o_Aext + sw128_off(TM, r, ch << 2)) = v;
+        *reinterpret_cast<float4*>(smem + p.o_Aext + sw128_off(8, r, ch << 2)) = v;
     }
     if (SUMS) {
         float* accz = reinterpret_cast<float*>(smem + p.o_acc);
         for (int i = tid; i < p.NA * (k + 1) * d; i += blockDim.x) accz[i] = 0.f;
         int* cz = reinterpret_cast<int*>(smem + p.o_cnt);
-        for (int i = tid; i < k; i += blockDim.x) cz[i] = 0;
-        int* sz = reinterpret_cast<int*>(smem + p.o_snap);
-        for (int i = tid; i < p.NA * k; i += blockDim.x) sz[i] = 0;
+        for (int i = tid; i < E_WARPS * k; i += blockDim.x) cz[i] = 0;
     }
     __syncthreads();
     for (int j = tid; j < nk; j += blockDim.x) {
@@ -400,7 +408,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(TM, nk);
-            const uint64_t aext_d = umma_desc_k_sw128(sbase + p.o_Aext);
+            const uint64_t aext_d = umma_desc_k_sw128_bcast(sbase + p.o_Aext);
             const uint64_t bext_d = umma_desc_k_sw128(sbase + p.o_Bext);
             int s = 0, b = 0;
             uint32_t ph = 0, bph = 0;
@@ -453,6 +461,8 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         const float beta2 = 2.f * 1.05f * 0.001953125f;
         const float gam = (float)(d + 3) * 1.1920929e-7f;
+        const uint32_t a_ecnt = sbase + p.o_cnt + (uint32_t)we * (uint32_t)(k * 4);
+        const uint32_t a_mmax = sbase + p.o_snap;
         double fv_acc = 0.0;
         int s = r % S;
         uint32_t ph = (uint32_t)((r / S) & 1);
@@ -553,6 +563,18 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             if (SUMS) {
                 // hand the labels to the accumulator warp of this lane quarter (rows past the end carry label k)
                 sts_u16(a_lab + s * (TM * 2) + row * 2, (uint32_t)lab);
+                {
+                    // rows per label among these 32 rows: private per-warp cluster counts (leaders touch distinct
+                    // addresses) and, for the accumulator warp, the largest multiplicity
+                    const unsigned peers = __match_any_sync(0xffffffffu, lab);
+                    const int mult = __popc(peers);
+                    if (lane == __ffs(peers) - 1 && lab < k) {
+                        const uint32_t ca = a_ecnt + (uint32_t)lab * 4;
+                        sts_s32(ca, lds_s32(ca) + mult);
+                    }
+                    const int mm = __reduce_max_sync(0xffffffffu, mult);
+                    if (lane == 0) sts_s32(a_mmax + (uint32_t)(s * 4 + q) * 4, mm);
+                }
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive_a(b_lfull + s * 8);
@@ -597,20 +619,20 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         const int g = lane >> FQL2;           // row slot inside a step
         const int fq = lane & (FQ - 1);
         const uint32_t kboff = (uint32_t)((fq >> 3) * TM * 128);
-        const uint32_t acc_w = sbase + p.o_acc + (uint32_t)a * (uint32_t)((k + 1) * d * 4);
-        const uint32_t acc_l = acc_w + fq * 16;
         const uint32_t rowbytes = (uint32_t)d * 4;
-        const uint32_t a_cntw = sbase + p.o_snap + (uint32_t)a * (uint32_t)(k * 4);  // private cluster counts
+        const uint32_t a_mmax = sbase + p.o_snap;
+        int run_max = 0;  // upper bound on the fp32 adds any accumulator row has taken since the last flush
+        const uint32_t acc_w = sbase + p.o_acc + (uint32_t)a * (uint32_t)(k + 1) * rowbytes;
+        const uint32_t acc_l = acc_w + fq * 16;
         double* gslot = p.fsum + ((size_t)blockIdx.x * p.NA + a) * (size_t)(k * d);
         bool first_flush = true;
-        int run_max = 0;  // upper bound on the rows any one accumulator row has taken since the last flush
 
         auto flush = [&]() {
-            // widen the private fp32 sums into this warp's fp64 slot (plain read-modify-write: sole owner)
+            // widen the private fp32 sums into this warp's fp64 slot (plain read-modify-write: sole owner), clear
             const int nq = (k * d) >> 2;
             for (int e = lane; e < nq; e += 32) {
                 const float4 v = lds_f4(acc_w + e * 16);
-                sts_f4(acc_w + e * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+                sts_f4_nc(acc_w + e * 16, make_float4(0.f, 0.f, 0.f, 0.f));
                 double2* gp = reinterpret_cast<double2*>(gslot + (size_t)e * 4);
                 double2 lo = make_double2(0.0, 0.0), hi = make_double2(0.0, 0.0);
                 if (!first_flush) {
@@ -638,17 +660,6 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             if (p.dbg) t1 = clock64();
             const uint32_t xq = a_stages + s * stage_bytes + kboff + (uint32_t)(q * 32 * 128);
             const uint32_t mylab = lds_u16(a_lab + s * (TM * 2) + (q * 32 + lane) * 2);
-            {
-                // rows per label among these 32 rows: private per-warp cluster counts (leaders hit distinct
-                // addresses) and the bound on fp32 adds per accumulator row since the last flush
-                const unsigned peers = __match_any_sync(0xffffffffu, mylab);
-                const int mult = __popc(peers);
-                if (lane == __ffs(peers) - 1 && mylab < (uint32_t)k) {
-                    const uint32_t ca = a_cntw + mylab * 4;
-                    sts_s32(ca, lds_s32(ca) + mult);
-                }
-                run_max += __reduce_max_sync(0xffffffffu, mult);
-            }
             // label collisions inside a step (rows that would hit the same accumulator row), for all steps
             unsigned coll = 0;
             if (RPI > 1) {
@@ -657,6 +668,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 for (int x = 1; x < RPI; ++x) c |= (__shfl_xor_sync(0xffffffffu, mylab, x) == mylab);
                 coll = __ballot_sync(0xffffffffu, c);
             }
+            run_max += lds_s32(a_mmax + (uint32_t)(s * 4 + q) * 4);
             constexpr int BATCH = NIT < 8 ? NIT : 8;
 #pragma unroll 1
             for (int it0 = 0; it0 < NIT; it0 += BATCH) {
@@ -671,29 +683,42 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                     aa[j] = acc_l + l * rowbytes;
                     xr[j] = lds_f4(xq + ((uint32_t)(rl << 7) | ((uint32_t)((rl ^ fq) & 7) << 4)));
                 }
+                const unsigned cb = RPI > 1 ? ((coll >> (it0 * RPI)) & (BATCH * RPI >= 32 ? 0xffffffffu : ((1u << (BATCH * RPI)) - 1u))) : 0u;
+                if (cb == 0u) {
+                    // common case, straight line: no two rows of any step share a label
 #pragma unroll
-                for (int j = 0; j < BATCH; ++j) {
-                    if (RPI > 1 && ((coll >> ((it0 + j) * RPI)) & ((1u << RPI) - 1u)) != 0u) {
-                        // two rows of this step share a label: one row at a time
-#pragma unroll
-                        for (int gg = 0; gg < RPI; ++gg) {
-                            if (g == gg) {
-                                float4 v = lds_f4(aa[j]);
-                                v.x += xr[j].x;
-                                v.y += xr[j].y;
-                                v.z += xr[j].z;
-                                v.w += xr[j].w;
-                                sts_f4_nc(aa[j], v);
-                            }
-                            __syncwarp();
-                        }
-                    } else {
+                    for (int j = 0; j < BATCH; ++j) {
                         float4 v = lds_f4(aa[j]);
                         v.x += xr[j].x;
                         v.y += xr[j].y;
                         v.z += xr[j].z;
                         v.w += xr[j].w;
                         sts_f4_nc(aa[j], v);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < BATCH; ++j) {
+                        // pick step j of the batch without dynamic register indexing
+                        float4 xj = xr[0];
+                        uint32_t aj = aa[0];
+#pragma unroll
+                        for (int t = 1; t < BATCH; ++t)
+                            if (j == t) {
+                                xj = xr[t];
+                                aj = aa[t];
+                            }
+#pragma unroll 1
+                        for (int gg = 0; gg < RPI; ++gg) {  // one row slot at a time: rows of a step may collide
+                            if (g == gg) {
+                                float4 v = lds_f4(aj);
+                                v.x += xj.x;
+                                v.y += xj.y;
+                                v.z += xj.z;
+                                v.w += xj.w;
+                                sts_f4_nc(aj, v);
+                            }
+                            __syncwarp();
+                        }
                     }
                 }
             }
@@ -731,10 +756,10 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
     if (SUMS) {
-        const int* cw = reinterpret_cast<const int*>(smem + p.o_snap);
+        const int* ce = reinterpret_cast<const int*>(smem + p.o_cnt);
         for (int c = tid; c < k; c += blockDim.x) {
             int t = 0;
-            for (int w = 0; w < p.NA; ++w) t += cw[w * k + c];
+            for (int w = 0; w < E_WARPS; ++w) t += ce[w * k + c];
             p.fcnt[(size_t)blockIdx.x * k + c] = (double)t;
         }
     }
@@ -785,8 +810,8 @@ TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
     pl.fql2 = d == 32 ? 3 : (d == 64 ? 4 : 5);
     // private fp32 accumulators: 8 warps when they fit in ~72 KB, else 4
     pl.NA = 8;
-    if ((size_t)8 * (k + 1) * d * 4 > 72 * 1024) pl.NA = 4;
-    if (sums && (size_t)pl.NA * (k + 1) * d * 4 > 96 * 1024) return pl;
+    if ((size_t)8 * (k + 1) * d * 4 > 80 * 1024) pl.NA = 4;
+    if (sums && (size_t)pl.NA * (k + 1) * d * 4 > 100 * 1024) return pl;
     // TMEM accumulator buffers: power of two, nbuf * nk <= 512
     int nb = 512 / pl.nk;
     pl.nbuf_log2 = nb >= 8 ? 3 : (nb >= 4 ? 2 : 1);
@@ -896,11 +921,11 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
     if (grid > p.num_tiles) grid = p.num_tiles;
     const int nslots = grid * pl.NA;
     const size_t kd = (size_t)a.k * a.d;
-    rc = ensure_part(h, ((size_t)nslots * kd + (size_t)grid * a.k + grid) * sizeof(double));
+    rc = ensure_part(h, ((size_t)nslots * kd + (size_t)nslots * a.k + grid) * sizeof(double));
     if (rc) return rc;
     p.fsum = sums ? h->part : nullptr;
     p.fcnt = h->part + (size_t)nslots * kd;
-    p.fv_part = a.fv_out ? h->part + (size_t)nslots * kd + (size_t)grid * a.k : nullptr;
+    p.fv_part = a.fv_out ? h->part + (size_t)nslots * kd + (size_t)nslots * a.k : nullptr;
 
     static const bool dbg_on = getenv("HK_TC_DEBUG") != nullptr;
     unsigned long long* dbg = nullptr;
