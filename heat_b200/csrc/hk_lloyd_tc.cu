@@ -101,7 +101,7 @@ __host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sum
     L.snap = o;  // per stage and lane quarter: largest label multiplicity among the 32 rows
     if (sums) o += up((size_t)S * 4 * 4, 16);
     L.bars = o;
-    o += 8 * 80;  // mbarriers
+    o += 8 * 96;  // mbarriers
     L.misc = o;
     o += 512;
     L.total = o + 1024;  // slack for manual 1024-byte alignment of the base
@@ -280,12 +280,13 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     const uint32_t a_B = sbase + p.o_B;
     const uint32_t a_lab = sbase + p.o_lab;
     float* cn = reinterpret_cast<float*>(smem + p.o_cn);
-    // mbarriers: full[S] | empty[S] | lfull[S] | tfull[NBUF] | tempty[NBUF]   (16 slots per array)
+    // mbarriers: full[S] | empty[S] | lfull[S] | tfull[NBUF] | tempty[NBUF] | mfull[S]   (16 slots per array)
     const uint32_t b_full = sbase + p.o_bars;
     const uint32_t b_empty = b_full + 16 * 8;
     const uint32_t b_lfull = b_full + 32 * 8;
     const uint32_t b_tfull = b_full + 48 * 8;
     const uint32_t b_tempty = b_full + 64 * 8;
+    const uint32_t b_mfull = b_full + 80 * 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.o_misc);
     float* cmax_s = reinterpret_cast<float*>(smem + p.o_misc + 16);
     int* force_exact_s = reinterpret_cast<int*>(smem + p.o_misc + 32);
@@ -305,6 +306,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + s, 1);
             mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 16 + s, 4 + (SUMS ? 4 : 0));
             mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 32 + s, 4);
+            mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 80 + s, 4);
         }
         for (int b = 0; b < NBUF; ++b) {
             mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 48 + b, 1);
@@ -498,24 +500,31 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             if (p.dbg) t1 = clock64();
             tc_fence_after();
             const uint32_t taddr = tlane + (uint32_t)(b * nk);
-            // two sweeps over the accumulator, 32 columns in registers at a time: min, then sign mask
-            float m = INFINITY;
+            // one sweep over the accumulator, 32 columns in registers at a time.  Per chunk: its minimum m_c and
+            // the mask of columns below m_c + 2E.  The chunk holding the global minimum has the right mask; the
+            // other chunks hold no candidate iff their minimum is at least 2E above it (else the row is
+            // ambiguous anyway: at least one candidate per such chunk).
+            float m_best = INFINITY, m_second = INFINITY;
+            unsigned mk_best = 0;
+            int c_best = 0;
             for (int c0 = 0; c0 < nk; c0 += 32) {
                 uint32_t a[32];
                 tmem_ld32(taddr + (uint32_t)c0, a);
                 tmem_wait_ld();
-                m = fminf(m, min32(a));
+                const float mc = min32(a);
+                const unsigned mk = below_mask32(a, mc + E2);
+                if (mc < m_best) {
+                    m_second = m_best;
+                    m_best = mc;
+                    mk_best = mk;
+                    c_best = c0;
+                } else {
+                    m_second = fminf(m_second, mc);
+                }
             }
-            const float thr = m + E2;
-            int cnt = 0, idx = 0;
-            for (int c0 = 0; c0 < nk; c0 += 32) {
-                uint32_t a[32];
-                tmem_ld32(taddr + (uint32_t)c0, a);
-                tmem_wait_ld();
-                const unsigned mk = below_mask32(a, thr);
-                cnt += __popc(mk);
-                if (mk) idx = c0 + __ffs(mk) - 1;
-            }
+            // NaN minima compare false everywhere: cnt stays != 1 and the exact path takes the row
+            const int cnt = (m_second >= m_best + E2) ? __popc(mk_best) : 2;
+            const int idx = c_best + __ffs(mk_best) - 1;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_a(b_tempty + b * 8);  // accumulator b may be overwritten
@@ -563,9 +572,11 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             if (SUMS) {
                 // hand the labels to the accumulator warp of this lane quarter (rows past the end carry label k)
                 sts_u16(a_lab + s * (TM * 2) + row * 2, (uint32_t)lab);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(b_lfull + s * 8);  // the accumulator warp can start on these rows
                 {
                     // rows per label among these 32 rows: private per-warp cluster counts (leaders touch distinct
-                    // addresses) and, for the accumulator warp, the largest multiplicity
+                    // addresses) and, for the accumulator warp's flush rule, the largest multiplicity
                     const unsigned peers = __match_any_sync(0xffffffffu, lab);
                     const int mult = __popc(peers);
                     if (lane == __ffs(peers) - 1 && lab < k) {
@@ -573,12 +584,11 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                         sts_s32(ca, lds_s32(ca) + mult);
                     }
                     const int mm = __reduce_max_sync(0xffffffffu, mult);
-                    if (lane == 0) sts_s32(a_mmax + (uint32_t)(s * 4 + q) * 4, mm);
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive_a(b_lfull + s * 8);
-                    mbar_arrive_a(b_empty + s * 8);
+                    if (lane == 0) {
+                        sts_s32(a_mmax + (uint32_t)(s * 4 + q) * 4, mm);
+                        mbar_arrive_a(b_mfull + s * 8);
+                        mbar_arrive_a(b_empty + s * 8);
+                    }
                 }
             } else {
                 __syncwarp();
@@ -668,7 +678,6 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 for (int x = 1; x < RPI; ++x) c |= (__shfl_xor_sync(0xffffffffu, mylab, x) == mylab);
                 coll = __ballot_sync(0xffffffffu, c);
             }
-            run_max += lds_s32(a_mmax + (uint32_t)(s * 4 + q) * 4);
             constexpr int BATCH = NIT < 8 ? NIT : 8;
 #pragma unroll 1
             for (int it0 = 0; it0 < NIT; it0 += BATCH) {
@@ -722,6 +731,8 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                     }
                 }
             }
+            warp_wait(b_mfull + s * 8, ph, lane);  // multiplicities of this tile published (long done by now)
+            run_max += lds_s32(a_mmax + (uint32_t)(s * 4 + q) * 4);
             __syncwarp();
             if (lane == 0) mbar_arrive_a(b_empty + s * 8);
             if (p.dbg) t2 = clock64();
