@@ -114,19 +114,6 @@ __device__ __forceinline__ float4 lds_f4(uint32_t a) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
-__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts_u4(uint32_t a, uint4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                 : "memory");
-}
-__device__ __forceinline__ void sts_f4(uint32_t a, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
-}
 // (volatile asm statements keep their relative order; the private-accumulator traffic needs no more than that)
 __device__ __forceinline__ void sts_f4_nc(uint32_t a, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
@@ -784,20 +771,37 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     }
 }
 
-// partials[c][0..d) = sum over accumulator slots, partials[c][d] = sum over CTAs of the counts (fixed order)
-__global__ void reduce_tc_kernel(const double* __restrict__ fsum, const double* __restrict__ fcnt, int nslots,
-                                 int nblocks, int k, int d, double* __restrict__ out, const int32_t* state) {
+// partials[c][0..d) = sum over accumulator slots, partials[c][d] = sum over CTAs of the counts.
+// Block = 32 outputs x 8 slot groups; every partial sum and the final 8-way combine run in a fixed order.
+__global__ void __launch_bounds__(256) reduce_tc_kernel(const double* __restrict__ fsum, const double* __restrict__ fcnt,
+                                                        int nslots, int nblocks, int k, int d,
+                                                        double* __restrict__ out, const int32_t* state) {
     if (state != nullptr && state[0] != 0) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= k * (d + 1)) return;
-    const int c = i / (d + 1), f = i - c * (d + 1);
+    __shared__ double sh[8][33];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const int len = k * (d + 1);
     double t = 0.0;
-    if (f < d) {
-        for (int b = 0; b < nslots; ++b) t += fsum[(size_t)b * k * d + (size_t)c * d + f];
-    } else {
-        for (int b = 0; b < nblocks; ++b) t += fcnt[(size_t)b * k + c];
+    if (i < len) {
+        const int c = i / (d + 1), f = i - c * (d + 1);
+        if (f < d) {
+            const int per = (nslots + 7) / 8;
+            const int b1 = min(nslots, (grp + 1) * per);
+            for (int b = grp * per; b < b1; ++b) t += fsum[(size_t)b * k * d + (size_t)c * d + f];
+        } else {
+            const int per = (nblocks + 7) / 8;
+            const int b1 = min(nblocks, (grp + 1) * per);
+            for (int b = grp * per; b < b1; ++b) t += fcnt[(size_t)b * k + c];
+        }
     }
-    out[i] = t;
+    sh[grp][lane] = t;
+    __syncthreads();
+    if (grp == 0 && i < len) {
+        double r = sh[0][lane];
+#pragma unroll
+        for (int g2 = 1; g2 < 8; ++g2) r += sh[g2][lane];
+        out[i] = r;
+    }
 }
 __global__ void reduce_scalar_tc_kernel(const double* __restrict__ v, int n, double* __restrict__ out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -987,8 +991,8 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
     }
     if (sums) {
         const int len = a.k * (a.d + 1);
-        reduce_tc_kernel<<<(len + 255) / 256, 256, 0, a.stream>>>(p.fsum, p.fcnt, nslots, grid, a.k, a.d, a.partials,
-                                                                  a.state);
+        reduce_tc_kernel<<<(len + 31) / 32, 256, 0, a.stream>>>(p.fsum, p.fcnt, nslots, grid, a.k, a.d, a.partials,
+                                                                a.state);
         HK_CUDA(cudaGetLastError());
         h->launches++;
     }

@@ -1,0 +1,137 @@
+"""Binding for a real Heat installation: route Heat's own ``KMeans`` / ``cdist`` through libhkmeans.
+
+    import heat as ht, heat_b200.integration as hki
+    hki.install()            # idempotent; hki.uninstall() restores the reference code
+    ht.cluster.KMeans(n_clusters=64, init=c0).fit(x)     # x: ht.DNDarray on a CUDA device, split=0 or None
+
+Only the hot path is replaced, and only when it applies (CUDA device, float32/float64, 2-D, split in {0, None});
+everything else falls through to the reference implementation untouched:
+
+* ``heat.cluster.KMeans.fit``            (heat/cluster/kmeans.py:105-148)  -> fused ``hk_lloyd_step`` loop
+* ``heat.cluster.KMeans._assign_to_cluster`` (heat/cluster/_kcluster.py:352-370) -> ``hk_assign``
+  (``predict`` and ``fit_predict`` go through it)
+* ``heat.spatial.distance._euclidian_fast`` (heat/spatial/distance.py:32-44) -> ``hk_cdist`` on the local blocks, which
+  accelerates ``cdist(quadratic_expansion=True)`` for every caller without touching ``_dist``'s split logic
+  (the operator plug point, distance.py:209-227).
+
+The per-iteration allreduce uses NCCL through ``torch.distributed``: the process group must map rank r of ``x.comm`` to
+the same rank (one process per GPU, ``cuda:{rank % device_count}`` as in heat/core/devices.py:116-120).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import engine as _engine
+from .communication import ProcessGroupCommunication
+
+_ORIG = {}
+
+
+def _eligible(x) -> bool:
+    t = x.larray
+    return t.is_cuda and t.dtype in (torch.float32, torch.float64) and t.dim() == 2 and x.split in (None, 0)
+
+
+def _pg(x):
+    comm = ProcessGroupCommunication()
+    if x.comm.size != comm.size or x.comm.rank != comm.rank:
+        raise RuntimeError("heat_b200.integration: torch.distributed must be initialised with the same rank/size as x.comm")
+    return comm
+
+
+def install() -> bool:
+    """Patch Heat in place.  Returns False (and does nothing) when Heat is not importable."""
+    try:
+        import heat as ht
+        from heat.core.dndarray import DNDarray
+        from heat.spatial import distance as hdist
+    except Exception:
+        return False
+    if _ORIG:
+        return True
+    KM = ht.cluster.KMeans
+    _ORIG.update(fit=KM.fit, assign=KM._assign_to_cluster, efast=hdist._euclidian_fast)
+
+    def _wrap(t, gshape, dtype, split, like):
+        return DNDarray(t, gshape, dtype, split, like.device, like.comm, True)
+
+    def fit(self, x, oversampling=2, iter_multiplier=1):
+        if not isinstance(x, DNDarray) or not _eligible(x):
+            return _ORIG["fit"](self, x, oversampling, iter_multiplier)
+        self._initialize_cluster_centers(x, oversampling, iter_multiplier)  # reference code (init runs once)
+        c0 = self._cluster_centers.larray
+        if c0.dtype != x.larray.dtype:
+            return _ORIG["fit"](self, x, oversampling, iter_multiplier)  # mixed dtypes: reference path
+        xl = x.larray if x.larray.stride(1) == 1 else x.larray.contiguous()
+        dev = xl.device
+        eng = _engine.get_engine(dev)
+        distributed = x.split is not None and x.comm.size > 1
+        if distributed:
+            eng.init_comm(_pg(x))
+        eng.cache_reset()
+        c = c0.to(dev).contiguous().clone()
+        c_prev = torch.empty_like(c)
+        shift2 = torch.zeros((), dtype=c.dtype, device=dev)
+        state = torch.zeros(4, dtype=torch.int32, device=dev)
+        use_tol = self.tol is not None
+        tol_cmp = float(np.float32(self.tol)) if use_tol else 0.0
+        done, chunk = 0, (8 if use_tol else self.max_iter)
+        while done < self.max_iter:
+            todo = min(chunk, self.max_iter - done)
+            for _ in range(todo):
+                eng.lloyd_step(xl, c, c_prev, use_tol, tol_cmp, shift2, state, distributed)
+            done += todo
+            if use_tol and done < self.max_iter and int(state[0].item()):
+                break
+        self._n_iter = int(state[1].item())
+        labels = torch.empty((xl.shape[0], 1), dtype=torch.int64, device=dev)
+        eng.assign(xl, c_prev, labels)
+        self._cluster_centers = _wrap(c, tuple(c.shape), self._cluster_centers.dtype, None, x)
+        self._inertia = _wrap(shift2, (), self._cluster_centers.dtype, None, x)
+        self._labels = DNDarray(labels, (x.shape[0], 1), ht.int64, x.split, x.device, x.comm, x.balanced)
+        return self
+
+    def _assign_to_cluster(self, x, eval_functional_value=False):
+        c = self._cluster_centers.larray
+        if not _eligible(x) or c.dtype != x.larray.dtype:
+            return _ORIG["assign"](self, x, eval_functional_value)
+        xl = x.larray if x.larray.stride(1) == 1 else x.larray.contiguous()
+        dev = xl.device
+        eng = _engine.get_engine(dev)
+        labels = torch.empty((xl.shape[0], 1), dtype=torch.int64, device=dev)
+        fv = torch.zeros(1, dtype=torch.float64, device=dev) if eval_functional_value else None
+        eng.assign(xl, c.to(dev).contiguous(), labels, fv)
+        if eval_functional_value:
+            if x.split is not None and x.comm.size > 1:
+                eng.init_comm(_pg(x))
+                eng.allreduce_f64(fv)
+            self._functional_value = _wrap(fv[0].to(xl.dtype), (), x.dtype, None, x)
+        return DNDarray(labels, (x.shape[0], 1), ht.int64, x.split, x.device, x.comm, x.balanced)
+
+    def _euclidian_fast(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if not (x.is_cuda and y.is_cuda and x.dtype == y.dtype and x.dtype in (torch.float32, torch.float64)
+                and x.dim() == 2 and y.dim() == 2):
+            return _ORIG["efast"](x, y)
+        xc = x if x.stride(1) == 1 else x.contiguous()
+        yc = y if y.stride(1) == 1 else y.contiguous()
+        out = torch.empty((xc.shape[0], yc.shape[0]), dtype=x.dtype, device=x.device)
+        _engine.get_engine(x.device).cdist(xc, yc, out, quadratic_expansion=True, sqrt=True)
+        return out
+
+    KM.fit = fit
+    KM._assign_to_cluster = _assign_to_cluster
+    hdist._euclidian_fast = _euclidian_fast
+    return True
+
+
+def uninstall() -> None:
+    if not _ORIG:
+        return
+    import heat as ht
+    from heat.spatial import distance as hdist
+
+    ht.cluster.KMeans.fit = _ORIG["fit"]
+    ht.cluster.KMeans._assign_to_cluster = _ORIG["assign"]
+    hdist._euclidian_fast = _ORIG["efast"]
+    _ORIG.clear()
