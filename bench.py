@@ -354,7 +354,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=list(WORKLOADS))
-    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tc", "generic"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--n", type=int, default=None, help="override the global row count (experiments only)")

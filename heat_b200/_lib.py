@@ -11,7 +11,7 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_void_
 
 HK_F32, HK_F64 = 0, 1
 HK_LABEL_NONE, HK_LABEL_U8, HK_LABEL_I32, HK_LABEL_I64 = 0, 1, 2, 3
-HK_PATH_AUTO, HK_PATH_SIMT, HK_PATH_TC = 0, 1, 2
+HK_PATH_AUTO, HK_PATH_SIMT, HK_PATH_TC, HK_PATH_GENERIC = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhkmeans.so")

@@ -57,6 +57,7 @@ static int run_pass(Handle* h, const LloydArgs& a) {
         }
         return launch_lloyd_tc(h, a);
     }
+    if (path == HK_PATH_SIMT && row128_supported(h, a)) return launch_lloyd_row128(h, a);
     return launch_lloyd_simt(h, a);
 }
 

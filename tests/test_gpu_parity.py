@@ -18,7 +18,7 @@ DEV = torch.device("cuda", 0)
 
 
 def _paths_for(dtype):
-    return ["simt", "tc", "auto"] if dtype == torch.float32 else ["simt", "auto"]
+    return ["simt", "generic", "tc", "auto"] if dtype == torch.float32 else ["simt", "generic", "auto"]
 
 
 def _fit(name, path, sync_every=8):
@@ -44,7 +44,7 @@ def _tc_ok(x, init):
 
 
 @pytest.mark.parametrize("name", list(CASES))
-@pytest.mark.parametrize("path", ["simt", "tc", "auto"])
+@pytest.mark.parametrize("path", ["simt", "generic", "tc", "auto"])
 def test_fit_matches_reference(name, path):
     spec = CASES[name]
     x, init = make_case(name)
@@ -82,6 +82,7 @@ def test_n_iter_independent_of_sync_interval(sync_every):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("n,d,k", [(1, 1, 1), (5, 3, 2), (257, 7, 3), (1000, 32, 64), (4099, 16, 8), (777, 64, 5),
+                                   (3001, 32, 7), (130, 16, 100),
                                    (3000, 128, 40), (2049, 200, 9), (600, 5, 300), (5000, 33, 1100)])
 def test_single_step_against_oracle(dtype, n, d, k):
     """One accumulate+finalize against the oracle for awkward shapes (ragged tiles, odd d, large k)."""
@@ -133,7 +134,7 @@ def test_empty_and_strided_and_unaligned_shards():
     x = torch.randn(3000, d + 5, generator=g)
     xs = x.to(DEV)[:, 2 : 2 + d]  # row stride d+5, base offset 8 bytes: not bulk-copy eligible
     lab = torch.empty(3000, dtype=torch.int64, device=DEV)
-    for path in ("simt", "auto"):
+    for path in ("simt", "generic", "auto"):
         eng.lloyd_accumulate(xs, c, part, labels=lab, path=path)
         ref = orc.assign_to_cluster(x[:, 2 : 2 + d].contiguous(), c.cpu()).view(-1)
         par = orc.compare_labels(x[:, 2 : 2 + d].contiguous(), c.cpu(), ref, lab.cpu())
