@@ -323,7 +323,7 @@ def run_ours(args, wl):
     peak, peak_src, pk = peaks()
     achieved = alg_bytes_rank / (kern_ms_avg * 1e-3) / 1e9 if kern_ms_avg > 0 else 0.0
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": measured_traffic(args.workload, variant) if world == 1 and not args.n else None,
+            "traffic": measured_traffic(args.workload, variant) if world == 1 and not args.rows else None,
             "peak_source": peak_src, "kernel": variant, "kernel_ms_avg": kern_ms_avg,
             "algorithmic_bytes_per_launch": alg_bytes_rank,
             "kernel_share_of_step": kern_ms_avg / ms_step if ms_step > 0 else None}
@@ -357,12 +357,12 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "tc", "generic"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--n", type=int, default=None, help="override the global row count (experiments only)")
+    ap.add_argument("--rows", type=int, default=None, help="override the global row count (experiments only)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
-    if args.n:
-        wl["n"] = args.n
-        wl["desc"] += f" [n overridden to {args.n}]"
+    if args.rows:
+        wl["n"] = args.rows
+        wl["desc"] += f" [n overridden to {args.rows}]"
     if args.impl == "reference":
         run_reference(args, wl)
     else:
