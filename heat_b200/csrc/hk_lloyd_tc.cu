@@ -633,48 +633,15 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 }
                 const unsigned cb = RPI > 1 ? ((coll >> (it0 * RPI)) & (BATCH * RPI >= 32 ? 0xffffffffu : ((1u << (BATCH * RPI)) - 1u))) : 0u;
                 if (cb == 0u) {
-                    // common case: no two rows of any step share a label.  Steps go in pairs: when the labels of
-                    // step j+1 do not occur in step j the two load-add-store chains are independent and overlap
-                    // (one shared-memory round trip instead of two); otherwise they run back to back.
+                    // common case, straight line: no two rows of any step share a label
 #pragma unroll
-                    for (int j = 0; j + 1 < BATCH; j += 2) {
-                        const uint32_t other = __shfl_sync(0xffffffffu, aa[j], (fq & (RPI - 1)) << FQL2);
-                        const bool hit = other == (aa[j + 1] - fq * 16);  // `other` comes from a lane with fq == 0
-                        if (!__any_sync(0xffffffffu, hit)) {
-                            float4 v0 = lds_f4(aa[j]);
-                            float4 v1 = lds_f4(aa[j + 1]);
-                            v0.x += xr[j].x;
-                            v0.y += xr[j].y;
-                            v0.z += xr[j].z;
-                            v0.w += xr[j].w;
-                            v1.x += xr[j + 1].x;
-                            v1.y += xr[j + 1].y;
-                            v1.z += xr[j + 1].z;
-                            v1.w += xr[j + 1].w;
-                            sts_f4_nc(aa[j], v0);
-                            sts_f4_nc(aa[j + 1], v1);
-                        } else {
-                            float4 v0 = lds_f4(aa[j]);
-                            v0.x += xr[j].x;
-                            v0.y += xr[j].y;
-                            v0.z += xr[j].z;
-                            v0.w += xr[j].w;
-                            sts_f4_nc(aa[j], v0);
-                            float4 v1 = lds_f4(aa[j + 1]);
-                            v1.x += xr[j + 1].x;
-                            v1.y += xr[j + 1].y;
-                            v1.z += xr[j + 1].z;
-                            v1.w += xr[j + 1].w;
-                            sts_f4_nc(aa[j + 1], v1);
-                        }
-                    }
-                    if (BATCH & 1) {
-                        float4 v = lds_f4(aa[BATCH - 1]);
-                        v.x += xr[BATCH - 1].x;
-                        v.y += xr[BATCH - 1].y;
-                        v.z += xr[BATCH - 1].z;
-                        v.w += xr[BATCH - 1].w;
-                        sts_f4_nc(aa[BATCH - 1], v);
+                    for (int j = 0; j < BATCH; ++j) {
+                        float4 v = lds_f4(aa[j]);
+                        v.x += xr[j].x;
+                        v.y += xr[j].y;
+                        v.z += xr[j].z;
+                        v.w += xr[j].w;
+                        sts_f4_nc(aa[j], v);
                     }
                 } else {
 #pragma unroll 1
