@@ -1,0 +1,406 @@
+// Tensor-core pairwise distances (fp32, quadratic expansion) for sm_100a — BASELINE config 2
+// (X 1M x 64 vs Y 4096 x 64): the output write (4*m*n bytes) is the roofline, the contraction 2*m*n*f is three
+// times what the FP32 pipes can do in that time, so x.y^T runs on tcgen05 as 3xTF32:
+//     x.y ~= xh.yh + xl.yh + xh.yl,   xh = x with the low 13 mantissa bits cleared (what kind::tf32 reads from the
+//     raw fp32 tile), xl = x - xh (exact), error ~1e-6 * |x||y| (the reference's sgemm: ~5e-7 * |x||y|)
+// A small pre-pass writes xl / yl and the row norms; the main kernel is a warp-specialised GEMM with a fused
+// epilogue  out = sqrt(clamp(|x|^2 + |y|^2 - 2 x.y, 0, inf))  (heat/spatial/distance.py:44, 59-64):
+//   warp 0      : TMA producer — A tiles (raw X and xl, 128 rows x f) once per row tile, B slots (raw Y / yl,
+//                 128 rows x 32 features = 16 KB) through a ring
+//   warp 1      : tcgen05.mma issuer (M=128, N=128, K=8), 4 accumulator buffers of 128 columns in TMEM
+//   warps 4-11  : epilogue (thread == output row == TMEM lane): tcgen05.ld 32 columns -> distances -> swizzled
+//                 staging tile in shared memory -> TMA store (cp.async.bulk.tensor, clipped at the matrix edge)
+// Replaces cdist -> _dist -> _euclidian_fast on the local blocks (heat/spatial/distance.py:32-64, 409-414).
+#include <math.h>
+
+#include "hk_tma.cuh"
+
+namespace hk {
+namespace {
+
+constexpr int TM = 128;   // output rows per tile (UMMA M)
+constexpr int TN = 128;   // output columns per accumulator (UMMA N)
+constexpr int NBUF = 4;   // TMEM accumulator buffers (4 x 128 columns)
+constexpr int NSLOT = 6;  // B ring slots of 16 KB
+constexpr int EPI_WARPS = 8;
+constexpr int NTHREADS = (4 + EPI_WARPS) * 32;
+
+struct CdParams {
+    int64_t m, n;
+    int f, nkb;
+    int num_row_tiles, num_chunks;
+    const float* xn;
+    const float* yn;
+    int sqrt_flag;
+    uint32_t o_A, o_B, o_stage, o_bars;
+};
+
+// xl = x - trunc_tf32(x), row norms (ascending feature order inside each lane, then a fixed shuffle tree)
+__global__ void split_lo_kernel(const float* __restrict__ A, int64_t rows, int f, int64_t ld, float* __restrict__ lo,
+                                float* __restrict__ nrm) {
+    const int lpr = f >> 2;  // lanes per row (8, 16, 24, 32)
+    const int rpw = 32 / lpr > 0 ? 32 / lpr : 1;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int sub = lane / lpr, li = lane - sub * lpr;
+    const int64_t r = warp * rpw + sub;
+    float s = 0.f;
+    if (sub < rpw && r < rows) {
+        const float4 v = *reinterpret_cast<const float4*>(A + r * ld + (li << 2));
+        float4 l;
+        l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        *reinterpret_cast<float4*>(lo + r * f + (li << 2)) = l;
+        s = fmaf(v.x, v.x, s);
+        s = fmaf(v.y, v.y, s);
+        s = fmaf(v.z, v.z, s);
+        s = fmaf(v.w, v.w, s);
+    }
+    // reduce over the lanes of a row (lpr is 8, 16 or 32 when it divides 32; 24 lanes: one row per warp)
+    if (lpr == 24) {
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    } else {
+        for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    if (sub < rpw && r < rows && li == 0) nrm[r] = s;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+    cdist_tc_kernel(const __grid_constant__ CUtensorMap xh_map, const __grid_constant__ CUtensorMap xl_map,
+                    const __grid_constant__ CUtensorMap yh_map, const __grid_constant__ CUtensorMap yl_map,
+                    const __grid_constant__ CUtensorMap out_map, const CdParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem =
+        reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int nkb = p.nkb;
+    const uint32_t a_A = sbase + p.o_A;        // [2 parts][nkb][128 rows x 128 B]
+    const uint32_t a_B = sbase + p.o_B;        // [NSLOT][128 rows x 128 B]
+    const uint32_t a_stage = sbase + p.o_stage;  // [2][128 rows x 128 B] output staging, 128B swizzle
+    // barriers: a_full | a_empty | b_full[NSLOT] | b_empty[NSLOT] | t_full[NBUF] | t_empty[NBUF]
+    const uint32_t b_afull = sbase + p.o_bars;
+    const uint32_t b_aempty = b_afull + 8;
+    const uint32_t b_bfull = b_afull + 16;
+    const uint32_t b_bempty = b_bfull + NSLOT * 8;
+    const uint32_t b_tfull = b_bempty + NSLOT * 8;
+    const uint32_t b_tempty = b_tfull + NBUF * 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.o_bars + 256);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const uint32_t kb_bytes = TM * 128;
+    const uint32_t a_bytes = (uint32_t)(2 * nkb) * kb_bytes;
+
+    if (tid == 0) {
+        uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.o_bars);
+        mbar_init(bars + 0, 1);
+        mbar_init(bars + 1, 1);
+        for (int i = 0; i < NSLOT; ++i) {
+            mbar_init(bars + 2 + i, 1);
+            mbar_init(bars + 2 + NSLOT + i, 1);
+        }
+        for (int i = 0; i < NBUF; ++i) {
+            mbar_init(bars + 2 + 2 * NSLOT + i, 1);
+            mbar_init(bars + 2 + 2 * NSLOT + NBUF + i, 4);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&xh_map);
+        tma_prefetch_desc(&xl_map);
+        tma_prefetch_desc(&yh_map);
+        tma_prefetch_desc(&yl_map);
+        tma_prefetch_desc(&out_map);
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t aph = 0;
+            int slot = 0;
+            uint32_t sph = 0;
+            for (int rt = blockIdx.x; rt < p.num_row_tiles; rt += gridDim.x) {
+                mbar_wait_a(b_aempty, aph ^ 1);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_afull), "r"(a_bytes)
+                             : "memory");
+                for (int kb = 0; kb < nkb; ++kb) {
+                    asm volatile(
+                        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+                        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(a_A + kb * kb_bytes),
+                        "l"(&xh_map), "r"(b_afull), "r"(kb * 32), "r"(rt * TM), "l"(kEvictFirst)
+                        : "memory");
+                    asm volatile(
+                        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+                        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(a_A + (nkb + kb) * kb_bytes),
+                        "l"(&xl_map), "r"(b_afull), "r"(kb * 32), "r"(rt * TM), "l"(kEvictFirst)
+                        : "memory");
+                }
+                aph ^= 1;
+                for (int c = 0; c < p.num_chunks; ++c) {
+                    for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll
+                        for (int part = 0; part < 2; ++part) {
+                            mbar_wait_a(b_bempty + slot * 8, sph ^ 1);
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_bfull + slot * 8),
+                                         "r"(kb_bytes)
+                                         : "memory");
+                            asm volatile(
+                                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+                                " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(a_B + slot * kb_bytes),
+                                "l"(part == 0 ? &yh_map : &yl_map), "r"(b_bfull + slot * 8), "r"(kb * 32), "r"(c * TN),
+                                "l"(kEvictLast)
+                                : "memory");
+                            if (++slot == NSLOT) {
+                                slot = 0;
+                                sph ^= 1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(TM, TN);
+            uint32_t aph = 0;
+            int slot = 0;
+            uint32_t sph = 0;
+            int buf = 0;
+            uint32_t tph = 0;
+            for (int rt = blockIdx.x; rt < p.num_row_tiles; rt += gridDim.x) {
+                mbar_wait_a(b_afull, aph);
+                aph ^= 1;
+                for (int c = 0; c < p.num_chunks; ++c) {
+                    mbar_wait_a(b_tempty + buf * 8, tph ^ 1);
+                    tc_fence_after();
+                    const uint32_t dcol = tmem_base + (uint32_t)(buf * TN);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        // slot 0: raw Y block (read as yh) against xh and xl; slot 1: yl block against xh
+                        mbar_wait_a(b_bfull + slot * 8, sph);
+                        tc_fence_after();
+                        {
+                            const uint32_t bb = a_B + slot * kb_bytes;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t bd = umma_desc_k_sw128(bb + ks * 32);
+                                umma_tf32(dcol, umma_desc_k_sw128(a_A + kb * kb_bytes + ks * 32), bd, idesc,
+                                          (kb | ks) != 0 ? 1u : 0u);
+                                umma_tf32(dcol, umma_desc_k_sw128(a_A + (nkb + kb) * kb_bytes + ks * 32), bd, idesc, 1u);
+                            }
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                             b_bempty + slot * 8)
+                                         : "memory");
+                            if (++slot == NSLOT) {
+                                slot = 0;
+                                sph ^= 1;
+                            }
+                        }
+                        mbar_wait_a(b_bfull + slot * 8, sph);
+                        tc_fence_after();
+                        {
+                            const uint32_t bb = a_B + slot * kb_bytes;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_tf32(dcol, umma_desc_k_sw128(a_A + kb * kb_bytes + ks * 32),
+                                          umma_desc_k_sw128(bb + ks * 32), idesc, 1u);
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                             b_bempty + slot * 8)
+                                         : "memory");
+                            if (++slot == NSLOT) {
+                                slot = 0;
+                                sph ^= 1;
+                            }
+                        }
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                     b_tfull + buf * 8)
+                                 : "memory");
+                    if (++buf == NBUF) {
+                        buf = 0;
+                        tph ^= 1;
+                    }
+                }
+                // the A tiles may be overwritten once every MMA of this row tile has completed
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_aempty)
+                             : "memory");
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue warps =================
+        const int we = warp - 4;
+        const int q = we & 3;    // TMEM lane quarter == warp % 4
+        const int grp = we >> 2;  // two groups of four warps alternate over the column chunks
+        const int row = q * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t stage = a_stage + (uint32_t)grp * kb_bytes;
+        const uint32_t srow = stage + (uint32_t)row * 128;
+        const int bar_id = 1 + grp;
+        int lc = 0;  // chunk counter of this CTA (all row tiles)
+        for (int rt = blockIdx.x; rt < p.num_row_tiles; rt += gridDim.x) {
+            const int64_t grow = (int64_t)rt * TM + row;
+            const float xn = grow < p.m ? __ldg(p.xn + grow) : 0.f;
+            for (int c = 0; c < p.num_chunks; ++c, ++lc) {
+                if ((lc & 1) != grp) continue;
+                const int buf = lc & (NBUF - 1);
+                const uint32_t tph = (uint32_t)((lc / NBUF) & 1);
+                warp_wait(b_tfull + buf * 8, tph, lane);
+                tc_fence_after();
+#pragma unroll 1
+                for (int sl = 0; sl < TN / 32; ++sl) {
+                    uint32_t a[32];
+                    tmem_ld32(tlane + (uint32_t)(buf * TN + sl * 32), a);
+                    tmem_wait_ld();
+                    if (sl == TN / 32 - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_a(b_tempty + buf * 8);  // accumulator drained by this warp
+                    }
+                    const int col0 = c * TN + sl * 32;
+                    // the previous TMA store of this staging buffer must have finished reading it
+                    if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    named_bar_sync(bar_id, 128);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (col0 + j < p.n) yv = __ldg(reinterpret_cast<const float4*>(p.yn + col0 + j));
+                        float4 o;
+                        o.x = fmaf(-2.f, __uint_as_float(a[j + 0]), xn + yv.x);
+                        o.y = fmaf(-2.f, __uint_as_float(a[j + 1]), xn + yv.y);
+                        o.z = fmaf(-2.f, __uint_as_float(a[j + 2]), xn + yv.z);
+                        o.w = fmaf(-2.f, __uint_as_float(a[j + 3]), xn + yv.w);
+                        o.x = o.x < 0.f ? 0.f : o.x;
+                        o.y = o.y < 0.f ? 0.f : o.y;
+                        o.z = o.z < 0.f ? 0.f : o.z;
+                        o.w = o.w < 0.f ? 0.f : o.w;
+                        if (p.sqrt_flag) {
+                            o.x = sqrtf(o.x);
+                            o.y = sqrtf(o.y);
+                            o.z = sqrtf(o.z);
+                            o.w = sqrtf(o.w);
+                        }
+                        // staging tile: 128 rows x 128 B, 16-byte chunk index XOR (row & 7) (matches the store map)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)((((j >> 2) ^ (row & 7))) << 4)),
+                                     "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                                     : "memory");
+                    }
+                    fence_proxy_async();
+                    named_bar_sync(bar_id, 128);
+                    if (q == 0 && lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&out_map),
+                                     "r"(stage), "r"(col0), "r"(rt * TM)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            }
+        }
+        if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+struct CdLayout {
+    size_t A, B, stage, bars, total;
+};
+CdLayout cd_layout(int nkb) {
+    CdLayout L;
+    size_t o = 0;
+    L.A = o;
+    o += (size_t)2 * nkb * TM * 128;
+    L.B = o;
+    o += (size_t)NSLOT * TM * 128;
+    L.stage = o;
+    o += (size_t)2 * TM * 128;
+    L.bars = o;
+    o += 512;
+    L.total = o + 1024;
+    return L;
+}
+
+}  // namespace
+
+bool cdist_tc_supported(const Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n,
+                        int64_t ldy, const void* out, int64_t ldo) {
+    if (f % 32 != 0 || f < 32 || f > 128) return false;
+    if (ldx % 4 != 0 || ldy % 4 != 0 || ldo % 4 != 0 || n % 4 != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15) ||
+        (reinterpret_cast<uintptr_t>(out) & 15))
+        return false;
+    if (m >= ((int64_t)1 << 31) - TM || n >= ((int64_t)1 << 31) - TN) return false;
+    if (m < 1024 || n < 128) return false;  // small problems: the exact-FMA kernel is as good and bit-closer
+    return cd_layout(f / 32).total <= (size_t)h->smem_optin;
+}
+
+int launch_cdist_tc(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n, int64_t ldy,
+                    void* out, int64_t ldo, int sqrt_flag, cudaStream_t st) {
+    const int nkb = f / 32;
+    // scratch: xl [m x f], yl [n x f], xn [m], yn [n]
+    const size_t need = ((size_t)m * f + (size_t)n * f + (size_t)m + (size_t)n + 64) * sizeof(float);
+    int rc = ensure_part(h, need);
+    if (rc) return rc;
+    float* xl = reinterpret_cast<float*>(h->part);
+    float* yl = xl + (size_t)m * f;
+    float* xn = yl + (size_t)n * f;
+    xn = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(xn) + 15) & ~(uintptr_t)15);
+    float* yn = xn + ((m + 3) / 4) * 4;
+    {
+        const int lpr = f >> 2;
+        const int rpw = 32 / lpr > 0 ? 32 / lpr : 1;
+        const int64_t wx = (m + rpw - 1) / rpw, wy = (n + rpw - 1) / rpw;
+        split_lo_kernel<<<(unsigned)((wx * 32 + 255) / 256), 256, 0, st>>>((const float*)X, m, f, ldx, xl, xn);
+        split_lo_kernel<<<(unsigned)((wy * 32 + 255) / 256), 256, 0, st>>>((const float*)Y, n, f, ldy, yl, yn);
+        HK_CUDA(cudaGetLastError());
+        h->launches += 2;
+    }
+    CUtensorMap xh_map, xl_map, yh_map, yl_map, out_map;
+    rc = make_tensor_map_2d(&xh_map, X, 4, (uint64_t)m, (uint64_t)f, (uint64_t)ldx, 32, TM, 128);
+    if (rc) return rc;
+    rc = make_tensor_map_2d(&xl_map, xl, 4, (uint64_t)m, (uint64_t)f, (uint64_t)f, 32, TM, 128);
+    if (rc) return rc;
+    rc = make_tensor_map_2d(&yh_map, Y, 4, (uint64_t)n, (uint64_t)f, (uint64_t)ldy, 32, TN, 128);
+    if (rc) return rc;
+    rc = make_tensor_map_2d(&yl_map, yl, 4, (uint64_t)n, (uint64_t)f, (uint64_t)f, 32, TN, 128);
+    if (rc) return rc;
+    rc = make_tensor_map_2d(&out_map, out, 4, (uint64_t)m, (uint64_t)n, (uint64_t)ldo, 32, TM, 128);
+    if (rc) return rc;
+
+    const CdLayout L = cd_layout(nkb);
+    CdParams p{};
+    p.m = m;
+    p.n = n;
+    p.f = f;
+    p.nkb = nkb;
+    p.num_row_tiles = (int)((m + TM - 1) / TM);
+    p.num_chunks = (int)((n + TN - 1) / TN);
+    p.xn = xn;
+    p.yn = yn;
+    p.sqrt_flag = sqrt_flag;
+    p.o_A = (uint32_t)L.A;
+    p.o_B = (uint32_t)L.B;
+    p.o_stage = (uint32_t)L.stage;
+    p.o_bars = (uint32_t)L.bars;
+    int grid = h->num_sms;
+    if (grid > p.num_row_tiles) grid = p.num_row_tiles;
+    HK_CUDA(cudaFuncSetAttribute(cdist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    prof_begin(h, st);
+    cdist_tc_kernel<<<grid, NTHREADS, L.total, st>>>(xh_map, xl_map, yh_map, yl_map, out_map, p);
+    prof_end(h, st);
+    HK_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+}  // namespace hk
