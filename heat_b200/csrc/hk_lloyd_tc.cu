@@ -706,6 +706,15 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
     if (SUMS) {
+        // fold the NA per-warp fp64 slots of this CTA into its first slot (fixed order), so that the
+        // cross-CTA reduction reads one slot per CTA
+        const int kd = k * d;
+        double* base = p.fsum + (size_t)blockIdx.x * p.NA * (size_t)kd;
+        for (int e = tid; e < kd; e += blockDim.x) {
+            double t = base[e];
+            for (int w = 1; w < p.NA; ++w) t += base[(size_t)w * kd + e];
+            base[e] = t;
+        }
         const int* ce = reinterpret_cast<const int*>(smem + p.o_cnt);
         for (int c = tid; c < k; c += blockDim.x) {
             int t = 0;
@@ -726,7 +735,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
 // partials[c][0..d) = sum over accumulator slots, partials[c][d] = sum over CTAs of the counts.
 // Block = 32 outputs x 8 slot groups; every partial sum and the final 8-way combine run in a fixed order.
 __global__ void __launch_bounds__(256) reduce_tc_kernel(const double* __restrict__ fsum, const double* __restrict__ fcnt,
-                                                        int nslots, int nblocks, int k, int d,
+                                                        int nslots, int slot_stride, int nblocks, int k, int d,
                                                         double* __restrict__ out, const int32_t* state) {
     if (state != nullptr && state[0] != 0) return;
     __shared__ double sh[8][33];
@@ -739,7 +748,7 @@ __global__ void __launch_bounds__(256) reduce_tc_kernel(const double* __restrict
         if (f < d) {
             const int per = (nslots + 7) / 8;
             const int b1 = min(nslots, (grp + 1) * per);
-            for (int b = grp * per; b < b1; ++b) t += fsum[(size_t)b * k * d + (size_t)c * d + f];
+            for (int b = grp * per; b < b1; ++b) t += fsum[(size_t)b * slot_stride * k * d + (size_t)c * d + f];
         } else {
             const int per = (nblocks + 7) / 8;
             const int b1 = min(nblocks, (grp + 1) * per);
@@ -943,7 +952,7 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
     }
     if (sums) {
         const int len = a.k * (a.d + 1);
-        reduce_tc_kernel<<<(len + 31) / 32, 256, 0, a.stream>>>(p.fsum, p.fcnt, nslots, grid, a.k, a.d, a.partials,
+        reduce_tc_kernel<<<(len + 31) / 32, 256, 0, a.stream>>>(p.fsum, p.fcnt, grid, pl.NA, grid, a.k, a.d, a.partials,
                                                                 a.state);
         HK_CUDA(cudaGetLastError());
         h->launches++;
