@@ -17,6 +17,7 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-Xcompiler",
     "-fPIC",
+    *os.environ.get("HK_NVCC_EXTRA", "").split(),  # experiments only, e.g. -DHK_MBAR_SPIN
 ]
 
 

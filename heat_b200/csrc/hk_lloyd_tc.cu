@@ -61,7 +61,9 @@ struct TcParams {
     double* fcnt;     // [grid][k] per-CTA cluster counts
     double* fv_part;  // [grid] or nullptr
     int S;            // smem stages
-    int nbuf_log2;    // TMEM accumulator buffers = 1 << nbuf_log2
+    int nbuf;         // TMEM accumulator buffers (distance tiles in flight)
+    uint32_t acc_col; // TMEM-resident cluster sums (ACCT kernels): first column, columns per accumulator warp pair
+    uint32_t nkacc;
     int NA;           // accumulator warps (8 or 4)
     int num_tiles;
     const int32_t* state;
@@ -70,7 +72,9 @@ struct TcParams {
     int want_write;  // 1: this launch fills `bounds`
     // shared-memory layout (byte offsets from the 1024-aligned base), computed on the host
     uint32_t o_stages, o_B, o_Aext, o_Bext, o_cn, o_acc, o_lab, o_cnt, o_snap, o_bars, o_misc;
+    int ablate;               // debug only (HK_TC_ABLATE): 1 = epilogue skips the TMEM sweep, 2 = accumulators skip the sums
     unsigned long long* dbg;  // optional [grid][32 warps][8] cycle counters (HK_TC_DEBUG=1)
+    unsigned long long* tl;   // optional timeline of CTA 0: [512 local tiles][8 events] clock64 stamps
 };
 
 struct TcLayout {
@@ -79,7 +83,7 @@ struct TcLayout {
 
 __host__ inline size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-__host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sums) {
+__host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sums, bool acc_smem = true) {
     TcLayout L;
     size_t o = 0;
     L.stages = o;
@@ -93,11 +97,11 @@ __host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sum
     L.cn = o;
     o += up((size_t)nk * 4, 16);
     L.acc = o;  // NA private fp32 accumulators [k+1][d] (row k swallows the rows past the end of X)
-    if (sums) o += up((size_t)NA * (k + 1) * d * 4, 16);
+    if (sums && acc_smem) o += up((size_t)NA * (k + 1) * d * 4, 16);
     L.lab = o;  // per stage: 128 labels (u16)
     if (sums) o += (size_t)S * TM * 2;
     L.cnt = o;  // private cluster counts of the 16 epilogue warps (int)
-    if (sums) o += up((size_t)E_WARPS * k * 4, 16);
+    if (sums) o += up((size_t)E_WARPS * (2 * k + 1) * 4, 16);  // + per-tile label histograms [E_WARPS][k+1]
     L.snap = o;  // per stage and lane quarter: largest label multiplicity among the 32 rows
     if (sums) o += up((size_t)S * 4 * 4, 16);
     L.bars = o;
@@ -204,7 +208,8 @@ enum { XN_COMPUTE = 0, XN_WRITE = 1, XN_READ = 2 };
 
 // SUMS: accumulate per-cluster sums (adds the accumulator warps); FQL2 = log2(d/4): lanes per row in the
 // accumulator warps (d = 32, 64, 128 -> 3, 4, 5)
-template <bool SUMS, int FQL2>
+// ACCT: the cluster sums live in TMEM (d = 32, k <= 64): lane = feature, column = cluster, per accumulator warp
+template <bool SUMS, int FQL2, bool ACCT>
 __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 0)) * 32, 1)
     lloyd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     const uint32_t sbase = smem_u32(smem);
     const int d = p.d, k = p.k, nk = p.nk, S = p.S;
     const int nkb = d >> 5;
-    const int NBUF = 1 << p.nbuf_log2;
+    const int NBUF = p.nbuf;
     const uint32_t a_stages = sbase + p.o_stages;
     const uint32_t a_B = sbase + p.o_B;
     const uint32_t a_lab = sbase + p.o_lab;
@@ -232,7 +237,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     double* fvred = reinterpret_cast<double*>(smem + p.o_misc + 64);  // [E_WARPS]
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler: role code uses uniform registers
     const int lane = tid & 31;
     const uint32_t stage_bytes = (uint32_t)TM * d * 4;
     const int ntiles = p.num_tiles;
@@ -278,10 +283,12 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         *reinterpret_cast<float4*>(smem + p.o_Aext + sw128_off(8, r, ch << 2)) = v;
     }
     if (SUMS) {
-        float* accz = reinterpret_cast<float*>(smem + p.o_acc);
-        for (int i = tid; i < p.NA * (k + 1) * d; i += blockDim.x) accz[i] = 0.f;
+        if (!ACCT) {
+            float* accz = reinterpret_cast<float*>(smem + p.o_acc);
+            for (int i = tid; i < p.NA * (k + 1) * d; i += blockDim.x) accz[i] = 0.f;
+        }
         int* cz = reinterpret_cast<int*>(smem + p.o_cnt);
-        for (int i = tid; i < E_WARPS * k; i += blockDim.x) cz[i] = 0;
+        for (int i = tid; i < E_WARPS * (2 * k + 1); i += blockDim.x) cz[i] = 0;
     }
     __syncthreads();
     for (int j = tid; j < nk; j += blockDim.x) {
@@ -316,15 +323,21 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            long long tw = 0;
-            const long long tstart = clock64();
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const long long ta = p.dbg ? clock64() : 0;
-                mbar_wait_a(b_empty + s * 8, ph ^ 1);
-                if (p.dbg) tw += clock64() - ta;
+        // the whole warp runs the loop (convergent, so addresses and descriptors live in uniform registers);
+        // one elected lane issues
+        int s = 0;
+        uint32_t ph = 0;
+        long long tw = 0;
+        const long long tstart = p.dbg ? clock64() : 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long long ta = p.dbg ? clock64() : 0;
+            mbar_wait_a(b_empty + s * 8, ph ^ 1);
+            if (p.dbg) tw += clock64() - ta;
+            if (elect_one()) {
+                if (p.tl && blockIdx.x == 0) {
+                    const int il = (tile - blockIdx.x) / gridDim.x;
+                    if (il < 512) p.tl[il * 8 + 0] = clock64();
+                }
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_full + s * 8),
                              "r"(stage_bytes)
                              : "memory");
@@ -334,38 +347,45 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                         " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(a_stages + s * stage_bytes + kb * TM * 128),
                         "l"(&xmap), "r"(b_full + s * 8), "r"(kb * 32), "r"(tile * TM), "l"(kEvictFirst)
                         : "memory");
-                if (++s == S) {
-                    s = 0;
-                    ph ^= 1;
-                }
             }
-            if (p.dbg) {
-                unsigned long long* o = p.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;
-                o[0] = (unsigned long long)tw;
-                o[1] = (unsigned long long)(clock64() - tstart);
+            __syncwarp();
+            if (++s == S) {
+                s = 0;
+                ph ^= 1;
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(TM, nk);
-            const uint64_t aext_d = umma_desc_k_sw128_bcast(sbase + p.o_Aext);
-            const uint64_t bext_d = umma_desc_k_sw128(sbase + p.o_Bext);
-            int s = 0, b = 0;
-            uint32_t ph = 0, bph = 0;
-            long long tw1 = 0, tw2 = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const long long ta = p.dbg ? clock64() : 0;
-                mbar_wait_a(b_tempty + b * 8, bph ^ 1);
-                const long long tb = p.dbg ? clock64() : 0;
-                mbar_wait_a(b_full + s * 8, ph);
-                if (p.dbg) {
-                    tw1 += tb - ta;
-                    tw2 += clock64() - tb;
+        if (p.dbg && lane == 0) {
+            unsigned long long* o = p.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;
+            o[0] = (unsigned long long)tw;
+            o[1] = (unsigned long long)(clock64() - tstart);
+        }
+    } else if (warp == 1 || warp == 3) {
+        // ================= MMA issuers (warp 1: even local tiles, warp 3: odd) =================
+        // one issuer cannot keep up: elect + 5 UTCHMMA + commit + two barrier waits cost ~600 cycles per tile
+        const int mpar = warp == 1 ? 0 : 1;
+        // convergent warp, one elected lane issues: descriptors are computed in uniform registers, so each
+        // tcgen05.mma is a single UTCHMMA instead of a per-lane R2UR waterfall
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t idesc = umma_idesc_tf32(TM, nk);
+        const uint64_t aext_d = umma_desc_k_sw128_bcast(sbase + p.o_Aext);
+        const uint64_t bext_d = umma_desc_k_sw128(sbase + p.o_Bext);
+        int s = mpar % S, b = mpar % NBUF;
+        uint32_t ph = (uint32_t)((mpar / S) & 1), bph = (uint32_t)((mpar / NBUF) & 1);
+        long long tw1 = 0, tw2 = 0, tw3 = 0;
+        for (int tile = blockIdx.x + mpar * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
+            const long long ta = p.dbg ? clock64() : 0;
+            mbar_wait_a(b_tempty + b * 8, bph ^ 1);
+            const long long tb = p.dbg ? clock64() : 0;
+            mbar_wait_a(b_full + s * 8, ph);
+            const long long tc0 = p.dbg ? clock64() : 0;
+            tc_fence_after();
+            const uint32_t a_base = a_stages + s * stage_bytes;
+            const uint32_t dcol = tmem_u + (uint32_t)(b * nk);
+            if (elect_one()) {
+                if (p.tl && blockIdx.x == 0) {
+                    const int il = (tile - blockIdx.x) / gridDim.x;
+                    if (il < 512) p.tl[il * 8 + 1] = clock64();
                 }
-                tc_fence_after();
-                const uint32_t a_base = a_stages + s * stage_bytes;
-                const uint32_t dcol = tmem_base + (uint32_t)(b * nk);
                 umma_tf32(dcol, aext_d, bext_d, idesc, 0u);  // D = |c_j|^2
                 for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
@@ -378,20 +398,29 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                  b_tfull + b * 8)
                              : "memory");
-                if (++s == S) {
-                    s = 0;
-                    ph ^= 1;
-                }
-                if (++b == NBUF) {
-                    b = 0;
-                    bph ^= 1;
-                }
             }
+            __syncwarp();
             if (p.dbg) {
-                unsigned long long* o = p.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;
-                o[0] = (unsigned long long)tw1;
-                o[1] = (unsigned long long)tw2;
+                tw1 += tb - ta;
+                tw2 += tc0 - tb;
+                tw3 += clock64() - tc0;
             }
+            s += 2;
+            if (s >= S) {
+                s -= S;
+                ph ^= 1;
+            }
+            b += 2;
+            if (b >= NBUF) {
+                b -= NBUF;
+                bph ^= 1;
+            }
+        }
+        if (p.dbg && lane == 0) {
+            unsigned long long* o = p.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;
+            o[0] = (unsigned long long)tw1;
+            o[1] = (unsigned long long)tw2;
+            o[2] = (unsigned long long)tw3;
         }
     } else if (warp >= E_FIRST && warp < E_FIRST + E_WARPS) {
         // ================= epilogue warps =================
@@ -403,16 +432,17 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         const float beta2 = 2.f * 1.05f * 0.001953125f;
         const float gam = (float)(d + 3) * 1.1920929e-7f;
         const uint32_t a_ecnt = sbase + p.o_cnt + (uint32_t)we * (uint32_t)(k * 4);
+        const uint32_t a_hist = sbase + p.o_cnt + (uint32_t)(E_WARPS * k * 4) + (uint32_t)we * (uint32_t)((k + 1) * 4);
         const uint32_t a_mmax = sbase + p.o_snap;
         double fv_acc = 0.0;
         int s = r % S;
         uint32_t ph = (uint32_t)((r / S) & 1);
+        int b = r % NBUF;
+        uint32_t bph = (uint32_t)((r / NBUF) & 1);
         int i = r;  // local tile counter of this CTA
         long long t_wait = 0, t_work = 0, t_pub = 0, t0 = 0, t1 = 0, t2 = 0;
         for (int tile = blockIdx.x + r * gridDim.x; tile < ntiles; tile += 4 * gridDim.x, i += 4) {
             if (p.dbg) t0 = clock64();
-            const int b = i & (NBUF - 1);
-            const uint32_t bph = (uint32_t)((i >> p.nbuf_log2) & 1);
             const uint32_t xt = a_stages + s * stage_bytes;
             const int row0 = tile * TM;
             const bool active = (int64_t)row0 + row < p.n;
@@ -437,6 +467,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
 
             warp_wait(b_tfull + b * 8, bph, lane);  // accumulator ready: s_j = |c_j|^2 - 2 x.c_j (TF32)
             if (p.dbg) t1 = clock64();
+            if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && i < 512) p.tl[i * 8 + 2] = clock64();
             tc_fence_after();
             const uint32_t taddr = tlane + (uint32_t)(b * nk);
             // one sweep over the accumulator, 32 columns in registers at a time.  Per chunk: its minimum m_c and
@@ -446,7 +477,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             float m_best = INFINITY, m_second = INFINITY;
             unsigned mk_best = 0;
             int c_best = 0;
-            for (int c0 = 0; c0 < nk; c0 += 32) {
+            for (int c0 = 0; c0 < ((p.ablate & 1) ? 0 : nk); c0 += 32) {
                 uint32_t a[32];
                 tmem_ld32(taddr + (uint32_t)c0, a);
                 tmem_wait_ld();
@@ -462,8 +493,12 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 }
             }
             // NaN minima compare false everywhere: cnt stays != 1 and the exact path takes the row
-            const int cnt = (m_second >= m_best + E2) ? __popc(mk_best) : 2;
-            const int idx = c_best + __ffs(mk_best) - 1;
+            int cnt = (m_second >= m_best + E2) ? __popc(mk_best) : 2;
+            int idx = c_best + __ffs(mk_best) - 1;
+            if (p.ablate & 1) {
+                cnt = 1;
+                idx = (row * 7 + tile) & (k - 1);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_a(b_tempty + b * 8);  // accumulator b may be overwritten
@@ -513,20 +548,23 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 sts_u16(a_lab + s * (TM * 2) + row * 2, (uint32_t)lab);
                 __syncwarp();
                 if (lane == 0) mbar_arrive_a(b_lfull + s * 8);  // the accumulator warp can start on these rows
+                if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && i < 512) p.tl[i * 8 + 3] = clock64();
                 {
-                    // rows per label among these 32 rows: private per-warp cluster counts (leaders touch distinct
-                    // addresses) and, for the accumulator warp's flush rule, the largest multiplicity
-                    const unsigned peers = __match_any_sync(0xffffffffu, lab);
-                    const int mult = __popc(peers);
-                    if (lane == __ffs(peers) - 1 && lab < k) {
-                        const uint32_t ca = a_ecnt + (uint32_t)lab * 4;
-                        sts_s32(ca, lds_s32(ca) + mult);
-                    }
+                    // rows per label among these 32 rows, through a private per-warp histogram in shared memory
+                    // (integer atomics: order independent): cluster counts and, for the accumulator warp's flush
+                    // rule, the largest multiplicity
+                    const uint32_t ha = a_hist + (uint32_t)lab * 4;
+                    int old;
+                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(ha) : "memory");
+                    if (lab < k) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a_ecnt + (uint32_t)lab * 4) : "memory");
+                    const int mult = lab < k ? old + 1 : 0;
+                    sts_s32(ha, 0);
                     const int mm = __reduce_max_sync(0xffffffffu, mult);
                     if (lane == 0) {
                         sts_s32(a_mmax + (uint32_t)(s * 4 + q) * 4, mm);
                         mbar_arrive_a(b_mfull + s * 8);
                         mbar_arrive_a(b_empty + s * 8);
+                        if (p.tl && blockIdx.x == 0 && q == 0 && i < 512) p.tl[i * 8 + 4] = clock64();
                     }
                 }
             } else {
@@ -537,6 +575,11 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             while (s >= S) {
                 s -= S;
                 ph ^= 1;
+            }
+            b += 4;
+            while (b >= NBUF) {
+                b -= NBUF;
+                bph ^= 1;
             }
             if (p.dbg) {
                 const long long t3 = clock64();
@@ -556,7 +599,122 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             for (int o = 16; o > 0; o >>= 1) fv_acc += __shfl_xor_sync(0xffffffffu, fv_acc, o);
             if (lane == 0) fvred[we] = fv_acc;
         }
-    } else if (SUMS && warp >= A_FIRST) {
+    } else if (SUMS && ACCT && warp >= A_FIRST) {
+        // ================= accumulator warps, sums in TMEM =================
+        // Warp (q, res) takes the rows of lane quarter q of every second tile.  Its private [k][32] fp32 sums
+        // sit in its own TMEM lane quarter: lane = feature, column = cluster, so a row costs one 128-byte
+        // shared-memory read plus a TMEM load-add-store on one column (no shared-memory read-modify-write).
+        const int a = warp - A_FIRST;
+        const int q = a & 3;
+        const int res = a >> 2;
+        const uint32_t tacc = __shfl_sync(0xffffffffu, tmem_base, 0) + ((uint32_t)(q * 32) << 16) + p.acc_col +
+                              (uint32_t)res * p.nkacc;
+        const uint32_t a_mmax = sbase + p.o_snap;
+        int run_max = 0;
+        double* gslot = p.fsum + ((size_t)blockIdx.x * p.NA + a) * (size_t)(k * 32);
+        bool first_flush = true;
+        for (uint32_t c = 0; c < p.nkacc; c += 8) tmem_st8_zero(tacc + c);
+        tmem_wait_st();
+
+        auto flush = [&]() {
+            // widen the fp32 sums into this warp's fp64 slot (sole owner: plain read-modify-write), clear them
+            tmem_wait_st();
+            for (uint32_t c0 = 0; c0 < p.nkacc; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tacc + c0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if ((int)c0 + j < k) {
+                        double* gp = gslot + (size_t)(c0 + j) * 32 + lane;
+                        const double t = first_flush ? 0.0 : *gp;
+                        *gp = t + (double)__uint_as_float(v[j]);
+                    }
+                }
+                for (uint32_t c = 0; c < 32; c += 8) tmem_st8_zero(tacc + c0 + c);
+            }
+            tmem_wait_st();
+            first_flush = false;
+            run_max = 0;
+        };
+
+        // byte offset of this lane's feature inside a swizzled 128-byte row, for the 8 row phases
+        const uint32_t lo4 = (uint32_t)(lane & 3) << 2;
+        int s = res % S;
+        uint32_t ph = (uint32_t)((res / S) & 1);
+        long long t_wait = 0, t_work = 0, t_fl = 0, t0 = 0, t1 = 0, t2 = 0;
+        for (int tile = blockIdx.x + res * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
+            if (p.dbg) t0 = clock64();
+            warp_wait(b_full + s * 8, ph, lane);   // x tile visible
+            warp_wait(b_lfull + s * 8, ph, lane);  // labels of all four lane quarters published
+            if (p.dbg) t1 = clock64();
+            const int ila = (tile - blockIdx.x) / gridDim.x;
+            if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && ila < 512) p.tl[ila * 8 + 5] = clock64();
+            const unsigned char* xq = smem + p.o_stages + (size_t)s * stage_bytes + q * 32 * 128;
+            // rows past the end of X are zero-filled by TMA: any valid column will do for them
+            const uint32_t mylab = min(lds_u16(a_lab + s * (TM * 2) + (q * 32 + lane) * 2), (uint32_t)(k - 1));
+            // groups of four consecutive rows are updated together: find the groups with a repeated label
+            bool c = false;
+#pragma unroll
+            for (int x = 1; x < 4; ++x) c |= (__shfl_xor_sync(0xffffffffu, mylab, x) == mylab);
+            const unsigned coll = __ballot_sync(0xffffffffu, c);
+#pragma unroll
+            for (int it0 = 0; it0 < ((p.ablate & 2) ? 0 : 32); it0 += 4) {
+                float x[4];
+                uint32_t ta[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rl = it0 + j;
+                    ta[j] = tacc + __shfl_sync(0xffffffffu, mylab, rl);
+                    x[j] = *reinterpret_cast<const float*>(
+                        xq + rl * 128 + ((((uint32_t)(lane >> 2) ^ (uint32_t)(rl & 7)) << 4) | lo4));
+                }
+                tmem_wait_st();  // the previous group's stores have landed (it may share a column)
+                if (((coll >> it0) & 0xFu) == 0u) {
+                    float v0 = tmem_ld1(ta[0]), v1 = tmem_ld1(ta[1]), v2 = tmem_ld1(ta[2]), v3 = tmem_ld1(ta[3]);
+                    tmem_wait_ld4(v0, v1, v2, v3);
+                    tmem_st1(ta[0], v0 + x[0]);
+                    tmem_st1(ta[1], v1 + x[1]);
+                    tmem_st1(ta[2], v2 + x[2]);
+                    tmem_st1(ta[3], v3 + x[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float v = tmem_ld1(ta[j]);
+                        tmem_wait_ld1(v);
+                        tmem_st1(ta[j], v + x[j]);
+                        tmem_wait_st();
+                    }
+                }
+            }
+            warp_wait(b_mfull + s * 8, ph, lane);  // multiplicities of this tile published (long done by now)
+            run_max += lds_s32(a_mmax + (uint32_t)(s * 4 + q) * 4);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(b_empty + s * 8);
+            if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && ila < 512) p.tl[ila * 8 + 6] = clock64();
+            if (p.dbg) t2 = clock64();
+            if (run_max >= 72) flush();
+            if (p.dbg) {
+                const long long t3 = clock64();
+                t_wait += t1 - t0;
+                t_work += t2 - t1;
+                t_fl += t3 - t2;
+            }
+            s += 2;
+            if (s >= S) {
+                s -= S;
+                ph ^= 1;
+            }
+        }
+        flush();
+        tc_fence_before();
+        if (p.dbg && lane == 0) {
+            unsigned long long* o = p.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;
+            o[0] = (unsigned long long)t_wait;
+            o[1] = (unsigned long long)t_work;
+            o[2] = (unsigned long long)t_fl;
+        }
+    } else if (SUMS && !ACCT && warp >= A_FIRST) {
         // ================= accumulator warps =================
         const int a = warp - A_FIRST;
         const int q = a & 3;         // lane quarter of the tile this warp accumulates
@@ -607,6 +765,8 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             warp_wait(b_full + s * 8, ph, lane);   // x tile visible
             warp_wait(b_lfull + s * 8, ph, lane);  // labels of all four lane quarters published
             if (p.dbg) t1 = clock64();
+            const int ila = (tile - blockIdx.x) / gridDim.x;
+            if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && ila < 512) p.tl[ila * 8 + 5] = clock64();
             const uint32_t xq = a_stages + s * stage_bytes + kboff + (uint32_t)(q * 32 * 128);
             const uint32_t mylab = lds_u16(a_lab + s * (TM * 2) + (q * 32 + lane) * 2);
             // label collisions inside a step (rows that would hit the same accumulator row), for all steps
@@ -619,7 +779,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             }
             constexpr int BATCH = NIT < 8 ? NIT : 8;
 #pragma unroll 1
-            for (int it0 = 0; it0 < NIT; it0 += BATCH) {
+            for (int it0 = 0; it0 < ((p.ablate & 2) ? 0 : NIT); it0 += BATCH) {
                 // fetch the rows and the accumulator addresses of a batch of steps, then run the
                 // load-add-store chains (steps may share a label, so the chains stay in order)
                 float4 xr[BATCH];
@@ -632,38 +792,26 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                     xr[j] = lds_f4(xq + ((uint32_t)(rl << 7) | ((uint32_t)((rl ^ fq) & 7) << 4)));
                 }
                 const unsigned cb = RPI > 1 ? ((coll >> (it0 * RPI)) & (BATCH * RPI >= 32 ? 0xffffffffu : ((1u << (BATCH * RPI)) - 1u))) : 0u;
-                if (cb == 0u) {
-                    // common case, straight line: no two rows of any step share a label
 #pragma unroll
-                    for (int j = 0; j < BATCH; ++j) {
+                for (int j = 0; j < BATCH; ++j) {
+                    if (RPI == 1 || ((cb >> (j * RPI)) & ((1u << RPI) - 1u)) == 0u) {
+                        // common case: no two rows of this step share a label
                         float4 v = lds_f4(aa[j]);
                         v.x += xr[j].x;
                         v.y += xr[j].y;
                         v.z += xr[j].z;
                         v.w += xr[j].w;
                         sts_f4_nc(aa[j], v);
-                    }
-                } else {
+                    } else {
 #pragma unroll 1
-                    for (int j = 0; j < BATCH; ++j) {
-                        // pick step j of the batch without dynamic register indexing
-                        float4 xj = xr[0];
-                        uint32_t aj = aa[0];
-#pragma unroll
-                        for (int t = 1; t < BATCH; ++t)
-                            if (j == t) {
-                                xj = xr[t];
-                                aj = aa[t];
-                            }
-#pragma unroll 1
-                        for (int gg = 0; gg < RPI; ++gg) {  // one row slot at a time: rows of a step may collide
+                        for (int gg = 0; gg < RPI; ++gg) {  // one row slot at a time
                             if (g == gg) {
-                                float4 v = lds_f4(aj);
-                                v.x += xj.x;
-                                v.y += xj.y;
-                                v.z += xj.z;
-                                v.w += xj.w;
-                                sts_f4_nc(aj, v);
+                                float4 v = lds_f4(aa[j]);
+                                v.x += xr[j].x;
+                                v.y += xr[j].y;
+                                v.z += xr[j].z;
+                                v.w += xr[j].w;
+                                sts_f4_nc(aa[j], v);
                             }
                             __syncwarp();
                         }
@@ -674,6 +822,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             run_max += lds_s32(a_mmax + (uint32_t)(s * 4 + q) * 4);
             __syncwarp();
             if (lane == 0) mbar_arrive_a(b_empty + s * 8);
+            if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && ila < 512) p.tl[ila * 8 + 6] = clock64();
             if (p.dbg) t2 = clock64();
             // widen before any accumulator row can have taken more than ~100 fp32 adds (timing independent)
             if (run_max >= 72) flush();
@@ -773,8 +922,9 @@ __global__ void reduce_scalar_tc_kernel(const double* __restrict__ v, int n, dou
 }
 
 struct TcPlan {
-    int S, nk, NA, nbuf_log2, fql2;
-    uint32_t tmem_cols;
+    int S, nk, NA, nbuf, fql2;
+    bool acct;  // cluster sums in TMEM
+    uint32_t tmem_cols, acc_col, nkacc;
     size_t smem;
     bool ok;
 };
@@ -788,15 +938,20 @@ TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
     pl.NA = 8;
     if ((size_t)8 * (k + 1) * d * 4 > 80 * 1024) pl.NA = 4;
     if (sums && (size_t)pl.NA * (k + 1) * d * 4 > 100 * 1024) return pl;
-    // TMEM accumulator buffers: power of two, nbuf * nk <= 512
-    int nb = 512 / pl.nk;
-    pl.nbuf_log2 = nb >= 8 ? 3 : (nb >= 4 ? 2 : 1);
+    // d = 32, k <= 64: the sums of the 8 accumulator warps fit in TMEM next to the distance buffers
+    static const bool acc_tmem_opt_in = getenv("HK_TC_ACC_TMEM") != nullptr;  // experiment: slower than shared memory so far
+    pl.acct = sums && d == 32 && k <= 64 && acc_tmem_opt_in;
+    pl.nkacc = pl.acct ? (uint32_t)pl.nk : 0u;
+    // TMEM: nbuf distance buffers of nk columns (+ 2 * nkacc columns of sums), 512 columns in all
+    int nb = (512 - 2 * (int)pl.nkacc) / pl.nk;
+    pl.nbuf = nb > 8 ? 8 : nb;
+    pl.acc_col = (uint32_t)(pl.nbuf * pl.nk);
     uint32_t cols = 32;
-    while (cols < (uint32_t)((1 << pl.nbuf_log2) * pl.nk)) cols <<= 1;
+    while (cols < pl.acc_col + 2 * pl.nkacc) cols <<= 1;
     pl.tmem_cols = cols;
     const size_t budget = (size_t)h->smem_optin;
     for (int S = 12; S >= 4; --S) {
-        TcLayout L = tc_layout(d, k, pl.nk, S, pl.NA, sums);
+        TcLayout L = tc_layout(d, k, pl.nk, S, pl.NA, sums, !pl.acct);
         if (L.total <= budget) {
             pl.S = S;
             pl.smem = L.total;
@@ -807,9 +962,9 @@ TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
     return pl;
 }
 
-template <bool SUMS, int FQL2>
+template <bool SUMS, int FQL2, bool ACCT>
 int launch_inst(Handle* h, const CUtensorMap& map, TcParams& p, size_t smem, int grid, cudaStream_t st) {
-    auto kern = lloyd_tc_kernel<SUMS, FQL2>;
+    auto kern = lloyd_tc_kernel<SUMS, FQL2, ACCT>;
     HK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(h, st);
     kern<<<grid, (MISC_WARPS + E_WARPS + (SUMS ? p.NA : 0)) * 32, smem, st>>>(map, p);
@@ -851,13 +1006,15 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
     p.labels = a.labels;
     p.label_kind = a.labels ? a.label_kind : HK_LABEL_NONE;
     p.S = pl.S;
-    p.nbuf_log2 = pl.nbuf_log2;
+    p.nbuf = pl.nbuf;
+    p.acc_col = pl.acc_col;
+    p.nkacc = pl.nkacc;
     p.NA = pl.NA;
     p.num_tiles = (int)((a.n + TM - 1) / TM);
     p.state = a.state;
     p.tmem_cols = pl.tmem_cols;
     {
-        const TcLayout L = tc_layout(a.d, a.k, pl.nk, pl.S, pl.NA, sums);
+        const TcLayout L = tc_layout(a.d, a.k, pl.nk, pl.S, pl.NA, sums, !pl.acct);
         p.o_stages = (uint32_t)L.stages;
         p.o_B = (uint32_t)L.B;
         p.o_Aext = (uint32_t)L.Aext;
@@ -910,19 +1067,29 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
         HK_CUDA(cudaMemsetAsync(dbg, 0, (size_t)grid * 32 * 8 * sizeof(unsigned long long), a.stream));
     }
     p.dbg = dbg;
+    static const int ablate = getenv("HK_TC_ABLATE") ? atoi(getenv("HK_TC_ABLATE")) : 0;
+    p.ablate = ablate;
+    unsigned long long* tl = nullptr;
+    if (dbg_on) {
+        HK_CUDA(cudaMalloc(&tl, 512 * 8 * sizeof(unsigned long long)));
+        HK_CUDA(cudaMemsetAsync(tl, 0, 512 * 8 * sizeof(unsigned long long), a.stream));
+    }
+    p.tl = tl;
 
     char name[112];
-    snprintf(name, sizeof(name), "tc<f32,d=%d,k=%d,S=%d,nbuf=%d,NA=%d,%s,%s>", a.d, a.k, pl.S, 1 << pl.nbuf_log2,
-             pl.NA, sums ? "sums" : "assign", p.want_write ? "xn-write" : "xn-cached");
+    snprintf(name, sizeof(name), "tc<f32,d=%d,k=%d,S=%d,nbuf=%d,NA=%d,%s,%s>", a.d, a.k, pl.S, pl.nbuf, pl.NA,
+             sums ? (pl.acct ? "sums-tmem" : "sums") : "assign", p.want_write ? "xn-write" : "xn-cached");
     h->variant = name;
 
     if (!sums) {
-        rc = launch_inst<false, 3>(h, map, p, pl.smem, grid, a.stream);
+        rc = launch_inst<false, 3, false>(h, map, p, pl.smem, grid, a.stream);
+    } else if (pl.acct) {
+        rc = launch_inst<true, 3, true>(h, map, p, pl.smem, grid, a.stream);
     } else {
         switch (pl.fql2) {
-            case 3: rc = launch_inst<true, 3>(h, map, p, pl.smem, grid, a.stream); break;
-            case 4: rc = launch_inst<true, 4>(h, map, p, pl.smem, grid, a.stream); break;
-            default: rc = launch_inst<true, 5>(h, map, p, pl.smem, grid, a.stream); break;
+            case 3: rc = launch_inst<true, 3, false>(h, map, p, pl.smem, grid, a.stream); break;
+            case 4: rc = launch_inst<true, 4, false>(h, map, p, pl.smem, grid, a.stream); break;
+            default: rc = launch_inst<true, 5, false>(h, map, p, pl.smem, grid, a.stream); break;
         }
     }
     if (rc) return rc;
@@ -931,16 +1098,29 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
         HK_CUDA(cudaStreamSynchronize(a.stream));
         HK_CUDA(cudaMemcpy(hbuf.data(), dbg, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         cudaFree(dbg);
-        double acc[32][3] = {};
+        double acc[32][8] = {};
         for (int b = 0; b < grid; ++b)
             for (int w = 0; w < 32; ++w)
-                for (int j = 0; j < 3; ++j) acc[w][j] += (double)hbuf[((size_t)b * 32 + w) * 8 + j] / grid;
+                for (int j = 0; j < 8; ++j) acc[w][j] += (double)hbuf[((size_t)b * 32 + w) * 8 + j] / grid;
+        {
+            std::vector<unsigned long long> ht(512 * 8);
+            HK_CUDA(cudaMemcpy(ht.data(), tl, ht.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            cudaFree(tl);
+            fprintf(stderr, "[hk tc timeline] CTA 0, cycles relative to the TMA issue of each tile: full@mma tfull@E lfull Edone lfull@A Adone | issue-to-issue\n");
+            for (int il = 200; il < 216; ++il) {
+                const unsigned long long* e = &ht[il * 8];
+                if (!e[0]) continue;
+                fprintf(stderr, "  tile %3d: %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", il, (long long)(e[1] - e[0]),
+                        (long long)(e[2] - e[0]), (long long)(e[3] - e[0]), (long long)(e[4] - e[0]), (long long)(e[5] - e[0]),
+                        (long long)(e[6] - e[0]), (long long)(e[0] - ht[(il - 1) * 8]));
+            }
+        }
         const double tiles_cta = (double)p.num_tiles / grid;
         fprintf(stderr, "[hk tc debug] %s tiles/CTA %.0f; mean cycles per CTA (per tile in brackets)\n", name, tiles_cta);
         fprintf(stderr, "  producer: wait-empty %.0f [%.0f]  total %.0f [%.0f]\n", acc[0][0], acc[0][0] / tiles_cta, acc[0][1],
                 acc[0][1] / tiles_cta);
-        fprintf(stderr, "  mma: wait-tempty %.0f [%.0f]  wait-full %.0f [%.0f]\n", acc[1][0], acc[1][0] / tiles_cta, acc[1][1],
-                acc[1][1] / tiles_cta);
+        fprintf(stderr, "  mma warp 1: wait-tempty %.0f  wait-full %.0f  issue+commit %.0f (per own tile)\n",
+                acc[1][0] / (tiles_cta / 2), acc[1][1] / (tiles_cta / 2), acc[1][2] / (tiles_cta / 2));
         for (int w = 4; w < 20; w += 5)
             fprintf(stderr, "  E warp %2d: wait %.0f [%.0f per own tile]  tmem+scan %.0f [%.0f]  label+publish %.0f [%.0f]\n", w,
                     acc[w][0], acc[w][0] / (tiles_cta / 4), acc[w][1], acc[w][1] / (tiles_cta / 4), acc[w][2],

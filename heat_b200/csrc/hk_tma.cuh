@@ -34,6 +34,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// one lane of a fully converged warp (elect.sync): code around it stays warp-uniform for the compiler
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // TMEM allocation: one warp, power-of-two column count >= 32; base address lands in shared memory
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
@@ -80,6 +93,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+
+// single-column TMEM accesses of the accumulator warps (lane = this thread's TMEM lane).  No "memory" clobber:
+// they touch nothing the compiler can see, and ordinary shared-memory loads may be scheduled across them.
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+    return __uint_as_float(v);
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, float v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(__float_as_uint(v)));
+}
+__device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u));
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;"); }
+// the loaded registers are operands of the wait, so their consumers cannot be scheduled above it
+__device__ __forceinline__ void tmem_wait_ld4(float& a, float& b, float& c, float& d) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(a), "+f"(b), "+f"(c), "+f"(d));
+}
+__device__ __forceinline__ void tmem_wait_ld1(float& a) { asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(a)); }
 
 // shared-memory matrix descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart
 // (cute::UMMA::SmemDescriptor bit layout: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version [46,48),
@@ -135,6 +168,19 @@ __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+#ifdef HK_MBAR_SPIN
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -146,6 +192,7 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar),
         "r"(parity), "r"(0x989680u)
         : "memory");
+#endif
 }
 // one lane waits, then the warp is released (keeps 31 lanes out of the wait loop)
 __device__ __forceinline__ void warp_wait(uint32_t bar, uint32_t parity, int lane) {
