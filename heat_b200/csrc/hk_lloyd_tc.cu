@@ -62,8 +62,6 @@ struct TcParams {
     double* fv_part;  // [grid] or nullptr
     int S;            // smem stages
     int nbuf;         // TMEM accumulator buffers (distance tiles in flight)
-    uint32_t acc_col; // TMEM-resident cluster sums (ACCT kernels): first column, columns per accumulator warp pair
-    uint32_t nkacc;
     int NA;           // accumulator warps (8 or 4)
     int num_tiles;
     const int32_t* state;
@@ -72,7 +70,6 @@ struct TcParams {
     int want_write;  // 1: this launch fills `bounds`
     // shared-memory layout (byte offsets from the 1024-aligned base), computed on the host
     uint32_t o_stages, o_B, o_Aext, o_Bext, o_cn, o_acc, o_lab, o_cnt, o_snap, o_bars, o_misc;
-    int ablate;               // debug only (HK_TC_ABLATE): 1 = epilogue skips the TMEM sweep, 2 = accumulators skip the sums
     unsigned long long* dbg;  // optional [grid][32 warps][8] cycle counters (HK_TC_DEBUG=1)
     unsigned long long* tl;   // optional timeline of CTA 0: [512 local tiles][8 events] clock64 stamps
 };
@@ -83,7 +80,7 @@ struct TcLayout {
 
 __host__ inline size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-__host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sums, bool acc_smem = true) {
+__host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sums) {
     TcLayout L;
     size_t o = 0;
     L.stages = o;
@@ -97,7 +94,7 @@ __host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sum
     L.cn = o;
     o += up((size_t)nk * 4, 16);
     L.acc = o;  // NA private fp32 accumulators [k+1][d] (row k swallows the rows past the end of X)
-    if (sums && acc_smem) o += up((size_t)NA * (k + 1) * d * 4, 16);
+    if (sums) o += up((size_t)NA * (k + 1) * d * 4, 16);
     L.lab = o;  // per stage: 128 labels (u16)
     if (sums) o += (size_t)S * TM * 2;
     L.cnt = o;  // private cluster counts of the 16 epilogue warps (int)
@@ -206,10 +203,35 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128_bcast(uint32_t smem_addr) 
 
 enum { XN_COMPUTE = 0, XN_WRITE = 1, XN_READ = 2 };
 
+// cycle counters per role / per-tile timeline of CTA 0: compiled in with -DHK_TC_TIMING only, the hot loops of the
+// shipped kernel carry no instrumentation
+#ifdef HK_TC_TIMING
+#define TC_T(...) __VA_ARGS__
+#else
+#define TC_T(...)
+#endif
+
+// Cold path of the epilogue (rows the filter cannot decide, and the functional value): exact fp32 formula over
+// all centroids with torch.min tie/NaN semantics.  Out of line so that the hot loop stays small.
+__device__ __noinline__ int exact_label(uint32_t xt, int row, uint32_t a_B, int nk, int k, int d, float xr,
+                                        const float* cn, float* best_out) {
+    float best = INFINITY;
+    int bl = 0;
+    for (int j = 0; j < k; ++j) {
+        float d2 = exact_d2(xt, row, a_B, nk, j, d, xr, cn[j]);
+        d2 = d2 < 0.f ? 0.f : d2;
+        if (d2 < best || (d2 != d2 && best == best)) {
+            best = d2;
+            bl = j;
+        }
+    }
+    *best_out = best;
+    return bl;
+}
+
 // SUMS: accumulate per-cluster sums (adds the accumulator warps); FQL2 = log2(d/4): lanes per row in the
 // accumulator warps (d = 32, 64, 128 -> 3, 4, 5)
-// ACCT: the cluster sums live in TMEM (d = 32, k <= 64): lane = feature, column = cluster, per accumulator warp
-template <bool SUMS, int FQL2, bool ACCT>
+template <bool SUMS, int FQL2>
 __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 0)) * 32, 1)
     lloyd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -237,7 +259,8 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     double* fvred = reinterpret_cast<double*>(smem + p.o_misc + 64);  // [E_WARPS]
 
     const int tid = threadIdx.x;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler: role code uses uniform registers
+    // warp-uniform for the compiler: the role code below computes addresses and descriptors in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int lane = tid & 31;
     const uint32_t stage_bytes = (uint32_t)TM * d * 4;
     const int ntiles = p.num_tiles;
@@ -283,10 +306,8 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         *reinterpret_cast<float4*>(smem + p.o_Aext + sw128_off(8, r, ch << 2)) = v;
     }
     if (SUMS) {
-        if (!ACCT) {
-            float* accz = reinterpret_cast<float*>(smem + p.o_acc);
-            for (int i = tid; i < p.NA * (k + 1) * d; i += blockDim.x) accz[i] = 0.f;
-        }
+        float* accz = reinterpret_cast<float*>(smem + p.o_acc);
+        for (int i = tid; i < p.NA * (k + 1) * d; i += blockDim.x) accz[i] = 0.f;
         int* cz = reinterpret_cast<int*>(smem + p.o_cnt);
         for (int i = tid; i < E_WARPS * (2 * k + 1); i += blockDim.x) cz[i] = 0;
     }
@@ -320,6 +341,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     const uint32_t tmem_base = *tmem_slot;
     const float cmax = *cmax_s;
     const bool force_exact = *force_exact_s != 0;
+    TC_T(long long tw0 = 0, tw1 = 0, tw2 = 0; long long t0 = 0, t1 = 0, t2 = 0;)
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -327,17 +349,16 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         // one elected lane issues
         int s = 0;
         uint32_t ph = 0;
-        long long tw = 0;
-        const long long tstart = p.dbg ? clock64() : 0;
+        TC_T(const long long tstart = clock64();)
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const long long ta = p.dbg ? clock64() : 0;
+            TC_T(t0 = clock64();)
             mbar_wait_a(b_empty + s * 8, ph ^ 1);
-            if (p.dbg) tw += clock64() - ta;
+            TC_T(tw0 += clock64() - t0;)
             if (elect_one()) {
-                if (p.tl && blockIdx.x == 0) {
+                TC_T(if (p.tl && blockIdx.x == 0) {
                     const int il = (tile - blockIdx.x) / gridDim.x;
                     if (il < 512) p.tl[il * 8 + 0] = clock64();
-                }
+                })
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_full + s * 8),
                              "r"(stage_bytes)
                              : "memory");
@@ -354,38 +375,33 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 ph ^= 1;
             }
         }
-        if (p.dbg && lane == 0) {
-            unsigned long long* o = p.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;
-            o[0] = (unsigned long long)tw;
-            o[1] = (unsigned long long)(clock64() - tstart);
-        }
+        TC_T(tw1 = clock64() - tstart;)
     } else if (warp == 1 || warp == 3) {
         // ================= MMA issuers (warp 1: even local tiles, warp 3: odd) =================
-        // one issuer cannot keep up: elect + 5 UTCHMMA + commit + two barrier waits cost ~600 cycles per tile
-        const int mpar = warp == 1 ? 0 : 1;
         // convergent warp, one elected lane issues: descriptors are computed in uniform registers, so each
-        // tcgen05.mma is a single UTCHMMA instead of a per-lane R2UR waterfall
+        // tcgen05.mma is a single UTCHMMA instead of a per-lane R2UR waterfall.  One issuer warp is not enough:
+        // two barrier waits + elect + 5 UTCHMMA + commit cost ~600 cycles per tile.
+        const int mpar = warp == 1 ? 0 : 1;
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t idesc = umma_idesc_tf32(TM, nk);
         const uint64_t aext_d = umma_desc_k_sw128_bcast(sbase + p.o_Aext);
         const uint64_t bext_d = umma_desc_k_sw128(sbase + p.o_Bext);
         int s = mpar % S, b = mpar % NBUF;
         uint32_t ph = (uint32_t)((mpar / S) & 1), bph = (uint32_t)((mpar / NBUF) & 1);
-        long long tw1 = 0, tw2 = 0, tw3 = 0;
         for (int tile = blockIdx.x + mpar * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
-            const long long ta = p.dbg ? clock64() : 0;
+            TC_T(t0 = clock64();)
             mbar_wait_a(b_tempty + b * 8, bph ^ 1);
-            const long long tb = p.dbg ? clock64() : 0;
+            TC_T(t1 = clock64();)
             mbar_wait_a(b_full + s * 8, ph);
-            const long long tc0 = p.dbg ? clock64() : 0;
+            TC_T(t2 = clock64();)
             tc_fence_after();
             const uint32_t a_base = a_stages + s * stage_bytes;
             const uint32_t dcol = tmem_u + (uint32_t)(b * nk);
             if (elect_one()) {
-                if (p.tl && blockIdx.x == 0) {
+                TC_T(if (p.tl && blockIdx.x == 0) {
                     const int il = (tile - blockIdx.x) / gridDim.x;
                     if (il < 512) p.tl[il * 8 + 1] = clock64();
-                }
+                })
                 umma_tf32(dcol, aext_d, bext_d, idesc, 0u);  // D = |c_j|^2
                 for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
@@ -400,11 +416,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                              : "memory");
             }
             __syncwarp();
-            if (p.dbg) {
-                tw1 += tb - ta;
-                tw2 += tc0 - tb;
-                tw3 += clock64() - tc0;
-            }
+            TC_T(tw0 += t1 - t0; tw1 += t2 - t1; tw2 += clock64() - t2;)
             s += 2;
             if (s >= S) {
                 s -= S;
@@ -416,43 +428,41 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 bph ^= 1;
             }
         }
-        if (p.dbg && lane == 0) {
-            unsigned long long* o = p.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;
-            o[0] = (unsigned long long)tw1;
-            o[1] = (unsigned long long)tw2;
-            o[2] = (unsigned long long)tw3;
-        }
     } else if (warp >= E_FIRST && warp < E_FIRST + E_WARPS) {
         // ================= epilogue warps =================
         const int we = warp - E_FIRST;
         const int q = we & 3;   // TMEM lane quarter (== warp % 4)
         const int r = we >> 2;  // tile residue mod 4
         const int row = q * 32 + lane;
-        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t tlane = __shfl_sync(0xffffffffu, tmem_base, 0) + ((uint32_t)(q * 32) << 16);
         const float beta2 = 2.f * 1.05f * 0.001953125f;
         const float gam = (float)(d + 3) * 1.1920929e-7f;
+        const float cmax2 = cmax * cmax;
         const uint32_t a_ecnt = sbase + p.o_cnt + (uint32_t)we * (uint32_t)(k * 4);
         const uint32_t a_hist = sbase + p.o_cnt + (uint32_t)(E_WARPS * k * 4) + (uint32_t)we * (uint32_t)((k + 1) * 4);
-        const uint32_t a_mmax = sbase + p.o_snap;
+        const uint32_t a_mmax_q = sbase + p.o_snap + (uint32_t)q * 4;
+        const uint32_t a_lab_row = a_lab + (uint32_t)row * 2;
+        const int n32 = (int)p.n;  // n < 2^31 (tc_supported)
+        const int label_kind = p.label_kind;
+        const bool want_fv = p.fv_part != nullptr;
         double fv_acc = 0.0;
         int s = r % S;
         uint32_t ph = (uint32_t)((r / S) & 1);
         int b = r % NBUF;
         uint32_t bph = (uint32_t)((r / NBUF) & 1);
-        int i = r;  // local tile counter of this CTA
-        long long t_wait = 0, t_work = 0, t_pub = 0, t0 = 0, t1 = 0, t2 = 0;
-        for (int tile = blockIdx.x + r * gridDim.x; tile < ntiles; tile += 4 * gridDim.x, i += 4) {
-            if (p.dbg) t0 = clock64();
+        TC_T(int i = r;)
+        for (int tile = blockIdx.x + r * gridDim.x; tile < ntiles; tile += 4 * gridDim.x) {
+            TC_T(t0 = clock64();)
             const uint32_t xt = a_stages + s * stage_bytes;
-            const int row0 = tile * TM;
-            const bool active = (int64_t)row0 + row < p.n;
+            const int grow = tile * TM + row;
+            const bool active = grow < n32;
 
             float xn, xs;  // |x|^2 and |x| of this row, or upper bounds for every row of the tile
-            if (xn_mode != XN_READ) warp_wait(b_full + s * 8, ph, lane);  // x tile landed
             if (xn_mode == XN_READ) {
                 xs = __ldg(p.bounds + tile);  // the cache holds sqrt(max |x|^2)
                 xn = xs * xs;
             } else {
+                warp_wait(b_full + s * 8, ph, lane);  // x tile landed
                 xn = row_norm2(xt, row, d);
                 xs = sqrtf(xn);
                 if (xn_mode == XN_WRITE) {
@@ -463,11 +473,11 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                     if (lane == 0) atomicMax(reinterpret_cast<int*>(p.bounds) + tile, __float_as_int(wm));
                 }
             }
-            const float E2 = 2.002f * (beta2 * xs * cmax + gam * (xn + cmax * cmax));
+            const float E2 = 2.002f * (beta2 * xs * cmax + gam * (xn + cmax2));
 
             warp_wait(b_tfull + b * 8, bph, lane);  // accumulator ready: s_j = |c_j|^2 - 2 x.c_j (TF32)
-            if (p.dbg) t1 = clock64();
-            if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && i < 512) p.tl[i * 8 + 2] = clock64();
+            TC_T(t1 = clock64();
+                 if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && i < 512) p.tl[i * 8 + 2] = clock64();)
             tc_fence_after();
             const uint32_t taddr = tlane + (uint32_t)(b * nk);
             // one sweep over the accumulator, 32 columns in registers at a time.  Per chunk: its minimum m_c and
@@ -477,7 +487,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             float m_best = INFINITY, m_second = INFINITY;
             unsigned mk_best = 0;
             int c_best = 0;
-            for (int c0 = 0; c0 < ((p.ablate & 1) ? 0 : nk); c0 += 32) {
+            for (int c0 = 0; c0 < nk; c0 += 32) {
                 uint32_t a[32];
                 tmem_ld32(taddr + (uint32_t)c0, a);
                 tmem_wait_ld();
@@ -492,80 +502,53 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                     m_second = fminf(m_second, mc);
                 }
             }
-            // NaN minima compare false everywhere: cnt stays != 1 and the exact path takes the row
-            int cnt = (m_second >= m_best + E2) ? __popc(mk_best) : 2;
-            int idx = c_best + __ffs(mk_best) - 1;
-            if (p.ablate & 1) {
-                cnt = 1;
-                idx = (row * 7 + tile) & (k - 1);
-            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_a(b_tempty + b * 8);  // accumulator b may be overwritten
+            TC_T(t2 = clock64();)
 
-            if (p.dbg) t2 = clock64();
-            int lab = k;
-            if (active) {
-                float best = INFINITY;
-                bool have_best = false;
-                float xr = xn;  // exact |x|^2 of this row (the cached value is only a bound)
-                if (cnt == 1 && !force_exact && xn < INFINITY) {
-                    lab = idx;
+            // NaN minima compare false everywhere: the row is then undecided and the exact path takes it
+            const bool decided =
+                (m_second >= m_best + E2) && (__popc(mk_best) == 1) && !force_exact && (xn < INFINITY);
+            int lab = c_best + __ffs(mk_best) - 1;
+            if (!active) lab = k;
+            if (active && (!decided || want_fv)) {
+                // cold: undecided row (near-tie within the TF32 bound, NaN/Inf) or the functional value is wanted
+                mbar_wait_a(b_full + s * 8, ph);  // this thread is about to read the x tile itself
+                const float xr = row_norm2(xt, row, d);  // exact |x|^2 (the cached value is only a bound)
+                float best;
+                if (!decided) {
+                    lab = exact_label(xt, row, a_B, nk, k, d, xr, cn, &best);
                 } else {
-                    // undecided (near-tie within the TF32 bound, NaN/Inf): exact formula, torch.min semantics
-                    if (xn_mode == XN_READ) {
-                        mbar_wait_a(b_full + s * 8, ph);  // this thread is about to read the x tile itself
-                        xr = row_norm2(xt, row, d);
-                    }
-                    int bl = 0;
-                    for (int j = 0; j < k; ++j) {
-                        float d2 = exact_d2(xt, row, a_B, nk, j, d, xr, cn[j]);
-                        d2 = d2 < 0.f ? 0.f : d2;
-                        if (d2 < best || (d2 != d2 && best == best)) {
-                            best = d2;
-                            bl = j;
-                        }
-                    }
-                    lab = bl;
-                    have_best = true;
+                    best = exact_d2(xt, row, a_B, nk, lab, d, xr, cn[lab]);
+                    best = best < 0.f ? 0.f : best;
                 }
-                if (p.label_kind != HK_LABEL_NONE) store_label_tc(p.labels, p.label_kind, (int64_t)row0 + row, lab);
-                if (p.fv_part != nullptr) {
-                    if (!have_best) {
-                        if (xn_mode == XN_READ) {
-                            mbar_wait_a(b_full + s * 8, ph);
-                            xr = row_norm2(xt, row, d);
-                        }
-                        best = exact_d2(xt, row, a_B, nk, lab, d, xr, cn[lab]);
-                        best = best < 0.f ? 0.f : best;
-                    }
+                if (want_fv) {
                     const float sq = sqrtf(best);
                     fv_acc += (double)(sq * sq);
                 }
             }
+            if (label_kind != HK_LABEL_NONE && active) store_label_tc(p.labels, label_kind, (int64_t)grow, lab);
             if (SUMS) {
                 // hand the labels to the accumulator warp of this lane quarter (rows past the end carry label k)
-                sts_u16(a_lab + s * (TM * 2) + row * 2, (uint32_t)lab);
+                sts_u16(a_lab_row + s * (TM * 2), (uint32_t)lab);
                 __syncwarp();
                 if (lane == 0) mbar_arrive_a(b_lfull + s * 8);  // the accumulator warp can start on these rows
-                if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && i < 512) p.tl[i * 8 + 3] = clock64();
-                {
-                    // rows per label among these 32 rows, through a private per-warp histogram in shared memory
-                    // (integer atomics: order independent): cluster counts and, for the accumulator warp's flush
-                    // rule, the largest multiplicity
-                    const uint32_t ha = a_hist + (uint32_t)lab * 4;
-                    int old;
-                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(ha) : "memory");
-                    if (lab < k) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a_ecnt + (uint32_t)lab * 4) : "memory");
-                    const int mult = lab < k ? old + 1 : 0;
-                    sts_s32(ha, 0);
-                    const int mm = __reduce_max_sync(0xffffffffu, mult);
-                    if (lane == 0) {
-                        sts_s32(a_mmax + (uint32_t)(s * 4 + q) * 4, mm);
-                        mbar_arrive_a(b_mfull + s * 8);
-                        mbar_arrive_a(b_empty + s * 8);
-                        if (p.tl && blockIdx.x == 0 && q == 0 && i < 512) p.tl[i * 8 + 4] = clock64();
-                    }
+                TC_T(if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && i < 512) p.tl[i * 8 + 3] = clock64();)
+                // rows per label among these 32 rows, through a private per-warp histogram in shared memory
+                // (integer atomics: order independent): cluster counts and, for the accumulator warp's flush
+                // rule, the largest multiplicity
+                const uint32_t ha = a_hist + (uint32_t)lab * 4;
+                int old;
+                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(ha) : "memory");
+                if (lab < k) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a_ecnt + (uint32_t)lab * 4) : "memory");
+                const int mm = __reduce_max_sync(0xffffffffu, lab < k ? old + 1 : 0);
+                sts_s32(ha, 0);
+                if (lane == 0) {
+                    sts_s32(a_mmax_q + (uint32_t)s * 16, mm);
+                    mbar_arrive_a(b_mfull + s * 8);
+                    mbar_arrive_a(b_empty + s * 8);
+                    TC_T(if (p.tl && blockIdx.x == 0 && q == 0 && i < 512) p.tl[i * 8 + 4] = clock64();)
                 }
             } else {
                 __syncwarp();
@@ -581,140 +564,14 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 b -= NBUF;
                 bph ^= 1;
             }
-            if (p.dbg) {
-                const long long t3 = clock64();
-                t_wait += t1 - t0;
-                t_work += t2 - t1;
-                t_pub += t3 - t2;
-            }
+            TC_T(tw0 += t1 - t0; tw1 += t2 - t1; tw2 += clock64() - t2; i += 4;)
         }
-        if (p.dbg && lane == 0) {
-            unsigned long long* o = p.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;
-            o[0] = (unsigned long long)t_wait;
-            o[1] = (unsigned long long)t_work;
-            o[2] = (unsigned long long)t_pub;
-        }
-        if (p.fv_part != nullptr) {
+        if (want_fv) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) fv_acc += __shfl_xor_sync(0xffffffffu, fv_acc, o);
             if (lane == 0) fvred[we] = fv_acc;
         }
-    } else if (SUMS && ACCT && warp >= A_FIRST) {
-        // ================= accumulator warps, sums in TMEM =================
-        // Warp (q, res) takes the rows of lane quarter q of every second tile.  Its private [k][32] fp32 sums
-        // sit in its own TMEM lane quarter: lane = feature, column = cluster, so a row costs one 128-byte
-        // shared-memory read plus a TMEM load-add-store on one column (no shared-memory read-modify-write).
-        const int a = warp - A_FIRST;
-        const int q = a & 3;
-        const int res = a >> 2;
-        const uint32_t tacc = __shfl_sync(0xffffffffu, tmem_base, 0) + ((uint32_t)(q * 32) << 16) + p.acc_col +
-                              (uint32_t)res * p.nkacc;
-        const uint32_t a_mmax = sbase + p.o_snap;
-        int run_max = 0;
-        double* gslot = p.fsum + ((size_t)blockIdx.x * p.NA + a) * (size_t)(k * 32);
-        bool first_flush = true;
-        for (uint32_t c = 0; c < p.nkacc; c += 8) tmem_st8_zero(tacc + c);
-        tmem_wait_st();
-
-        auto flush = [&]() {
-            // widen the fp32 sums into this warp's fp64 slot (sole owner: plain read-modify-write), clear them
-            tmem_wait_st();
-            for (uint32_t c0 = 0; c0 < p.nkacc; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tacc + c0, v);
-                tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if ((int)c0 + j < k) {
-                        double* gp = gslot + (size_t)(c0 + j) * 32 + lane;
-                        const double t = first_flush ? 0.0 : *gp;
-                        *gp = t + (double)__uint_as_float(v[j]);
-                    }
-                }
-                for (uint32_t c = 0; c < 32; c += 8) tmem_st8_zero(tacc + c0 + c);
-            }
-            tmem_wait_st();
-            first_flush = false;
-            run_max = 0;
-        };
-
-        // byte offset of this lane's feature inside a swizzled 128-byte row, for the 8 row phases
-        const uint32_t lo4 = (uint32_t)(lane & 3) << 2;
-        int s = res % S;
-        uint32_t ph = (uint32_t)((res / S) & 1);
-        long long t_wait = 0, t_work = 0, t_fl = 0, t0 = 0, t1 = 0, t2 = 0;
-        for (int tile = blockIdx.x + res * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
-            if (p.dbg) t0 = clock64();
-            warp_wait(b_full + s * 8, ph, lane);   // x tile visible
-            warp_wait(b_lfull + s * 8, ph, lane);  // labels of all four lane quarters published
-            if (p.dbg) t1 = clock64();
-            const int ila = (tile - blockIdx.x) / gridDim.x;
-            if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && ila < 512) p.tl[ila * 8 + 5] = clock64();
-            const unsigned char* xq = smem + p.o_stages + (size_t)s * stage_bytes + q * 32 * 128;
-            // rows past the end of X are zero-filled by TMA: any valid column will do for them
-            const uint32_t mylab = min(lds_u16(a_lab + s * (TM * 2) + (q * 32 + lane) * 2), (uint32_t)(k - 1));
-            // groups of four consecutive rows are updated together: find the groups with a repeated label
-            bool c = false;
-#pragma unroll
-            for (int x = 1; x < 4; ++x) c |= (__shfl_xor_sync(0xffffffffu, mylab, x) == mylab);
-            const unsigned coll = __ballot_sync(0xffffffffu, c);
-#pragma unroll
-            for (int it0 = 0; it0 < ((p.ablate & 2) ? 0 : 32); it0 += 4) {
-                float x[4];
-                uint32_t ta[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int rl = it0 + j;
-                    ta[j] = tacc + __shfl_sync(0xffffffffu, mylab, rl);
-                    x[j] = *reinterpret_cast<const float*>(
-                        xq + rl * 128 + ((((uint32_t)(lane >> 2) ^ (uint32_t)(rl & 7)) << 4) | lo4));
-                }
-                tmem_wait_st();  // the previous group's stores have landed (it may share a column)
-                if (((coll >> it0) & 0xFu) == 0u) {
-                    float v0 = tmem_ld1(ta[0]), v1 = tmem_ld1(ta[1]), v2 = tmem_ld1(ta[2]), v3 = tmem_ld1(ta[3]);
-                    tmem_wait_ld4(v0, v1, v2, v3);
-                    tmem_st1(ta[0], v0 + x[0]);
-                    tmem_st1(ta[1], v1 + x[1]);
-                    tmem_st1(ta[2], v2 + x[2]);
-                    tmem_st1(ta[3], v3 + x[3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float v = tmem_ld1(ta[j]);
-                        tmem_wait_ld1(v);
-                        tmem_st1(ta[j], v + x[j]);
-                        tmem_wait_st();
-                    }
-                }
-            }
-            warp_wait(b_mfull + s * 8, ph, lane);  // multiplicities of this tile published (long done by now)
-            run_max += lds_s32(a_mmax + (uint32_t)(s * 4 + q) * 4);
-            __syncwarp();
-            if (lane == 0) mbar_arrive_a(b_empty + s * 8);
-            if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && ila < 512) p.tl[ila * 8 + 6] = clock64();
-            if (p.dbg) t2 = clock64();
-            if (run_max >= 72) flush();
-            if (p.dbg) {
-                const long long t3 = clock64();
-                t_wait += t1 - t0;
-                t_work += t2 - t1;
-                t_fl += t3 - t2;
-            }
-            s += 2;
-            if (s >= S) {
-                s -= S;
-                ph ^= 1;
-            }
-        }
-        flush();
-        tc_fence_before();
-        if (p.dbg && lane == 0) {
-            unsigned long long* o = p.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;
-            o[0] = (unsigned long long)t_wait;
-            o[1] = (unsigned long long)t_work;
-            o[2] = (unsigned long long)t_fl;
-        }
-    } else if (SUMS && !ACCT && warp >= A_FIRST) {
+    } else if (SUMS && warp >= A_FIRST) {
         // ================= accumulator warps =================
         const int a = warp - A_FIRST;
         const int q = a & 3;         // lane quarter of the tile this warp accumulates
@@ -723,14 +580,19 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         constexpr int FQ = 1 << FQL2;         // lanes per row (feature quads): 8, 16, 32
         constexpr int RPI = 32 / FQ;          // rows per step: 4, 2, 1
         constexpr int NIT = 32 / RPI;         // steps per 32-row quarter: 8, 16, 32
+        constexpr int BATCH = NIT < 8 ? NIT : 8;
         const int g = lane >> FQL2;           // row slot inside a step
         const int fq = lane & (FQ - 1);
-        const uint32_t kboff = (uint32_t)((fq >> 3) * TM * 128);
         const uint32_t rowbytes = (uint32_t)d * 4;
-        const uint32_t a_mmax = sbase + p.o_snap;
+        const uint32_t a_mmax_q = sbase + p.o_snap + (uint32_t)q * 4;
+        const uint32_t a_lab_lane = a_lab + (uint32_t)(q * 32 + lane) * 2;
         int run_max = 0;  // upper bound on the fp32 adds any accumulator row has taken since the last flush
         const uint32_t acc_w = sbase + p.o_acc + (uint32_t)a * (uint32_t)(k + 1) * rowbytes;
         const uint32_t acc_l = acc_w + fq * 16;
+        // this lane's 16 bytes inside row (q*32 + g) of a stage; step `it` adds it*RPI*128 bytes and, because
+        // the 128-byte swizzle depends on (row & 7), toggles the chunk index by ((it*RPI) & 7)
+        const uint32_t x_lane = (uint32_t)((fq >> 3) * TM * 128 + (q * 32 + g) * 128);
+        const uint32_t fq7 = (uint32_t)(fq & 7);
         double* gslot = p.fsum + ((size_t)blockIdx.x * p.NA + a) * (size_t)(k * d);
         bool first_flush = true;
 
@@ -759,16 +621,14 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
 
         int s = res % S;
         uint32_t ph = (uint32_t)((res / S) & 1);
-        long long t_wait = 0, t_work = 0, t_fl = 0, t0 = 0, t1 = 0, t2 = 0;
         for (int tile = blockIdx.x + res * gridDim.x; tile < ntiles; tile += nres * gridDim.x) {
-            if (p.dbg) t0 = clock64();
+            TC_T(t0 = clock64();)
             warp_wait(b_full + s * 8, ph, lane);   // x tile visible
             warp_wait(b_lfull + s * 8, ph, lane);  // labels of all four lane quarters published
-            if (p.dbg) t1 = clock64();
-            const int ila = (tile - blockIdx.x) / gridDim.x;
-            if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && ila < 512) p.tl[ila * 8 + 5] = clock64();
-            const uint32_t xq = a_stages + s * stage_bytes + kboff + (uint32_t)(q * 32 * 128);
-            const uint32_t mylab = lds_u16(a_lab + s * (TM * 2) + (q * 32 + lane) * 2);
+            TC_T(t1 = clock64(); const int ila = (tile - blockIdx.x) / gridDim.x;
+                 if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && ila < 512) p.tl[ila * 8 + 5] = clock64();)
+            const uint32_t xq = a_stages + s * stage_bytes + x_lane;
+            const uint32_t mylab = lds_u16(a_lab_lane + s * (TM * 2));
             // label collisions inside a step (rows that would hit the same accumulator row), for all steps
             unsigned coll = 0;
             if (RPI > 1) {
@@ -777,21 +637,20 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 for (int x = 1; x < RPI; ++x) c |= (__shfl_xor_sync(0xffffffffu, mylab, x) == mylab);
                 coll = __ballot_sync(0xffffffffu, c);
             }
-            constexpr int BATCH = NIT < 8 ? NIT : 8;
 #pragma unroll 1
-            for (int it0 = 0; it0 < ((p.ablate & 2) ? 0 : NIT); it0 += BATCH) {
+            for (int it0 = 0; it0 < NIT; it0 += BATCH) {
                 // fetch the rows and the accumulator addresses of a batch of steps, then run the
                 // load-add-store chains (steps may share a label, so the chains stay in order)
                 float4 xr[BATCH];
                 uint32_t aa[BATCH];
 #pragma unroll
                 for (int j = 0; j < BATCH; ++j) {
-                    const int rl = (it0 + j) * RPI + g;  // row inside the quarter
-                    const uint32_t l = __shfl_sync(0xffffffffu, mylab, rl);
+                    const int rs = (it0 + j) * RPI;  // first row of the step inside the quarter
+                    const uint32_t l = __shfl_sync(0xffffffffu, mylab, rs + g);
                     aa[j] = acc_l + l * rowbytes;
-                    xr[j] = lds_f4(xq + ((uint32_t)(rl << 7) | ((uint32_t)((rl ^ fq) & 7) << 4)));
+                    xr[j] = lds_f4(xq + (uint32_t)(rs << 7) + (((fq7 ^ (uint32_t)((rs + g) & 7))) << 4));
                 }
-                const unsigned cb = RPI > 1 ? ((coll >> (it0 * RPI)) & (BATCH * RPI >= 32 ? 0xffffffffu : ((1u << (BATCH * RPI)) - 1u))) : 0u;
+                const unsigned cb = RPI > 1 ? (coll >> (it0 * RPI)) : 0u;
 #pragma unroll
                 for (int j = 0; j < BATCH; ++j) {
                     if (RPI == 1 || ((cb >> (j * RPI)) & ((1u << RPI) - 1u)) == 0u) {
@@ -819,19 +678,14 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 }
             }
             warp_wait(b_mfull + s * 8, ph, lane);  // multiplicities of this tile published (long done by now)
-            run_max += lds_s32(a_mmax + (uint32_t)(s * 4 + q) * 4);
+            run_max += lds_s32(a_mmax_q + (uint32_t)s * 16);
             __syncwarp();
             if (lane == 0) mbar_arrive_a(b_empty + s * 8);
-            if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && ila < 512) p.tl[ila * 8 + 6] = clock64();
-            if (p.dbg) t2 = clock64();
+            TC_T(if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && ila < 512) p.tl[ila * 8 + 6] = clock64();
+                 t2 = clock64();)
             // widen before any accumulator row can have taken more than ~100 fp32 adds (timing independent)
             if (run_max >= 72) flush();
-            if (p.dbg) {
-                const long long t3 = clock64();
-                t_wait += t1 - t0;
-                t_work += t2 - t1;
-                t_fl += t3 - t2;
-            }
+            TC_T(tw0 += t1 - t0; tw1 += t2 - t1; tw2 += clock64() - t2;)
             s += nres;
             if (s >= S) {
                 s -= S;
@@ -839,13 +693,13 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             }
         }
         flush();
-        if (p.dbg && lane == 0) {
-            unsigned long long* o = p.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;
-            o[0] = (unsigned long long)t_wait;
-            o[1] = (unsigned long long)t_work;
-            o[2] = (unsigned long long)t_fl;
-        }
     }
+    TC_T(if (p.dbg && lane == 0) {
+        unsigned long long* o = p.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;
+        o[0] = (unsigned long long)tw0;
+        o[1] = (unsigned long long)tw1;
+        o[2] = (unsigned long long)tw2;
+    })
 
     // ---------------- teardown ---------------------------------------------------------------------------
     tc_fence_before();
@@ -923,8 +777,7 @@ __global__ void reduce_scalar_tc_kernel(const double* __restrict__ v, int n, dou
 
 struct TcPlan {
     int S, nk, NA, nbuf, fql2;
-    bool acct;  // cluster sums in TMEM
-    uint32_t tmem_cols, acc_col, nkacc;
+    uint32_t tmem_cols;
     size_t smem;
     bool ok;
 };
@@ -938,20 +791,15 @@ TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
     pl.NA = 8;
     if ((size_t)8 * (k + 1) * d * 4 > 80 * 1024) pl.NA = 4;
     if (sums && (size_t)pl.NA * (k + 1) * d * 4 > 100 * 1024) return pl;
-    // d = 32, k <= 64: the sums of the 8 accumulator warps fit in TMEM next to the distance buffers
-    static const bool acc_tmem_opt_in = getenv("HK_TC_ACC_TMEM") != nullptr;  // experiment: slower than shared memory so far
-    pl.acct = sums && d == 32 && k <= 64 && acc_tmem_opt_in;
-    pl.nkacc = pl.acct ? (uint32_t)pl.nk : 0u;
-    // TMEM: nbuf distance buffers of nk columns (+ 2 * nkacc columns of sums), 512 columns in all
-    int nb = (512 - 2 * (int)pl.nkacc) / pl.nk;
+    // TMEM: nbuf distance buffers of nk columns each (at most 8, 512 columns in all)
+    int nb = 512 / pl.nk;
     pl.nbuf = nb > 8 ? 8 : nb;
-    pl.acc_col = (uint32_t)(pl.nbuf * pl.nk);
     uint32_t cols = 32;
-    while (cols < pl.acc_col + 2 * pl.nkacc) cols <<= 1;
+    while (cols < (uint32_t)(pl.nbuf * pl.nk)) cols <<= 1;
     pl.tmem_cols = cols;
     const size_t budget = (size_t)h->smem_optin;
     for (int S = 12; S >= 4; --S) {
-        TcLayout L = tc_layout(d, k, pl.nk, S, pl.NA, sums, !pl.acct);
+        TcLayout L = tc_layout(d, k, pl.nk, S, pl.NA, sums);
         if (L.total <= budget) {
             pl.S = S;
             pl.smem = L.total;
@@ -962,9 +810,9 @@ TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
     return pl;
 }
 
-template <bool SUMS, int FQL2, bool ACCT>
+template <bool SUMS, int FQL2>
 int launch_inst(Handle* h, const CUtensorMap& map, TcParams& p, size_t smem, int grid, cudaStream_t st) {
-    auto kern = lloyd_tc_kernel<SUMS, FQL2, ACCT>;
+    auto kern = lloyd_tc_kernel<SUMS, FQL2>;
     HK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(h, st);
     kern<<<grid, (MISC_WARPS + E_WARPS + (SUMS ? p.NA : 0)) * 32, smem, st>>>(map, p);
@@ -1007,14 +855,12 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
     p.label_kind = a.labels ? a.label_kind : HK_LABEL_NONE;
     p.S = pl.S;
     p.nbuf = pl.nbuf;
-    p.acc_col = pl.acc_col;
-    p.nkacc = pl.nkacc;
     p.NA = pl.NA;
     p.num_tiles = (int)((a.n + TM - 1) / TM);
     p.state = a.state;
     p.tmem_cols = pl.tmem_cols;
     {
-        const TcLayout L = tc_layout(a.d, a.k, pl.nk, pl.S, pl.NA, sums, !pl.acct);
+        const TcLayout L = tc_layout(a.d, a.k, pl.nk, pl.S, pl.NA, sums);
         p.o_stages = (uint32_t)L.stages;
         p.o_B = (uint32_t)L.B;
         p.o_Aext = (uint32_t)L.Aext;
@@ -1060,15 +906,17 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
     p.fcnt = h->part + (size_t)nslots * kd;
     p.fv_part = a.fv_out ? h->part + (size_t)nslots * kd + (size_t)nslots * a.k : nullptr;
 
-    static const bool dbg_on = getenv("HK_TC_DEBUG") != nullptr;
+#ifdef HK_TC_TIMING
+    static const bool dbg_on = getenv("HK_TC_DEBUG") != nullptr;  // role timing needs a -DHK_TC_TIMING build
+#else
+    const bool dbg_on = false;
+#endif
     unsigned long long* dbg = nullptr;
     if (dbg_on) {
         HK_CUDA(cudaMalloc(&dbg, (size_t)grid * 32 * 8 * sizeof(unsigned long long)));
         HK_CUDA(cudaMemsetAsync(dbg, 0, (size_t)grid * 32 * 8 * sizeof(unsigned long long), a.stream));
     }
     p.dbg = dbg;
-    static const int ablate = getenv("HK_TC_ABLATE") ? atoi(getenv("HK_TC_ABLATE")) : 0;
-    p.ablate = ablate;
     unsigned long long* tl = nullptr;
     if (dbg_on) {
         HK_CUDA(cudaMalloc(&tl, 512 * 8 * sizeof(unsigned long long)));
@@ -1078,18 +926,16 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
 
     char name[112];
     snprintf(name, sizeof(name), "tc<f32,d=%d,k=%d,S=%d,nbuf=%d,NA=%d,%s,%s>", a.d, a.k, pl.S, pl.nbuf, pl.NA,
-             sums ? (pl.acct ? "sums-tmem" : "sums") : "assign", p.want_write ? "xn-write" : "xn-cached");
+             sums ? "sums" : "assign", p.want_write ? "xn-write" : "xn-cached");
     h->variant = name;
 
     if (!sums) {
-        rc = launch_inst<false, 3, false>(h, map, p, pl.smem, grid, a.stream);
-    } else if (pl.acct) {
-        rc = launch_inst<true, 3, true>(h, map, p, pl.smem, grid, a.stream);
+        rc = launch_inst<false, 3>(h, map, p, pl.smem, grid, a.stream);
     } else {
         switch (pl.fql2) {
-            case 3: rc = launch_inst<true, 3, false>(h, map, p, pl.smem, grid, a.stream); break;
-            case 4: rc = launch_inst<true, 4, false>(h, map, p, pl.smem, grid, a.stream); break;
-            default: rc = launch_inst<true, 5, false>(h, map, p, pl.smem, grid, a.stream); break;
+            case 3: rc = launch_inst<true, 3>(h, map, p, pl.smem, grid, a.stream); break;
+            case 4: rc = launch_inst<true, 4>(h, map, p, pl.smem, grid, a.stream); break;
+            default: rc = launch_inst<true, 5>(h, map, p, pl.smem, grid, a.stream); break;
         }
     }
     if (rc) return rc;
