@@ -15,11 +15,12 @@
 // Warp roles per CTA (1 CTA per SM, persistent, static tile -> CTA map); all hand-offs are mbarriers with
 // one arrival per warp, there is no CTA- or group-wide barrier in the steady state:
 //   warp 0      : TMA producer (cp.async.bulk.tensor, 128B swizzle, EVICT_FIRST) into an S-stage ring
-//   warp 1      : tcgen05.mma issuer (one lane); accumulator buffer = tile % NBUF in TMEM
+//   warps 1, 3  : tcgen05.mma issuers for even / odd local tiles (one elected lane each); accumulator buffer =
+//                 tile % NBUF in TMEM
 //   warp 2      : TMEM allocation / release
-//   warps 4-19  : epilogue warps.  Warp (q, r) owns TMEM lane quarter q of the tiles i == r (mod 4):
+//   warps 4-15  : epilogue warps.  Warp (q, r) owns TMEM lane quarter q of the tiles i == r (mod 3):
 //                 tcgen05.ld -> min + sign mask -> label (or exact re-evaluation) -> label to shared memory
-//   warps 20-27 : accumulator warps (only when sums are wanted).  Warp (q, r') owns rows of lane quarter q of
+//   warps 16-23 : accumulator warps (only when sums are wanted).  Warp (q, r') owns rows of lane quarter q of
 //                 the tiles i == r' (mod NA/4) and a PRIVATE fp32 [k+1][d] accumulator in shared memory:
 //                 lanes cover 128/d rows x d/4 feature quads per step, add the row into the accumulator row
 //                 of its label with plain load-add-store (no atomics: the array is private, label collisions
@@ -42,9 +43,19 @@
 namespace hk {
 namespace {
 
+// Tunables (measured at config 3 on B200: ER=3/MI=2 3.06 ms, ER=4/MI=2 3.29 ms, ER=2/MI=2 3.21 ms, ER=3/MI=1 3.15 ms):
+// the kernel is bound by instruction issue, and every waiting warp polls its barrier, so fewer warps win as long
+// as no role becomes the bottleneck.
+#ifndef HK_TC_ER
+#define HK_TC_ER 3  // tile residues handled by the epilogue warps (4 warps each)
+#endif
+#ifndef HK_TC_MI
+#define HK_TC_MI 2  // MMA issuer warps
+#endif
 constexpr int TM = 128;         // rows per tile (UMMA M)
 constexpr int MISC_WARPS = 4;   // producer, MMA, TMEM allocator, spare
-constexpr int E_WARPS = 16;     // epilogue warps: 4 lane quarters x 4 tile residues
+constexpr int E_WARPS = 4 * HK_TC_ER;  // epilogue warps: 4 lane quarters x ER tile residues
+constexpr int ER = HK_TC_ER;
 constexpr int A_WARPS_MAX = 8;  // accumulator warps (8, or 4 when the private accumulators are large)
 constexpr int E_FIRST = MISC_WARPS;
 constexpr int A_FIRST = MISC_WARPS + E_WARPS;
@@ -376,7 +387,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             }
         }
         TC_T(tw1 = clock64() - tstart;)
-    } else if (warp == 1 || warp == 3) {
+    } else if (warp == 1 || (HK_TC_MI == 2 && warp == 3)) {
         // ================= MMA issuers (warp 1: even local tiles, warp 3: odd) =================
         // convergent warp, one elected lane issues: descriptors are computed in uniform registers, so each
         // tcgen05.mma is a single UTCHMMA instead of a per-lane R2UR waterfall.  One issuer warp is not enough:
@@ -388,7 +399,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         const uint64_t bext_d = umma_desc_k_sw128(sbase + p.o_Bext);
         int s = mpar % S, b = mpar % NBUF;
         uint32_t ph = (uint32_t)((mpar / S) & 1), bph = (uint32_t)((mpar / NBUF) & 1);
-        for (int tile = blockIdx.x + mpar * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
+        for (int tile = blockIdx.x + mpar * gridDim.x; tile < ntiles; tile += HK_TC_MI * gridDim.x) {
             TC_T(t0 = clock64();)
             mbar_wait_a(b_tempty + b * 8, bph ^ 1);
             TC_T(t1 = clock64();)
@@ -417,12 +428,12 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             }
             __syncwarp();
             TC_T(tw0 += t1 - t0; tw1 += t2 - t1; tw2 += clock64() - t2;)
-            s += 2;
+            s += HK_TC_MI;
             if (s >= S) {
                 s -= S;
                 ph ^= 1;
             }
-            b += 2;
+            b += HK_TC_MI;
             if (b >= NBUF) {
                 b -= NBUF;
                 bph ^= 1;
@@ -451,7 +462,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         int b = r % NBUF;
         uint32_t bph = (uint32_t)((r / NBUF) & 1);
         TC_T(int i = r;)
-        for (int tile = blockIdx.x + r * gridDim.x; tile < ntiles; tile += 4 * gridDim.x) {
+        for (int tile = blockIdx.x + r * gridDim.x; tile < ntiles; tile += ER * gridDim.x) {
             TC_T(t0 = clock64();)
             const uint32_t xt = a_stages + s * stage_bytes;
             const int grow = tile * TM + row;
@@ -554,17 +565,17 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 __syncwarp();
                 if (lane == 0) mbar_arrive_a(b_empty + s * 8);
             }
-            s += 4;
+            s += ER;
             while (s >= S) {
                 s -= S;
                 ph ^= 1;
             }
-            b += 4;
+            b += ER;
             while (b >= NBUF) {
                 b -= NBUF;
                 bph ^= 1;
             }
-            TC_T(tw0 += t1 - t0; tw1 += t2 - t1; tw2 += clock64() - t2; i += 4;)
+            TC_T(tw0 += t1 - t0; tw1 += t2 - t1; tw2 += clock64() - t2; i += ER;)
         }
         if (want_fv) {
 #pragma unroll
