@@ -67,6 +67,14 @@ __global__ void split_lo_kernel(const float* __restrict__ A, int64_t rows, int f
     if (sub < rpw && r < rows && li == 0) nrm[r] = s;
 }
 
+// one MUFU instead of the ~8-instruction IEEE sequence: the 3xTF32 product already carries ~1e-6 relative error,
+// the epilogue is issue-bound, and the result stays within the parity tolerance of the exact path
+__device__ __forceinline__ float sqrt_fast(float v) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
     cdist_tc_kernel(const __grid_constant__ CUtensorMap xh_map, const __grid_constant__ CUtensorMap xl_map,
                     const __grid_constant__ CUtensorMap yh_map, const __grid_constant__ CUtensorMap yl_map,
@@ -89,7 +97,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.o_bars + 256);
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler (uniform-register role code)
     const int lane = tid & 31;
     const uint32_t kb_bytes = TM * 128;
     const uint32_t a_bytes = (uint32_t)(2 * nkb) * kb_bytes;
@@ -121,12 +129,14 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        // convergent warp, one elected lane issues (addresses and descriptors stay in uniform registers)
+        {
             uint32_t aph = 0;
             int slot = 0;
             uint32_t sph = 0;
             for (int rt = blockIdx.x; rt < p.num_row_tiles; rt += gridDim.x) {
                 mbar_wait_a(b_aempty, aph ^ 1);
+                if (elect_one()) {
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_afull), "r"(a_bytes)
                              : "memory");
                 for (int kb = 0; kb < nkb; ++kb) {
@@ -141,12 +151,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                         "l"(&xl_map), "r"(b_afull), "r"(kb * 32), "r"(rt * TM), "l"(kEvictFirst)
                         : "memory");
                 }
+                }
+                __syncwarp();
                 aph ^= 1;
                 for (int c = 0; c < p.num_chunks; ++c) {
                     for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
                         for (int part = 0; part < 2; ++part) {
                             mbar_wait_a(b_bempty + slot * 8, sph ^ 1);
+                            if (elect_one()) {
                             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_bfull + slot * 8),
                                          "r"(kb_bytes)
                                          : "memory");
@@ -156,6 +169,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                                 "l"(part == 0 ? &yh_map : &yl_map), "r"(b_bfull + slot * 8), "r"(kb * 32), "r"(c * TN),
                                 "l"(kEvictLast)
                                 : "memory");
+                            }
+                            __syncwarp();
                             if (++slot == NSLOT) {
                                 slot = 0;
                                 sph ^= 1;
@@ -167,7 +182,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // convergent warp: waits by all lanes, tcgen05 instructions by one elected lane
+        {
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t idesc = umma_idesc_tf32(TM, TN);
             uint32_t aph = 0;
             int slot = 0;
@@ -180,12 +197,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 for (int c = 0; c < p.num_chunks; ++c) {
                     mbar_wait_a(b_tempty + buf * 8, tph ^ 1);
                     tc_fence_after();
-                    const uint32_t dcol = tmem_base + (uint32_t)(buf * TN);
+                    const uint32_t dcol = tmem_u + (uint32_t)(buf * TN);
                     for (int kb = 0; kb < nkb; ++kb) {
                         // slot 0: raw Y block (read as yh) against xh and xl; slot 1: yl block against xh
                         mbar_wait_a(b_bfull + slot * 8, sph);
                         tc_fence_after();
-                        {
+                        if (elect_one()) {
                             const uint32_t bb = a_B + slot * kb_bytes;
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
@@ -197,14 +214,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                              b_bempty + slot * 8)
                                          : "memory");
-                            if (++slot == NSLOT) {
-                                slot = 0;
-                                sph ^= 1;
-                            }
+                        }
+                        __syncwarp();
+                        if (++slot == NSLOT) {
+                            slot = 0;
+                            sph ^= 1;
                         }
                         mbar_wait_a(b_bfull + slot * 8, sph);
                         tc_fence_after();
-                        {
+                        if (elect_one()) {
                             const uint32_t bb = a_B + slot * kb_bytes;
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks)
@@ -213,23 +231,28 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                              b_bempty + slot * 8)
                                          : "memory");
-                            if (++slot == NSLOT) {
-                                slot = 0;
-                                sph ^= 1;
-                            }
+                        }
+                        __syncwarp();
+                        if (++slot == NSLOT) {
+                            slot = 0;
+                            sph ^= 1;
                         }
                     }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                     b_tfull + buf * 8)
-                                 : "memory");
+                    if (elect_one())
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                         b_tfull + buf * 8)
+                                     : "memory");
+                    __syncwarp();
                     if (++buf == NBUF) {
                         buf = 0;
                         tph ^= 1;
                     }
                 }
                 // the A tiles may be overwritten once every MMA of this row tile has completed
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_aempty)
-                             : "memory");
+                if (elect_one())
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_aempty)
+                                 : "memory");
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -280,10 +303,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                         o.z = o.z < 0.f ? 0.f : o.z;
                         o.w = o.w < 0.f ? 0.f : o.w;
                         if (p.sqrt_flag) {
-                            o.x = sqrtf(o.x);
-                            o.y = sqrtf(o.y);
-                            o.z = sqrtf(o.z);
-                            o.w = sqrtf(o.w);
+                            o.x = sqrt_fast(o.x);
+                            o.y = sqrt_fast(o.y);
+                            o.z = sqrt_fast(o.z);
+                            o.w = sqrt_fast(o.w);
                         }
                         // staging tile: 128 rows x 128 B, 16-byte chunk index XOR (row & 7) (matches the store map)
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)((((j >> 2) ^ (row & 7))) << 4)),
