@@ -48,7 +48,15 @@ static int check_common(const char* fn, hk_handle_t h, const void* X, int64_t n,
 
 static int run_pass(Handle* h, const LloydArgs& a) {
     int path = a.path;
-    if (path == HK_PATH_AUTO) path = tc_supported(h, a) ? HK_PATH_TC : HK_PATH_SIMT;
+    if (path == HK_PATH_AUTO) {
+        if (tc_supported(h, a)) {
+            path = HK_PATH_TC;
+        } else if (bigk_supported(h, a) && !row128_supported(h, a)) {
+            return launch_lloyd_bigk(h, a);  // large k: distances on the tensor cores, sort-based sums
+        } else {
+            path = HK_PATH_SIMT;
+        }
+    }
     if (path == HK_PATH_TC) {
         if (!tc_supported(h, a)) {
             set_error("tensor-core path does not support dtype=%d d=%d k=%d ldx=%lld", a.dtype, a.d, a.k,

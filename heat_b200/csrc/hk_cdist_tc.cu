@@ -21,7 +21,7 @@ namespace {
 constexpr int TM = 128;   // output rows per tile (UMMA M)
 constexpr int TN = 128;   // output columns per accumulator (UMMA N)
 constexpr int NBUF = 4;   // TMEM accumulator buffers (4 x 128 columns)
-constexpr int NSLOT = 6;  // B ring slots of 16 KB
+constexpr int NSLOT = 6;  // B ring slots of 16 KB (barrier layout; the ring itself uses p.nslot <= NSLOT of them)
 constexpr int EPI_WARPS = 8;
 constexpr int NTHREADS = (4 + EPI_WARPS) * 32;
 
@@ -32,6 +32,7 @@ struct CdParams {
     const float* xn;
     const float* yn;
     int sqrt_flag;
+    int nslot;  // B ring slots in use (2..NSLOT)
     uint32_t o_A, o_B, o_stage, o_bars;
 };
 
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                                 : "memory");
                             }
                             __syncwarp();
-                            if (++slot == NSLOT) {
+                            if (++slot == p.nslot) {
                                 slot = 0;
                                 sph ^= 1;
                             }
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                                          : "memory");
                         }
                         __syncwarp();
-                        if (++slot == NSLOT) {
+                        if (++slot == p.nslot) {
                             slot = 0;
                             sph ^= 1;
                         }
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                                          : "memory");
                         }
                         __syncwarp();
-                        if (++slot == NSLOT) {
+                        if (++slot == p.nslot) {
                             slot = 0;
                             sph ^= 1;
                         }
@@ -338,19 +339,26 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 struct CdLayout {
     size_t A, B, stage, bars, total;
 };
-CdLayout cd_layout(int nkb) {
+CdLayout cd_layout(int nkb, int nslot) {
     CdLayout L;
     size_t o = 0;
     L.A = o;
     o += (size_t)2 * nkb * TM * 128;
     L.B = o;
-    o += (size_t)NSLOT * TM * 128;
+    o += (size_t)nslot * TM * 128;
     L.stage = o;
     o += (size_t)2 * TM * 128;
     L.bars = o;
     o += 512;
     L.total = o + 1024;
     return L;
+}
+
+// largest B ring (2..NSLOT slots) that fits next to the A tiles
+int cd_nslot(const Handle* h, int nkb) {
+    for (int ns = NSLOT; ns >= 2; --ns)
+        if (cd_layout(nkb, ns).total <= (size_t)h->smem_optin) return ns;
+    return 0;
 }
 
 }  // namespace
@@ -364,7 +372,7 @@ bool cdist_tc_supported(const Handle* h, const void* X, int64_t m, int f, int64_
         return false;
     if (m >= ((int64_t)1 << 31) - TM || n >= ((int64_t)1 << 31) - TN) return false;
     if (m < 1024 || n < 128) return false;  // small problems: the exact-FMA kernel is as good and bit-closer
-    return cd_layout(f / 32).total <= (size_t)h->smem_optin;
+    return cd_nslot(h, f / 32) >= 2;
 }
 
 int launch_cdist_tc(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n, int64_t ldy,
@@ -400,8 +408,10 @@ int launch_cdist_tc(Handle* h, const void* X, int64_t m, int f, int64_t ldx, con
     rc = make_tensor_map_2d(&out_map, out, 4, (uint64_t)m, (uint64_t)n, (uint64_t)ldo, 32, TM, 128);
     if (rc) return rc;
 
-    const CdLayout L = cd_layout(nkb);
+    const int nslot = cd_nslot(h, nkb);
+    const CdLayout L = cd_layout(nkb, nslot);
     CdParams p{};
+    p.nslot = nslot;
     p.m = m;
     p.n = n;
     p.f = f;

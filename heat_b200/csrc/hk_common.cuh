@@ -102,6 +102,8 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a);   // fp32 tensor-core path; 
 bool tc_supported(const Handle* h, const LloydArgs& a);
 int launch_lloyd_row128(Handle* h, const LloydArgs& a);  // exact FMA, rows of exactly 128 bytes
 bool row128_supported(const Handle* h, const LloydArgs& a);
+int launch_lloyd_bigk(Handle* h, const LloydArgs& a);  // fp32, k too large for the fused kernel: multi-pass
+bool bigk_supported(const Handle* h, const LloydArgs& a);
 
 int launch_finalize(Handle* h, const double* partials, const void* C_in, void* C_out, void* C_prev,
                     int k, int d, int dtype, int use_tol, double tol_cmp, void* shift2_out,

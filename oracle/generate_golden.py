@@ -3,6 +3,7 @@
 Run in the build container only (needs /root/reference; the GPU box does not have it):
 
     python oracle/generate_golden.py            # writes tests/golden/*.npz + MANIFEST.json
+    python oracle/generate_golden.py --only NAME   # (re)records one case, keeps the others
 
 The reference is imported from /root/reference under ``oracle/mpi4py_shim`` (mpi4py is not installed in
 this image).  Inputs come from seeded generators that the tests re-run (``heat_b200.synthetic`` and the
@@ -104,8 +105,14 @@ def main():
         return
     import heat as ht
 
+    only = sys.argv[2] if len(sys.argv) > 2 and sys.argv[1] == "--only" else None  # add one case, keep the rest
     manifest = {"reference_version": ht.__version__, "torch": torch.__version__, "cases": {}}
+    if only is not None:
+        with open(os.path.join(GOLD, "MANIFEST.json")) as f:
+            manifest = json.load(f)
     for name, spec in CASES.items():
+        if only is not None and name != only:
+            continue
         res = run_case(name)
         np.savez_compressed(os.path.join(GOLD, f"{name}.npz"), **res)
         manifest["cases"][name] = {"n_iter": int(res["n_iter"]), "inertia": float(res["inertia"]),
@@ -125,7 +132,8 @@ def main():
             print("   np=2 bit-identical to np=1:", same, flush=True)
             if same:
                 os.remove(os.path.join(GOLD, f"{name}__np2.npz"))  # Q7: nothing new to store
-    np.savez_compressed(os.path.join(GOLD, "cdist.npz"), **run_cdist())
+    if only is None:
+        np.savez_compressed(os.path.join(GOLD, "cdist.npz"), **run_cdist())
     with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 

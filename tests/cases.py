@@ -26,6 +26,8 @@ CASES = {
     "replicated_f32": dict(n=6000, d=8, k=6, dtype="f32", max_iter=50, tol=1e-4, split=None),
     "odd_d5_k3_f32": dict(n=7001, d=5, k=3, dtype="f32", max_iter=50, tol=1e-4),
     "wide_d128_k32_f32": dict(n=6000, d=128, k=32, dtype="f32", max_iter=30, tol=1e-4),
+    # k above the 256-centroid limit of the fused tensor-core kernel: the large-k path (BASELINE configs[3] shape class)
+    "bigk_f32_d64_k320": dict(n=40000, d=64, k=320, dtype="f32", max_iter=6, tol=None, offset=0.8, init_noise=0.5),
     "q3_count_gt_2p24_f64": dict(n=(1 << 24) + 5, d=1, k=1, dtype="f64", max_iter=1, tol=None, kind="ramp"),
 }
 
