@@ -33,6 +33,14 @@ struct CdParams {
     const float* yn;
     int sqrt_flag;
     int nslot;  // B ring slots in use (2..NSLOT)
+    // ARGMIN variant (large-k Lloyd pass): no distance matrix is written; per row the first-index argmin over all n
+    // columns goes to labels[], rows whose runner-up is within window * (|x|^2 + *cmax2) are appended to queue[]
+    int32_t* labels;
+    int32_t* queue;
+    int* qcount;
+    const float* cmax2;
+    float window;
+    int64_t row_base;  // global index of row 0 (labels / queue entries are global)
     uint32_t o_A, o_B, o_stage, o_bars;
 };
 
@@ -76,6 +84,7 @@ __device__ __forceinline__ float sqrt_fast(float v) {
     return r;
 }
 
+template <bool ARGMIN>
 __global__ void __launch_bounds__(NTHREADS, 1)
     cdist_tc_kernel(const __grid_constant__ CUtensorMap xh_map, const __grid_constant__ CUtensorMap xl_map,
                     const __grid_constant__ CUtensorMap yh_map, const __grid_constant__ CUtensorMap yl_map,
@@ -270,6 +279,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         for (int rt = blockIdx.x; rt < p.num_row_tiles; rt += gridDim.x) {
             const int64_t grow = (int64_t)rt * TM + row;
             const float xn = grow < p.m ? __ldg(p.xn + grow) : 0.f;
+            // ARGMIN: running minimum over this group's chunks (same scheme as the fused Lloyd epilogue)
+            float m_best = INFINITY, m_second = INFINITY;
+            unsigned mk_best = 0;
+            int c_best = 0;
+            const float thr = ARGMIN ? p.window * (xn + __ldg(p.cmax2)) : 0.f;
             for (int c = 0; c < p.num_chunks; ++c, ++lc) {
                 if ((lc & 1) != grp) continue;
                 const int buf = lc & (NBUF - 1);
@@ -287,6 +301,33 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                         if (lane == 0) mbar_arrive_a(b_tempty + buf * 8);  // accumulator drained by this warp
                     }
                     const int col0 = c * TN + sl * 32;
+                    if (ARGMIN) {
+                        // d^2 of 32 columns in place, then chunk minimum + mask of the columns within thr of it
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 yv = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);  // columns >= n never win
+                            if (col0 + j < p.n) yv = __ldg(reinterpret_cast<const float4*>(p.yn + col0 + j));
+                            float o0 = fmaf(-2.f, __uint_as_float(a[j + 0]), xn + yv.x);
+                            float o1 = fmaf(-2.f, __uint_as_float(a[j + 1]), xn + yv.y);
+                            float o2 = fmaf(-2.f, __uint_as_float(a[j + 2]), xn + yv.z);
+                            float o3 = fmaf(-2.f, __uint_as_float(a[j + 3]), xn + yv.w);
+                            a[j + 0] = __float_as_uint(o0 < 0.f ? 0.f : o0);
+                            a[j + 1] = __float_as_uint(o1 < 0.f ? 0.f : o1);
+                            a[j + 2] = __float_as_uint(o2 < 0.f ? 0.f : o2);
+                            a[j + 3] = __float_as_uint(o3 < 0.f ? 0.f : o3);
+                        }
+                        const float mc = min32(a);
+                        const unsigned mk = below_mask32(a, mc + thr);
+                        if (mc < m_best) {
+                            m_second = m_best;
+                            m_best = mc;
+                            mk_best = mk;
+                            c_best = col0;
+                        } else {
+                            m_second = fminf(m_second, mc);
+                        }
+                        continue;
+                    }
                     // the previous TMA store of this staging buffer must have finished reading it
                     if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     named_bar_sync(bar_id, 128);
@@ -324,8 +365,38 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                     }
                 }
             }
+            if (ARGMIN) {
+                // group 1 hands its state to group 0 through the (otherwise unused) staging tile; group 0 merges,
+                // stores the label and queues undecided rows.  NaN minima compare false everywhere: m_best stays
+                // +inf with an empty mask, the row is undecided and the exact kernel takes it.
+                const bool own_ok = (m_second >= m_best + thr) && (__popc(mk_best) == 1);
+                const int own_idx = c_best + __ffs(mk_best) - 1;
+                const uint32_t xch = a_stage + (uint32_t)row * 16;
+                named_bar_sync(3, 256);  // the previous row tile's exchange has been read
+                if (grp == 1) {
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(xch), "f"(m_best), "f"(__int_as_float(own_idx)),
+                                 "f"(own_ok ? 1.f : 0.f), "f"(0.f)
+                                 : "memory");
+                }
+                named_bar_sync(3, 256);
+                if (grp == 0) {
+                    float om, oi, ook, pad;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(om), "=f"(oi), "=f"(ook), "=f"(pad) : "r"(xch));
+                    const int o_idx = __float_as_int(oi);
+                    const bool take_other = om < m_best;  // equal minima: undecided below, the index does not matter
+                    const float best = take_other ? om : m_best;
+                    const float lose = take_other ? m_best : om;
+                    const bool ok = (take_other ? (ook != 0.f) : own_ok) && (lose >= best + thr);
+                    int lab = take_other ? o_idx : own_idx;
+                    if (lab < 0 || lab >= (int)p.n) lab = 0;  // undecided rows only (empty mask)
+                    if (grow < p.m) {
+                        p.labels[p.row_base + grow] = lab;
+                        if (!ok) p.queue[atomicAdd(p.qcount, 1)] = (int32_t)(p.row_base + grow);
+                    }
+                }
+            }
         }
-        if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (!ARGMIN && q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     tc_fence_before();
@@ -375,8 +446,17 @@ bool cdist_tc_supported(const Handle* h, const void* X, int64_t m, int f, int64_
     return cd_nslot(h, f / 32) >= 2;
 }
 
-int launch_cdist_tc(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n, int64_t ldy,
-                    void* out, int64_t ldo, int sqrt_flag, cudaStream_t st) {
+namespace {
+struct ArgminOut {
+    int32_t* labels;
+    int32_t* queue;
+    int* qcount;
+    const float* cmax2;
+    float window;
+    int64_t row_base;
+};
+int launch_cdist_tc_impl(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n, int64_t ldy,
+                         void* out, int64_t ldo, int sqrt_flag, const ArgminOut* am, cudaStream_t st) {
     const int nkb = f / 32;
     // scratch: xl [m x f], yl [n x f], xn [m], yn [n]
     const size_t need = ((size_t)m * f + (size_t)n * f + (size_t)m + (size_t)n + 64) * sizeof(float);
@@ -405,7 +485,10 @@ int launch_cdist_tc(Handle* h, const void* X, int64_t m, int f, int64_t ldx, con
     if (rc) return rc;
     rc = make_tensor_map_2d(&yl_map, yl, 4, (uint64_t)n, (uint64_t)f, (uint64_t)f, 32, TN, 128);
     if (rc) return rc;
-    rc = make_tensor_map_2d(&out_map, out, 4, (uint64_t)m, (uint64_t)n, (uint64_t)ldo, 32, TM, 128);
+    if (am == nullptr)
+        rc = make_tensor_map_2d(&out_map, out, 4, (uint64_t)m, (uint64_t)n, (uint64_t)ldo, 32, TM, 128);
+    else
+        out_map = xl_map;  // unused by the ARGMIN kernel
     if (rc) return rc;
 
     const int nslot = cd_nslot(h, nkb);
@@ -427,13 +510,41 @@ int launch_cdist_tc(Handle* h, const void* X, int64_t m, int f, int64_t ldx, con
     p.o_bars = (uint32_t)L.bars;
     int grid = h->num_sms;
     if (grid > p.num_row_tiles) grid = p.num_row_tiles;
-    HK_CUDA(cudaFuncSetAttribute(cdist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    prof_begin(h, st);
-    cdist_tc_kernel<<<grid, NTHREADS, L.total, st>>>(xh_map, xl_map, yh_map, yl_map, out_map, p);
-    prof_end(h, st);
+    if (am != nullptr) {
+        p.labels = am->labels;
+        p.queue = am->queue;
+        p.qcount = am->qcount;
+        p.cmax2 = am->cmax2;
+        p.window = am->window;
+        p.row_base = am->row_base;
+        HK_CUDA(cudaFuncSetAttribute(cdist_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        prof_begin(h, st);
+        cdist_tc_kernel<true><<<grid, NTHREADS, L.total, st>>>(xh_map, xl_map, yh_map, yl_map, out_map, p);
+        prof_end(h, st);
+    } else {
+        HK_CUDA(cudaFuncSetAttribute(cdist_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        prof_begin(h, st);
+        cdist_tc_kernel<false><<<grid, NTHREADS, L.total, st>>>(xh_map, xl_map, yh_map, yl_map, out_map, p);
+        prof_end(h, st);
+    }
     HK_CUDA(cudaGetLastError());
     h->launches++;
     return 0;
+}
+}  // namespace
+
+int launch_cdist_tc(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n, int64_t ldy,
+                    void* out, int64_t ldo, int sqrt_flag, cudaStream_t st) {
+    return launch_cdist_tc_impl(h, X, m, f, ldx, Y, n, ldy, out, ldo, sqrt_flag, nullptr, st);
+}
+
+// distances are consumed in the epilogue: labels[row_base + r] = first-index argmin_j d2(x_r, y_j); rows whose runner-up
+// lies within window * (|x|^2 + *cmax2) of the minimum (or that contain NaN) are appended to queue[] (large-k Lloyd pass)
+int launch_cdist_tc_argmin(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n, int64_t ldy,
+                           int32_t* labels, int64_t row_base, int32_t* queue, int* qcount, const float* cmax2, float window,
+                           cudaStream_t st) {
+    ArgminOut am{labels, queue, qcount, cmax2, window, row_base};
+    return launch_cdist_tc_impl(h, X, m, f, ldx, Y, n, ldy, nullptr, 4, 0, &am, st);
 }
 
 }  // namespace hk

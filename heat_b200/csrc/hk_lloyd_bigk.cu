@@ -3,10 +3,10 @@
 // (N=20M, d=128, k=1024).  Replaces the same reference code as the fused kernels
 // (heat/cluster/_kcluster.py:352-370 + heat/cluster/kmeans.py:76-103), as a short sequence of passes:
 //
-//   1. distances, chunk by chunk of rows, with the tcgen05 3xTF32 cdist kernel (hk_cdist_tc.cu) into a scratch tile
-//      [rows x k] that stays L2/HBM resident only until the next kernel has read it;
-//   2. argmin_rows_kernel: one warp per row -> first-index argmin, runner-up and NaN detection.  Rows whose runner-up is
-//      within the rounding window of the 3xTF32 product are queued for
+//   1. distances with the tcgen05 3xTF32 kernel of hk_cdist_tc.cu, ARGMIN variant: the epilogue keeps a running
+//      first-index minimum per row instead of writing the [rows x k] tile (1M rows per launch: bounded by the xl scratch);
+//   2. (only for a last chunk below 1024 rows: exact cdist kernel + argmin_rows_kernel, every row queued.)  Rows whose
+//      runner-up is within the rounding window of the 3xTF32 product, or that contain NaN, are queued for
 //   3. exact_fix_kernel: exact fp32 formula of heat/spatial/distance.py:59-64 over all centroids with torch.min tie/NaN
 //      semantics (one warp per queued row) - so labels are those of the exact-FMA kernels;
 //   4. cluster sums without atomics on floating point data: counting sort of the row indices by label (integer atomics),
@@ -21,6 +21,9 @@ namespace hk {
 
 int launch_cdist_tc(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n, int64_t ldy,
                     void* out, int64_t ldo, int sqrt_flag, cudaStream_t st);
+int launch_cdist_tc_argmin(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n, int64_t ldy,
+                           int32_t* labels, int64_t row_base, int32_t* queue, int* qcount, const float* cmax2, float window,
+                           cudaStream_t st);
 bool cdist_tc_supported(const Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n,
                         int64_t ldy, const void* out, int64_t ldo);
 
@@ -377,17 +380,17 @@ int launch_lloyd_bigk(Handle* h, const LloydArgs& a) {
     const int k = a.k, d = a.d;
     const int64_t n = a.n;
     cudaStream_t st = a.stream;
-    // scratch tile of distances: at most ~1 GiB, a multiple of 128 rows
-    int64_t chunk = ((int64_t)1 << 28) / k;
-    chunk = chunk / 128 * 128;
+    // rows per launch of the distance kernel: bounded by its xl scratch (chunk * d floats), a multiple of 128 rows
+    int64_t chunk = (int64_t)1 << 20;
     if (chunk > n) chunk = (n + 127) / 128 * 128;
+    const int64_t tail_rows = 1024;  // a last chunk below the tensor-core kernel's minimum goes through the exact kernel
     size_t off = 0;
     auto take = [&](size_t bytes) {
         const size_t o = off;
         off += al(bytes);
         return o;
     };
-    const size_t o_dist = take((size_t)chunk * k * 4), o_cn = take((size_t)k * 4), o_cmax = take(4),
+    const size_t o_dist = take((size_t)tail_rows * k * 4), o_cn = take((size_t)k * 4), o_cmax = take(4),
                  o_lab = take((size_t)n * 4), o_queue = take((size_t)n * 4), o_perm = take((size_t)n * 4),
                  o_qc = take(4), o_hist = take((size_t)k * 4), o_offs = take((size_t)(k + 1) * 4),
                  o_cur = take((size_t)k * 4), o_part = take((size_t)k * SPLIT * d * 8),
@@ -416,7 +419,7 @@ int launch_lloyd_bigk(Handle* h, const LloydArgs& a) {
 
     const float* X = reinterpret_cast<const float*>(a.X);
     const float* C = reinterpret_cast<const float*>(a.C);
-    if (!cdist_tc_supported(h, X, chunk < n ? chunk : n, d, a.ldx, C, k, d, s.dist, k)) {
+    if (!cdist_tc_supported(h, X, chunk < n ? chunk : n, d, a.ldx, C, k, d, s.lab, 4)) {
         set_error("lloyd_bigk: shape not supported by the distance kernel (n=%lld d=%d k=%d)", (long long)n, d, k);
         return -2;
     }
@@ -430,24 +433,19 @@ int launch_lloyd_bigk(Handle* h, const LloydArgs& a) {
     for (int64_t r0 = 0; r0 < n; r0 += chunk) {
         const int64_t rows = n - r0 < chunk ? n - r0 : chunk;
         int rc;
-        if (rows >= 1024) {
-            rc = launch_cdist_tc(h, X + (size_t)r0 * a.ldx, rows, d, a.ldx, C, k, d, s.dist, k, 0, st);
+        if (rows >= tail_rows) {
+            // distances + argmin fused: the [rows x k] tile never leaves the SM
+            rc = launch_cdist_tc_argmin(h, X + (size_t)r0 * a.ldx, rows, d, a.ldx, C, k, d, s.lab, r0, s.queue, s.qcount,
+                                        s.cmax2, window, st);
+            if (rc) return rc;
         } else {
             rc = launch_cdist(h, X + (size_t)r0 * a.ldx, rows, d, a.ldx, C, k, d, s.dist, k, HK_F32, 1, 0, st);
+            if (rc) return rc;
+            const int nb = (int)((rows + 7) / 8);
+            argmin_rows_kernel<<<nb, 256, 0, st>>>(s.dist, (int)rows, k, k, r0, n, nullptr, s.cmax2, window, 1, s.lab, s.queue,
+                                                   s.qcount, nullptr, a.state);
+            h->launches++;
         }
-        if (rc) return rc;
-        // |x|^2 of the chunk: recomputed by the cdist launcher into the handle's scratch (first floats after xl, yl)
-        const float* xn = nullptr;
-        {
-            // layout of launch_cdist_tc's scratch: xl [rows*d], yl [k*d], then xn (16-byte aligned)
-            const float* xl = reinterpret_cast<const float*>(h->part);
-            const float* p = xl + (size_t)rows * d + (size_t)k * d;
-            xn = reinterpret_cast<const float*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
-        }
-        const int nb = (int)((rows + 7) / 8);
-        argmin_rows_kernel<<<nb, 256, 0, st>>>(s.dist, (int)rows, k, k, r0, n, xn, s.cmax2, window, rows >= 1024 ? 0 : 1,
-                                               s.lab, s.queue, s.qcount, nullptr, a.state);
-        h->launches++;
     }
     exact_fix_kernel<<<h->num_sms * 4, 256, 0, st>>>(X, d, a.ldx, C, s.cn, k, s.queue, s.qcount, s.lab, a.state);
     h->launches++;

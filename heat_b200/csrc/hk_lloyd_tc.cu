@@ -158,60 +158,6 @@ __device__ __noinline__ float row_norm2(uint32_t xt, int row, int d) {
     return xn;
 }
 
-// (a0 - t, a1 - t) with one packed FP32x2 add (sm_100 FADD2)
-__device__ __forceinline__ void sub2(uint32_t a0, uint32_t a1, uint64_t negthr2, uint32_t& r0, uint32_t& r1) {
-    uint64_t in, out;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(in) : "r"(a0), "r"(a1));
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(out) : "l"(in), "l"(negthr2));
-    asm("mov.b64 {%0, %1}, %2;" : "=r"(r0), "=r"(r1) : "l"(out));
-}
-// sign-bit mask of (s_j < thr) for 32 accumulator columns: bit j <-> column j (4 independent shift chains)
-__device__ __forceinline__ unsigned below_mask32(const uint32_t* a, float thr) {
-    const uint32_t nt = __float_as_uint(-thr);
-    uint64_t negthr2;
-    asm("mov.b64 %0, {%1, %1};" : "=l"(negthr2) : "r"(nt));
-    unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-#pragma unroll
-    for (int j = 6; j >= 0; j -= 2) {
-        uint32_t t0, t1;
-        sub2(a[j], a[j + 1], negthr2, t0, t1);
-        m0 = __funnelshift_l(t1, m0, 1);
-        m0 = __funnelshift_l(t0, m0, 1);
-        sub2(a[8 + j], a[9 + j], negthr2, t0, t1);
-        m1 = __funnelshift_l(t1, m1, 1);
-        m1 = __funnelshift_l(t0, m1, 1);
-        sub2(a[16 + j], a[17 + j], negthr2, t0, t1);
-        m2 = __funnelshift_l(t1, m2, 1);
-        m2 = __funnelshift_l(t0, m2, 1);
-        sub2(a[24 + j], a[25 + j], negthr2, t0, t1);
-        m3 = __funnelshift_l(t1, m3, 1);
-        m3 = __funnelshift_l(t0, m3, 1);
-    }
-    return m0 | (m1 << 8) | (m2 << 16) | (m3 << 24);
-}
-__device__ __forceinline__ float min32(const uint32_t* a) {
-    float m0 = __uint_as_float(a[0]), m1 = __uint_as_float(a[1]), m2 = __uint_as_float(a[2]),
-          m3 = __uint_as_float(a[3]);
-#pragma unroll
-    for (int j = 4; j < 32; j += 4) {
-        m0 = fminf(m0, __uint_as_float(a[j]));
-        m1 = fminf(m1, __uint_as_float(a[j + 1]));
-        m2 = fminf(m2, __uint_as_float(a[j + 2]));
-        m3 = fminf(m3, __uint_as_float(a[j + 3]));
-    }
-    return fminf(fminf(m0, m1), fminf(m2, m3));
-}
-
-// K-major SWIZZLE_128B descriptor whose 8-row groups all alias the same 1 KB (stride byte offset 0)
-__device__ __forceinline__ uint64_t umma_desc_k_sw128_bcast(uint32_t smem_addr) {
-    uint64_t dsc = 0;
-    dsc |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    dsc |= (uint64_t)1 << 16;
-    dsc |= (uint64_t)1 << 46;
-    dsc |= (uint64_t)2 << 61;
-    return dsc;
-}
-
 enum { XN_COMPUTE = 0, XN_WRITE = 1, XN_READ = 2 };
 
 // cycle counters per role / per-tile timeline of CTA 0: compiled in with -DHK_TC_TIMING only, the hot loops of the
