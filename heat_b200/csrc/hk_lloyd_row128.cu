@@ -21,7 +21,11 @@ namespace {
 
 constexpr int TM = 128;
 constexpr int MISC_WARPS = 4;
-constexpr int E_WARPS = 16;
+#ifndef HK_ROW_ER
+#define HK_ROW_ER 4
+#endif
+constexpr int ER = HK_ROW_ER;           // tile residues handled by the distance warps (4 warps each)
+constexpr int E_WARPS = 4 * ER;
 constexpr int A_WARPS = 8;
 constexpr int E_FIRST = MISC_WARPS;
 constexpr int A_FIRST = MISC_WARPS + E_WARPS;
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS : 0)) 
         double fv_acc = 0.0;
         int s = r % S;
         uint32_t ph = (uint32_t)((r / S) & 1);
-        for (int tile = blockIdx.x + r * gridDim.x; tile < ntiles; tile += 4 * gridDim.x) {
+        for (int tile = blockIdx.x + r * gridDim.x; tile < ntiles; tile += ER * gridDim.x) {
             const uint32_t xrow = a_stages + s * STAGE_BYTES + (uint32_t)row * 128;
             const int row0 = tile * TM;
             const bool active = (int64_t)row0 + row < p.n;
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS : 0)) 
                 __syncwarp();
                 if (lane == 0) mbar_arrive_a(b_empty + s * 8);
             }
-            s += 4;
+            s += ER;
             while (s >= S) {
                 s -= S;
                 ph ^= 1;
