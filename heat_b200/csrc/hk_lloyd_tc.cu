@@ -110,8 +110,8 @@ __host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sum
     if (sums) o += (size_t)S * TM * 2;
     L.cnt = o;  // private cluster counts of the 16 epilogue warps (int)
     if (sums) o += up((size_t)E_WARPS * (2 * k + 1) * 4, 16);  // + per-tile label histograms [E_WARPS][k+1]
-    L.snap = o;  // per stage and lane quarter: largest label multiplicity among the 32 rows
-    if (sums) o += up((size_t)S * 4 * 4, 16);
+    L.snap = o;  // multiplicity ring: [32 local tiles][4 lane quarters] largest label multiplicity among the 32 rows
+    if (sums) o += 32 * 4 * 4;
     L.bars = o;
     o += 8 * 96;  // mbarriers
     L.misc = o;
@@ -203,13 +203,12 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     const uint32_t a_B = sbase + p.o_B;
     const uint32_t a_lab = sbase + p.o_lab;
     float* cn = reinterpret_cast<float*>(smem + p.o_cn);
-    // mbarriers: full[S] | empty[S] | lfull[S] | tfull[NBUF] | tempty[NBUF] | mfull[S]   (16 slots per array)
+    // mbarriers: full[S] | empty[S] | lfull[S] | tfull[NBUF] | tempty[NBUF]   (16 slots per array)
     const uint32_t b_full = sbase + p.o_bars;
     const uint32_t b_empty = b_full + 16 * 8;
     const uint32_t b_lfull = b_full + 32 * 8;
     const uint32_t b_tfull = b_full + 48 * 8;
     const uint32_t b_tempty = b_full + 64 * 8;
-    const uint32_t b_mfull = b_full + 80 * 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.o_misc);
     float* cmax_s = reinterpret_cast<float*>(smem + p.o_misc + 16);
     int* force_exact_s = reinterpret_cast<int*>(smem + p.o_misc + 32);
@@ -230,7 +229,6 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + s, 1);
             mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 16 + s, 4 + (SUMS ? 4 : 0));
             mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 32 + s, 4);
-            mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 80 + s, 4);
         }
         for (int b = 0; b < NBUF; ++b) {
             mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 48 + b, 1);
@@ -407,8 +405,8 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         uint32_t ph = (uint32_t)((r / S) & 1);
         int b = r % NBUF;
         uint32_t bph = (uint32_t)((r / NBUF) & 1);
-        TC_T(int i = r;)
-        for (int tile = blockIdx.x + r * gridDim.x; tile < ntiles; tile += ER * gridDim.x) {
+        int i = r;  // local tile counter of this CTA
+        for (int tile = blockIdx.x + r * gridDim.x; tile < ntiles; tile += ER * gridDim.x, i += ER) {
             TC_T(t0 = clock64();)
             const uint32_t xt = a_stages + s * stage_bytes;
             const int grow = tile * TM + row;
@@ -502,8 +500,11 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 const int mm = __reduce_max_sync(0xffffffffu, lab < k ? old + 1 : 0);
                 sts_s32(ha, 0);
                 if (lane == 0) {
-                    sts_s32(a_mmax_q + (uint32_t)s * 16, mm);
-                    mbar_arrive_a(b_mfull + s * 8);
+                    // 32-deep ring indexed by the local tile number, read `lag` tiles later by the accumulator warp (lag
+                    // is a multiple of ER): this warp's lfull arrival for that later tile orders the store, so the
+                    // ring needs no barrier of its own; slot i is rewritten for tile i+32, which cannot be in flight
+                    // (at most S <= 12 tiles are) before tile i+lag has been accumulated
+                    sts_s32(a_mmax_q + (uint32_t)(i & 31) * 16, mm);
                     mbar_arrive_a(b_empty + s * 8);
                     TC_T(if (p.tl && blockIdx.x == 0 && q == 0 && i < 512) p.tl[i * 8 + 4] = clock64();)
                 }
@@ -521,7 +522,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 b -= NBUF;
                 bph ^= 1;
             }
-            TC_T(tw0 += t1 - t0; tw1 += t2 - t1; tw2 += clock64() - t2; i += ER;)
+            TC_T(tw0 += t1 - t0; tw1 += t2 - t1; tw2 += clock64() - t2;)
         }
         if (want_fv) {
 #pragma unroll
@@ -578,7 +579,10 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
 
         int s = res % S;
         uint32_t ph = (uint32_t)((res / S) & 1);
-        for (int tile = blockIdx.x + res * gridDim.x; tile < ntiles; tile += nres * gridDim.x) {
+        int i = res;  // local tile counter of this CTA
+        // smallest common multiple of ER (same epilogue warp) and nres (same accumulator warp)
+        const int lag = (nres == 2 && (ER & 1)) ? 2 * ER : ER;
+        for (int tile = blockIdx.x + res * gridDim.x; tile < ntiles; tile += nres * gridDim.x, i += nres) {
             TC_T(t0 = clock64();)
             warp_wait(b_full + s * 8, ph, lane);   // x tile visible
             warp_wait(b_lfull + s * 8, ph, lane);  // labels of all four lane quarters published
@@ -634,14 +638,15 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                     }
                 }
             }
-            warp_wait(b_mfull + s * 8, ph, lane);  // multiplicities of this tile published (long done by now)
-            run_max += lds_s32(a_mmax_q + (uint32_t)s * 16);
+            // multiplicity bound of this warp's tile `lag` back (ordered by the lfull wait of this tile, see the epilogue)
+            if (i >= lag) run_max += lds_s32(a_mmax_q + (uint32_t)((i - lag) & 31) * 16);
             __syncwarp();
             if (lane == 0) mbar_arrive_a(b_empty + s * 8);
             TC_T(if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && ila < 512) p.tl[ila * 8 + 6] = clock64();
                  t2 = clock64();)
-            // widen before any accumulator row can have taken more than ~100 fp32 adds (timing independent)
-            if (run_max >= 72) flush();
+            // widen before any accumulator row can have taken more than ~150 fp32 adds: the multiplicities of this
+            // warp's last lag/nres tiles are not in run_max yet (at most 32 each, ~3 in practice).  Timing independent.
+            if (run_max >= 48) flush();
             TC_T(tw0 += t1 - t0; tw1 += t2 - t1; tw2 += clock64() - t2;)
             s += nres;
             if (s >= S) {
