@@ -413,11 +413,13 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             const bool active = grow < n32;
 
             float xn, xs;  // |x|^2 and |x| of this row, or upper bounds for every row of the tile
+            // x tile landed.  Observed here even when only the cached bound is read, so that the labels published
+            // below order the accumulator warps after the TMA writes without a wait of their own.
+            warp_wait(b_full + s * 8, ph, lane);
             if (xn_mode == XN_READ) {
                 xs = __ldg(p.bounds + tile);  // the cache holds sqrt(max |x|^2)
                 xn = xs * xs;
             } else {
-                warp_wait(b_full + s * 8, ph, lane);  // x tile landed
                 xn = row_norm2(xt, row, d);
                 xs = sqrtf(xn);
                 if (xn_mode == XN_WRITE) {
@@ -584,8 +586,9 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         const int lag = (nres == 2 && (ER & 1)) ? 2 * ER : ER;
         for (int tile = blockIdx.x + res * gridDim.x; tile < ntiles; tile += nres * gridDim.x, i += nres) {
             TC_T(t0 = clock64();)
-            warp_wait(b_full + s * 8, ph, lane);   // x tile visible
-            warp_wait(b_lfull + s * 8, ph, lane);  // labels of all four lane quarters published
+            // labels of all four lane quarters published; the epilogue warps observed the x tile before publishing,
+            // so this wait also orders the reads of the tile below
+            warp_wait(b_lfull + s * 8, ph, lane);
             TC_T(t1 = clock64(); const int ila = (tile - blockIdx.x) / gridDim.x;
                  if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && ila < 512) p.tl[ila * 8 + 5] = clock64();)
             const uint32_t xq = a_stages + s * stage_bytes + x_lane;
