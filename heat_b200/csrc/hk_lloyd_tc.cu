@@ -546,6 +546,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         const uint32_t rowbytes = (uint32_t)d * 4;
         const uint32_t a_mmax_q = sbase + p.o_snap + (uint32_t)q * 4;
         const uint32_t a_lab_lane = a_lab + (uint32_t)(q * 32 + lane) * 2;
+        const uint32_t a_lab_grp = a_lab + (uint32_t)(q * 32 + g) * 2;  // label of row slot g of step 0
         int run_max = 0;  // upper bound on the fp32 adds any accumulator row has taken since the last flush
         const uint32_t acc_w = sbase + p.o_acc + (uint32_t)a * (uint32_t)(k + 1) * rowbytes;
         const uint32_t acc_l = acc_w + fq * 16;
@@ -610,7 +611,8 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
 #pragma unroll
                 for (int j = 0; j < BATCH; ++j) {
                     const int rs = (it0 + j) * RPI;  // first row of the step inside the quarter
-                    const uint32_t l = __shfl_sync(0xffffffffu, mylab, rs + g);
+                    // straight from shared memory (an independent load) rather than a shuffle of mylab
+                    const uint32_t l = lds_u16(a_lab_grp + s * (TM * 2) + (uint32_t)(rs * 2));
                     aa[j] = acc_l + l * rowbytes;
                     xr[j] = lds_f4(xq + (uint32_t)(rs << 7) + (((fq7 ^ (uint32_t)((rs + g) & 7))) << 4));
                 }
