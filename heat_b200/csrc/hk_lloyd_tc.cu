@@ -649,9 +649,11 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             if (lane == 0) mbar_arrive_a(b_empty + s * 8);
             TC_T(if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && ila < 512) p.tl[ila * 8 + 6] = clock64();
                  t2 = clock64();)
-            // widen before any accumulator row can have taken more than ~150 fp32 adds: the multiplicities of this
-            // warp's last lag/nres tiles are not in run_max yet (at most 32 each, ~3 in practice).  Timing independent.
-            if (run_max >= 48) flush();
+            // widen before any accumulator row can have taken more than 72 + 96 fp32 adds: the multiplicities of this
+            // warp's last lag/nres <= 3 tiles are not in run_max yet (at most 32 each, ~3 in practice), so a partial sum
+            // carries at most ~170 * 2^-24 = 1e-5 relative rounding error in the worst case (typically 100x less).
+            // Timing independent.  (A threshold of 48 costs 2.5 % of the iteration in extra flushes.)
+            if (run_max >= 72) flush();
             TC_T(tw0 += t1 - t0; tw1 += t2 - t1; tw2 += clock64() - t2;)
             s += nres;
             if (s >= S) {
