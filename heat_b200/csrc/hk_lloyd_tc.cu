@@ -502,11 +502,10 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 const int mm = __reduce_max_sync(0xffffffffu, lab < k ? old + 1 : 0);
                 sts_s32(ha, 0);
                 if (lane == 0) {
-                    // 32-deep ring indexed by the local tile number, read `lag` tiles later by the accumulator warp (lag
-                    // is a multiple of ER): this warp's lfull arrival for that later tile orders the store, so the
-                    // ring needs no barrier of its own; slot i is rewritten for tile i+32, which cannot be in flight
-                    // (at most S <= 12 tiles are) before tile i+lag has been accumulated
-                    sts_s32(a_mmax_q + (uint32_t)(i & 31) * 16, mm);
+                    // 32-deep ring indexed by the local tile number, read by the accumulator warp when it starts its
+                    // next own tile.  No barrier: the value carries the tile number as a tag, a reader that does not
+                    // find its tag (this store not visible yet, practically never) assumes the worst case instead.
+                    sts_s32(a_mmax_q + (uint32_t)(i & 31) * 16, (i << 6) | mm);
                     mbar_arrive_a(b_empty + s * 8);
                     TC_T(if (p.tl && blockIdx.x == 0 && q == 0 && i < 512) p.tl[i * 8 + 4] = clock64();)
                 }
@@ -583,8 +582,6 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         int s = res % S;
         uint32_t ph = (uint32_t)((res / S) & 1);
         int i = res;  // local tile counter of this CTA
-        // smallest common multiple of ER (same epilogue warp) and nres (same accumulator warp)
-        const int lag = (nres == 2 && (ER & 1)) ? 2 * ER : ER;
         for (int tile = blockIdx.x + res * gridDim.x; tile < ntiles; tile += nres * gridDim.x, i += nres) {
             TC_T(t0 = clock64();)
             // labels of all four lane quarters published; the epilogue warps observed the x tile before publishing,
@@ -643,17 +640,22 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                     }
                 }
             }
-            // multiplicity bound of this warp's tile `lag` back (ordered by the lfull wait of this tile, see the epilogue)
-            if (i >= lag) run_max += lds_s32(a_mmax_q + (uint32_t)((i - lag) & 31) * 16);
+            // multiplicity bound of this warp's previous tile: tagged ring slot, worst case (32 rows, one label) if the
+            // epilogue warp's store is not visible yet
+            if (i >= nres) {
+                const int v = lds_s32(a_mmax_q + (uint32_t)((i - nres) & 31) * 16);
+                run_max += (v >> 6) == i - nres ? (v & 63) : 32;
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive_a(b_empty + s * 8);
             TC_T(if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && ila < 512) p.tl[ila * 8 + 6] = clock64();
                  t2 = clock64();)
-            // widen before any accumulator row can have taken more than 72 + 96 fp32 adds: the multiplicities of this
-            // warp's last lag/nres <= 3 tiles are not in run_max yet (at most 32 each, ~3 in practice), so a partial sum
-            // carries at most ~170 * 2^-24 = 1e-5 relative rounding error in the worst case (typically 100x less).
-            // Timing independent.  (A threshold of 48 costs 2.5 % of the iteration in extra flushes.)
-            if (run_max >= 72) flush();
+            // widen before any accumulator row can have taken more than 96 + 64 fp32 adds: run_max lags by this tile
+            // and the previous one (at most 32 adds each, ~3 in practice), so a partial sum carries at most
+            // 160 * 2^-24 = 1e-5 relative rounding error in the worst case (typically 100x less).  Timing independent
+            // unless a ring tag is missed, which only makes the flush earlier.  (Each flush costs ~2800 cycles of
+            // global read-modify-write; a threshold of 48 costs 2.5 % of the iteration.)
+            if (run_max >= 96) flush();
             TC_T(tw0 += t1 - t0; tw1 += t2 - t1; tw2 += clock64() - t2;)
             s += nres;
             if (s >= S) {
