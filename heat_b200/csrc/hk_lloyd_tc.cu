@@ -1,6 +1,6 @@
 // Tensor-core Lloyd pass (fp32 data) for sm_100a: TMA-streamed row tiles, tcgen05 TF32 distance filter with
 // fp32 accumulators in TMEM, exact-FMA refinement of the rows the filter cannot decide, and deterministic
-// per-cluster column sums kept in registers.
+// per-cluster column sums in private shared-memory accumulators.
 //
 // Why a filter: at k=64, d=32 the distance contraction costs 2*k = 128 FLOP per 4-byte element, three
 // times what the FP32 pipes can sustain at HBM speed, so x.c^T runs on the 5th-gen tensor cores
@@ -25,8 +25,11 @@
 //                 lanes cover 128/d rows x d/4 feature quads per step, add the row into the accumulator row
 //                 of its label with plain load-add-store (no atomics: the array is private, label collisions
 //                 inside a step are detected up front and serialised).  The array is widened into a per-warp
-//                 fp64 slot in global memory (L2) before any cluster can have received more than ~100 rows,
+//                 fp64 slot in global memory (L2) before any cluster can have received more than 160 rows,
 //                 so fp32 partial sums stay short.  Fixed row order and fixed reduction order -> deterministic.
+//                 The accumulator warps are the slowest stage: they wait on ONE barrier per tile (labels published;
+//                 the epilogue warps observe the TMA barrier first, which orders the tile reads transitively), and
+//                 the label multiplicities they need for the flush rule arrive through a barrier-free tagged ring.
 // The accumulator is seeded with |c_j|^2 by one extra k-step (ones x three exact TF32 pieces of |c_j|^2)
 // and B holds -2*c, so TMEM already contains s_j = |c_j|^2 - 2 x.c_j and the epilogue is min + sign-mask.
 // |x|^2 (needed only for the bound E) is computed per row in the first pass over a matrix and cached as a
