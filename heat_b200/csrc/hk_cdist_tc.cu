@@ -41,6 +41,7 @@ struct CdParams {
     const float* cmax2;
     float window;
     int64_t row_base;  // global index of row 0 (labels / queue entries are global)
+    const int32_t* state;  // optional: state[0] != 0 -> the pass is skipped (fit already converged)
     uint32_t o_A, o_B, o_stage, o_bars;
 };
 
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                     const __grid_constant__ CUtensorMap yh_map, const __grid_constant__ CUtensorMap yl_map,
                     const __grid_constant__ CUtensorMap out_map, const CdParams p) {
     extern __shared__ unsigned char smem_raw[];
+    if (ARGMIN && p.state != nullptr && p.state[0] != 0) return;  // uniform across the grid
     unsigned char* smem =
         reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
@@ -454,6 +456,7 @@ struct ArgminOut {
     const float* cmax2;
     float window;
     int64_t row_base;
+    const int32_t* state;
 };
 int launch_cdist_tc_impl(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n, int64_t ldy,
                          void* out, int64_t ldo, int sqrt_flag, const ArgminOut* am, cudaStream_t st) {
@@ -517,6 +520,7 @@ int launch_cdist_tc_impl(Handle* h, const void* X, int64_t m, int f, int64_t ldx
         p.cmax2 = am->cmax2;
         p.window = am->window;
         p.row_base = am->row_base;
+        p.state = am->state;
         HK_CUDA(cudaFuncSetAttribute(cdist_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
         prof_begin(h, st);
         cdist_tc_kernel<true><<<grid, NTHREADS, L.total, st>>>(xh_map, xl_map, yh_map, yl_map, out_map, p);
@@ -542,8 +546,8 @@ int launch_cdist_tc(Handle* h, const void* X, int64_t m, int f, int64_t ldx, con
 // lies within window * (|x|^2 + *cmax2) of the minimum (or that contain NaN) are appended to queue[] (large-k Lloyd pass)
 int launch_cdist_tc_argmin(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n, int64_t ldy,
                            int32_t* labels, int64_t row_base, int32_t* queue, int* qcount, const float* cmax2, float window,
-                           cudaStream_t st) {
-    ArgminOut am{labels, queue, qcount, cmax2, window, row_base};
+                           const int32_t* state, cudaStream_t st) {
+    ArgminOut am{labels, queue, qcount, cmax2, window, row_base, state};
     return launch_cdist_tc_impl(h, X, m, f, ldx, Y, n, ldy, nullptr, 4, 0, &am, st);
 }
 

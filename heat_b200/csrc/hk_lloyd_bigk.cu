@@ -23,7 +23,7 @@ int launch_cdist_tc(Handle* h, const void* X, int64_t m, int f, int64_t ldx, con
                     void* out, int64_t ldo, int sqrt_flag, cudaStream_t st);
 int launch_cdist_tc_argmin(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n, int64_t ldy,
                            int32_t* labels, int64_t row_base, int32_t* queue, int* qcount, const float* cmax2, float window,
-                           cudaStream_t st);
+                           const int32_t* state, cudaStream_t st);
 bool cdist_tc_supported(const Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n,
                         int64_t ldy, const void* out, int64_t ldo);
 
@@ -436,7 +436,7 @@ int launch_lloyd_bigk(Handle* h, const LloydArgs& a) {
         if (rows >= tail_rows) {
             // distances + argmin fused: the [rows x k] tile never leaves the SM
             rc = launch_cdist_tc_argmin(h, X + (size_t)r0 * a.ldx, rows, d, a.ldx, C, k, d, s.lab, r0, s.queue, s.qcount,
-                                        s.cmax2, window, st);
+                                        s.cmax2, window, a.state, st);
             if (rc) return rc;
         } else {
             rc = launch_cdist(h, X + (size_t)r0 * a.ldx, rows, d, a.ldx, C, k, d, s.dist, k, HK_F32, 1, 0, st);
