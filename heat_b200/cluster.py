@@ -99,30 +99,33 @@ class KMeans(BaseEstimator):
             raise ValueError(f"Oversampling factor should be at least 2, but was {oversampling}")
         if iter_multiplier < 1:
             raise ValueError(f"Iteration multiplier should be at least 1, but was {iter_multiplier}")
+        # argument errors first (ValueError), layout limits second (NotImplementedError): the order in which the
+        # reference reports them (tests/cluster/test_kmeans.py:68-100)
+        if isinstance(self.init, DNDarray):
+            if len(self.init.shape) != 2:
+                raise ValueError(f"passed centroids need to be two-dimensional, but are {len(self.init.shape)}")
+            if self.init.shape[0] != self.n_clusters or self.init.shape[1] != x.shape[1]:
+                raise ValueError("passed centroids do not match cluster count or data shape")
+        elif not (isinstance(self.init, str) and self.init in ("random", "probability_based", "batchparallel")):
+            raise ValueError(
+                'init needs to be one of "random", ht.DNDarray, "kmeans++", or "batchparallel", '
+                f"but was {self.init}")
         if len(x.shape) != 2:
             raise NotImplementedError("Only 2D data matrices are currently supported")
         if x.split not in (None, 0):
             raise NotImplementedError("Not implemented for other splitting-axes")
 
         if isinstance(self.init, DNDarray):
-            if len(self.init.shape) != 2:
-                raise ValueError(f"passed centroids need to be two-dimensional, but are {len(self.init.shape)}")
-            if self.init.shape[0] != self.n_clusters or self.init.shape[1] != x.shape[1]:
-                raise ValueError("passed centroids do not match cluster count or data shape")
             self._cluster_centers = self.init.resplit(None)
         elif self.init == "random":
             g = torch.Generator()
             g.manual_seed(0 if self.random_state is None else int(self.random_state))
             idx = torch.randint(0, max(x.shape[0] - 1, 1), (self.n_clusters,), generator=g)
             self._cluster_centers = _gather_rows(x, idx)
-        elif self.init in ("probability_based", "batchparallel"):
+        else:
             raise NotImplementedError(
                 f'init="{self.init}" is outside the accelerated path (SURVEY.md §8f N2); pass a DNDarray of '
                 'initial centroids or init="random"')
-        else:
-            raise ValueError(
-                'init needs to be one of "random", ht.DNDarray, "kmeans++", or "batchparallel", '
-                f"but was {self.init}")
 
     # -- the hot loop -------------------------------------------------------------------------------------
     def fit(self, x: DNDarray, oversampling: float = 2, iter_multiplier: float = 1):

@@ -134,14 +134,18 @@ def array(obj, dtype: Optional[torch.dtype] = None, split: Optional[int] = None,
         t = t.to(torch.float32)  # Heat's default float is float32 (types.py)
     if device is not None:
         t = t.to(device)
-    for ax in (split, is_split):
-        if ax is not None and ax not in (0, -t.ndim if t.ndim else 0):
-            if ax != 0:
-                raise NotImplementedError("only split=0 / split=None are supported on this path")
+    if is_split is not None and is_split not in (0, -t.ndim if t.ndim else 0):
+        raise NotImplementedError("only is_split=0 is supported on this path")
     if split is not None:
-        _, lshape, slices = comm.chunk(t.shape, 0)
+        if split < 0:
+            split += t.ndim
+        if not 0 <= split < max(t.ndim, 1):
+            raise ValueError(f"split axis {split} out of range for a {t.ndim}-dimensional array")
+        # any axis can be split (heat/core/factories.py:428-434); the k-means path itself accepts only axis 0 and
+        # raises NotImplementedError for the others, exactly like the reference (tests/cluster/test_kmeans.py:68-100)
+        _, lshape, slices = comm.chunk(t.shape, split)
         local = t[slices]
-        return DNDarray(local, tuple(t.shape), t.dtype, 0, t.device, comm, True)
+        return DNDarray(local, tuple(t.shape), t.dtype, split, t.device, comm, True)
     if is_split is not None:
         n = torch.tensor([t.shape[0]], dtype=torch.int64)
         if comm.is_distributed():

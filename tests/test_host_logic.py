@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -95,6 +96,34 @@ def test_exception_contract():
         hb.spatial.cdist(hb.array(torch.randn(3, 4)), hb.array(torch.randn(3, 5)))
     with pytest.raises(TypeError):
         hb.spatial.cdist(torch.randn(3, 4), hb.array(torch.randn(3, 4)))
+
+
+def test_reference_exception_list_on_split1_data():
+    # reference: tests/cluster/test_kmeans.py:68-100 (test_exceptions), statement by statement, with a split=1 matrix
+    x = hb.array(torch.randn(150, 4), split=1)
+    assert x.split == 1
+    k = 3
+    with pytest.raises(NotImplementedError):
+        hb.cluster.KMeans(n_clusters=k).fit(x)
+    with pytest.raises(ValueError):
+        hb.cluster.KMeans(n_clusters=k).set_params(foo="bar")
+    with pytest.raises(ValueError):
+        hb.cluster.KMeans(n_clusters=k, init="random_number").fit(x)
+    with pytest.raises(NotImplementedError):
+        hb.cluster.KMeans(n_clusters=k, init="batchparallel").fit(x)
+    with pytest.raises(ValueError):
+        hb.cluster.KMeans(n_clusters=k, init=np.array([1, 2, 3])).fit(x)
+    with pytest.raises(ValueError):
+        hb.cluster.KMeans(n_clusters=k).fit(x, oversampling=-1)
+    with pytest.raises(ValueError):
+        hb.cluster.KMeans(n_clusters=k).fit(x, iter_multiplier=-1)
+    with pytest.raises(ValueError):
+        hb.cluster.KMeans(n_clusters=k, init=hb.array([1, 2])).fit(x)
+    with pytest.raises(NotImplementedError):
+        hb.cluster.KMeans(n_clusters=k, init="probability_based").fit(x)
+    # cdist on other splittings: tests/spatial/test_distances.py:190-205
+    with pytest.raises(NotImplementedError):
+        hb.spatial.cdist(x, x)
 
 
 def test_array_factory_split_semantics():
