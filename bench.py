@@ -125,6 +125,11 @@ def timed_cpu_reference(n_sample: int, d: int, k: int, dtype, steps: int, warmup
     from heat_b200.synthetic import blobs_shard, initial_centroids
     from oracle import kmeans_oracle as orc
 
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank; only rank 0 runs this)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     x, _ = blobs_shard(n_sample, d, k if kind == "kmeans" else 16, dtype=dtype)
     if kind == "cdist":
         y = torch.randn(k, d, dtype=dtype)
