@@ -223,6 +223,9 @@ class KMeans(BaseEstimator):
         """Reference: heat/cluster/_kcluster.py:398-415."""
         if not isinstance(x, DNDarray):
             raise ValueError(f"input needs to be a ht.DNDarray, but was  {type(x)}")
+        if x.larray.is_cuda:
+            # the library caches |x| bounds per matrix *address*; a caller may have rewritten x in place since the fit
+            _engine.get_engine(x.larray.device).cache_reset()
         return self._assign_to_cluster(x, eval_functional_value=True)
 
     def fit_predict(self, x: DNDarray) -> DNDarray:

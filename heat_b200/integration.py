@@ -101,6 +101,8 @@ def install() -> bool:
         eng = _engine.get_engine(dev)
         labels = torch.empty((xl.shape[0], 1), dtype=torch.int64, device=dev)
         fv = torch.zeros(1, dtype=torch.float64, device=dev) if eval_functional_value else None
+        if eval_functional_value:
+            eng.cache_reset()  # predict: x may have been rewritten in place since the fit (bounds are cached per address)
         eng.assign(xl, c.to(dev).contiguous(), labels, fv)
         if eval_functional_value:
             if x.split is not None and x.comm.size > 1:
