@@ -26,7 +26,7 @@ SIGNATURES = {
     "hk_lloyd_accumulate": (
         c_int,
         [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
-         c_int, c_void_p],
+         c_void_p, c_int64, c_int, c_void_p],
     ),
     "hk_lloyd_finalize": (
         c_int,
@@ -36,12 +36,18 @@ SIGNATURES = {
     "hk_lloyd_step": (
         c_int,
         [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
-         c_int, c_double, c_void_p, c_void_p, c_int, c_int, c_void_p],
+         c_int, c_double, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p],
     ),
+    "hk_lloyd_run": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_double,
+         c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_void_p],
+    ),
+    "hk_row_ws_bytes": (c_int64, [c_int64]),
     "hk_assign": (
         c_int,
         [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
-         c_int, c_void_p],
+         c_void_p, c_int64, c_int, c_void_p],
     ),
     "hk_cdist": (
         c_int,
@@ -52,7 +58,12 @@ SIGNATURES = {
     "hk_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "hk_comm_destroy": (c_int, [c_void_p]),
     "hk_allreduce_f64": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
-    "hk_cache_reset": (c_int, [c_void_p]),
+    "hk_comm_peer_export": (c_int, [c_void_p, c_int64, c_void_p]),
+    "hk_comm_peer_import": (c_int, [c_void_p, c_void_p]),
+    "hk_comm_mode": (c_int, [c_void_p]),
+    "hk_stats_read": (c_int, [c_void_p, POINTER(c_int64)]),
+    "hk_graph_enable": (c_int, [c_void_p, c_int]),
+    "hk_graph_launch_count": (c_int64, [c_void_p]),
     "hk_launch_count": (c_int64, [c_void_p]),
     "hk_last_variant": (c_char_p, [c_void_p]),
     "hk_profile_enable": (c_int, [c_void_p, c_int]),

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import engine as _engine
-from .communication import get_comm
+from .communication import IN_PLACE, get_comm
 from .dndarray import DNDarray, array
 
 _FLOATS = (torch.float32, torch.float64)
@@ -141,28 +141,34 @@ class KMeans(BaseEstimator):
         distributed = x.split is not None and x.comm.is_distributed()
         if distributed:
             eng.init_comm(x.comm)
-        eng.cache_reset()  # per-matrix bounds are recomputed in the first pass of every fit
 
         centers0 = self._cluster_centers.larray.to(dev)
         c_dtype = centers0.dtype if centers0.dtype in _FLOATS else cdtype
+        if c_dtype == torch.float64 and cdtype == torch.float32:
+            # float32 data + float64 centroids: the reference promotes both operands of cdist to float64
+            # (distance.py:392-395), so distances, sums and functional value are float64
+            xl = xl.to(torch.float64)
+            cdtype = torch.float64
         k, d = centers0.shape
         use_tol = self.tol is not None
         tol_cmp = float(np.float32(self.tol)) if use_tol else 0.0
         state = torch.zeros(4, dtype=torch.int32, device=dev)
         max_iter = int(self.max_iter)
         chunk = max_iter if not use_tol else max(1, int(self.sync_every))
+        # per-matrix workspace of the tensor-core path (|x| bounds), tied to this fit's view of the rows
+        row_ws = eng.row_workspace(xl.shape[0])
 
         if c_dtype == cdtype:
-            # fused step: accumulate -> ncclAllReduce -> finalize, centroids updated in place
+            # fused step: pass over the shard -> finish kernel (slot reduce, peer-memory sum over the ranks, finalize),
+            # centroids updated in place; `chunk` iterations per call, replayed from a CUDA graph inside the library
             c = centers0.to(cdtype).contiguous().clone()
             c_prev = torch.empty_like(c)
             shift2 = torch.zeros((), dtype=cdtype, device=dev)
             done = 0
             while done < max_iter:
                 todo = min(chunk, max_iter - done)
-                for _ in range(todo):
-                    eng.lloyd_step(xl, c, c_prev, use_tol, tol_cmp, shift2, state, distributed,
-                                   path=self.kernel_path)
+                eng.lloyd_run(xl, c, c_prev, use_tol, tol_cmp, shift2, state, distributed, todo,
+                              path=self.kernel_path, row_ws=row_ws)
                 done += todo
                 if use_tol and done < max_iter:
                     if int(state[0].item()):  # one host sync per `sync_every` iterations
@@ -179,7 +185,7 @@ class KMeans(BaseEstimator):
             it = 0
             while it < max_iter:
                 pre.copy_(c_lo)
-                eng.lloyd_accumulate(xl, pre, part, path=self.kernel_path)
+                eng.lloyd_accumulate(xl, pre, part, path=self.kernel_path, row_ws=row_ws)
                 if distributed:
                     eng.allreduce_f64(part)
                 eng.lloyd_finalize(part, c_lo, c_lo, use_tol, tol_cmp, shift2, state)
@@ -194,7 +200,7 @@ class KMeans(BaseEstimator):
 
         # labels of the last iteration, i.e. against its pre-update centroids (quirk Q5)
         labels = torch.empty((xl.shape[0], 1), dtype=torch.int64, device=dev)
-        eng.assign(xl, pre.to(cdtype), labels, path=self.kernel_path)
+        eng.assign(xl, pre.to(cdtype), labels, path=self.kernel_path, row_ws=row_ws)
 
         comm = x.comm
         self._cluster_centers = DNDarray(centers, (k, d), centers.dtype, None, dev, comm, True)
@@ -207,7 +213,11 @@ class KMeans(BaseEstimator):
         xl, cdtype = _device_operands(x)
         dev = xl.device
         eng = _engine.get_engine(dev)
-        c = self._cluster_centers.larray.to(device=dev, dtype=cdtype).contiguous()
+        c = self._cluster_centers.larray.to(dev)
+        if c.dtype == torch.float64 and cdtype == torch.float32:  # promotion of distance.py:392-395
+            xl = xl.to(torch.float64)
+            cdtype = torch.float64
+        c = c.to(cdtype).contiguous()
         labels = torch.empty((xl.shape[0], 1), dtype=torch.int64, device=dev)
         fv = torch.zeros(1, dtype=torch.float64, device=dev) if eval_functional_value else None
         eng.assign(xl, c, labels, fv, path=self.kernel_path)
@@ -223,9 +233,6 @@ class KMeans(BaseEstimator):
         """Reference: heat/cluster/_kcluster.py:398-415."""
         if not isinstance(x, DNDarray):
             raise ValueError(f"input needs to be a ht.DNDarray, but was  {type(x)}")
-        if x.larray.is_cuda:
-            # the library caches |x| bounds per matrix *address*; a caller may have rewritten x in place since the fit
-            _engine.get_engine(x.larray.device).cache_reset()
         return self._assign_to_cluster(x, eval_functional_value=True)
 
     def fit_predict(self, x: DNDarray) -> DNDarray:
@@ -254,11 +261,14 @@ def _gather_rows(x: DNDarray, idx: torch.Tensor) -> DNDarray:
     if x.split is None:
         out.copy_(x.larray[idx.to(x.larray.device)])
     else:
-        off, _, _ = x.comm.chunk(x.shape, 0)
+        # true row offset of this shard: exclusive scan of the local row counts (arrays built with is_split=0
+        # need not follow the balanced partition of comm.chunk)
         n_loc = x.larray.shape[0]
+        counts = [int.from_bytes(b, "little") for b in x.comm.allgather_bytes(int(n_loc).to_bytes(8, "little"))]
+        off = sum(counts[: x.comm.rank])
         for j, g in enumerate(idx.tolist()):
             if off <= g < off + n_loc:
                 out[j] = x.larray[g - off]
         if x.comm.is_distributed():
-            x.comm.Allreduce("IN_PLACE", out)
+            x.comm.Allreduce(IN_PLACE, out)
     return DNDarray(out, (k, d), out.dtype, None, out.device, x.comm, True)

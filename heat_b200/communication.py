@@ -4,8 +4,9 @@ Mirrors the parts of ``heat.core.communication`` this path touches
 (/root/reference/heat/core/communication.py): the ``Communication`` interface (:80-123 —
 ``is_distributed``, ``chunk``), ``rank``/``size`` and the call-site convention
 ``comm.Allreduce(MPI.IN_PLACE, tensor, MPI.SUM)`` (heat/core/_operations.py:510).  The reduction of
-the per-iteration k x (d+1) partials does not go through here on the GPU path: it is issued by
-``hk_lloyd_step`` itself (ncclAllReduce on the kernel's stream, see csrc/hk_comm.cu).
+the per-iteration k x (d+1) partials does not go through here on the GPU path: ``hk_lloyd_step`` exchanges them
+inside its finish kernel through peer-mapped GPU memory (csrc/hk_finalize.cu, csrc/hk_comm.cu); this class only
+carries the bootstrap (NCCL id, cudaIpc handles) and small host-side collectives.
 """
 from __future__ import annotations
 
@@ -15,7 +16,16 @@ from typing import Optional, Tuple
 
 import torch
 
-IN_PLACE = "IN_PLACE"
+
+
+class _InPlace:
+    """Sentinel for ``comm.Allreduce(IN_PLACE, buf, SUM)`` (mpi4py's ``MPI.IN_PLACE``)."""
+
+    def __repr__(self):
+        return "IN_PLACE"
+
+
+IN_PLACE = _InPlace()
 SUM = "SUM"
 
 
@@ -80,7 +90,7 @@ class ProcessGroupCommunication(Communication):
         """In-place sum over ranks (communication.py:1089-1110); np == 1 short-circuits (:1064)."""
         if op != SUM:
             raise NotImplementedError("only SUM is used on this path")
-        if sendbuf is not IN_PLACE:
+        if sendbuf is not IN_PLACE and not (isinstance(sendbuf, str) and sendbuf == "IN_PLACE"):
             recvbuf.copy_(sendbuf)
         if self.size > 1:
             self._dist.all_reduce(recvbuf, op=self._dist.ReduceOp.SUM, group=self.group)
@@ -99,6 +109,14 @@ class ProcessGroupCommunication(Communication):
         parts = [torch.empty((cmax,) + tail, dtype=local.dtype, device=local.device) for _ in counts]
         self._dist.all_gather(parts, mine, group=self.group)
         return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+    def allgather_bytes(self, payload: bytes) -> list:
+        """Every rank's ``payload`` in rank order (small host-side objects: IPC handles, row counts)."""
+        if self.size == 1:
+            return [payload]
+        out = [None] * self.size
+        self._dist.all_gather_object(out, payload, group=self.group)
+        return out
 
     def bcast_bytes(self, payload: Optional[bytes], root: int = 0) -> bytes:
         if self.size == 1:

@@ -28,10 +28,25 @@ static int grow(void** p, size_t* have, size_t need) {
 }
 int ensure_part(Handle* h, size_t bytes) { return grow((void**)&h->part, &h->part_bytes, bytes); }
 int ensure_red(Handle* h, size_t bytes) { return grow((void**)&h->red, &h->red_bytes, bytes); }
+int ensure_stats(Handle* h) {
+    if (h->stats) return 0;
+    HK_CUDA(cudaMalloc(&h->stats, 8 * sizeof(unsigned long long)));
+    HK_CUDA(cudaMemset(h->stats, 0, 8 * sizeof(unsigned long long)));
+    return 0;
+}
 
 int comm_unique_id(void* id128);
 int comm_init(Handle* h, int nranks, int rank, const void* id128);
 int comm_destroy(Handle* h);
+int comm_peer_export(Handle* h, int64_t cap, void* handle64);
+int comm_peer_import(Handle* h, const void* handles);
+
+static int ensure_fin_sync(Handle* h) {
+    if (h->fin_sync) return 0;
+    HK_CUDA(cudaMalloc(&h->fin_sync, 2 * sizeof(unsigned int)));
+    HK_CUDA(cudaMemset(h->fin_sync, 0, 2 * sizeof(unsigned int)));
+    return 0;
+}
 
 static int check_common(const char* fn, hk_handle_t h, const void* X, int64_t n, int d, int64_t ldx,
                         int dtype, const void* C, int k) {
@@ -107,7 +122,9 @@ int hk_destroy(hk_handle_t hh) {
     if (h->part) cudaFree(h->part);
     if (h->red) cudaFree(h->red);
     if (h->tc_scratch) cudaFree(h->tc_scratch);
-    if (h->xb) cudaFree(h->xb);
+    if (h->stats) cudaFree(h->stats);
+    if (h->fin_sync) cudaFree(h->fin_sync);
+    if (h->run_graph) cudaGraphExecDestroy(h->run_graph);
     delete h;
     return 0;
 }
@@ -127,8 +144,8 @@ int hk_chunk(int64_t n_global, int nranks, int rank, int64_t* offset, int64_t* r
 }
 
 int hk_lloyd_accumulate(hk_handle_t hh, const void* X, int64_t n_local, int d, int64_t ldx, int dtype,
-                        const void* C, int k, void* labels, int label_kind, double* partials, int path,
-                        void* stream) {
+                        const void* C, int k, void* labels, int label_kind, double* partials, void* row_ws,
+                        int64_t row_ws_bytes, int path, void* stream) {
     int rc = check_common("hk_lloyd_accumulate", hh, X, n_local, d, ldx, dtype, C, k);
     if (rc) return rc;
     HK_ARG(partials != nullptr, "hk_lloyd_accumulate: partials is null");
@@ -140,7 +157,8 @@ int hk_lloyd_accumulate(hk_handle_t hh, const void* X, int64_t n_local, int d, i
         h->variant = "empty";
         return 0;
     }
-    LloydArgs a{X, n_local, d, ldx, dtype, C, k, labels, label_kind, partials, nullptr, nullptr, path, st};
+    LloydArgs a{X,       n_local, d,      ldx,          dtype,   C,    k, labels, label_kind, partials, nullptr,
+                nullptr, row_ws,  row_ws_bytes, nullptr, path, st};
     return run_pass(h, a);
 }
 
@@ -156,34 +174,157 @@ int hk_lloyd_finalize(hk_handle_t hh, const double* partials, const void* C_in, 
                            state, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int hk_lloyd_step(hk_handle_t hh, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, void* C,
-                  void* C_prev, int k, void* labels, int label_kind, int use_tol, double tol_cmp,
-                  void* shift2_out, int32_t* state, int allreduce, int path, void* stream) {
-    int rc = check_common("hk_lloyd_step", hh, X, n_local, d, ldx, dtype, C, k);
-    if (rc) return rc;
-    Handle* h = reinterpret_cast<Handle*>(hh);
-    HK_CUDA(cudaSetDevice(h->device));
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+// one Lloyd step on stream st: pass over X, then ONE finish launch (slot reduce -> peer exchange -> finalize); the
+// reduce / ncclAllReduce / finalize sequence remains as the fallback when the peers are not mapped
+static int step_impl(Handle* h, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, void* C, void* C_prev,
+                     int k, void* labels, int label_kind, int use_tol, double tol_cmp, void* shift2_out,
+                     int32_t* state, int allreduce, void* row_ws, int64_t row_ws_bytes, int path, cudaStream_t st) {
     const size_t len = (size_t)k * (d + 1);
-    rc = ensure_red(h, len * sizeof(double));
+    int rc = ensure_red(h, len * sizeof(double));
     if (rc) return rc;
+    rc = ensure_fin_sync(h);
+    if (rc) return rc;
+    const bool exchange = allreduce && h->nranks > 1;
+    const bool fused = !exchange || (h->peer_ready && len <= h->peer_cap);
+    SlotInfo slots;
     if (n_local == 0) {
         HK_CUDA(cudaMemsetAsync(h->red, 0, len * sizeof(double), st));
         h->variant = "empty";
     } else {
-        LloydArgs a{X, n_local, d, ldx, dtype, C, k, labels, label_kind, h->red, nullptr, state, path, st};
+        LloydArgs a{X,     n_local, d,            ldx,                       dtype, C, k, labels, label_kind, h->red, nullptr,
+                    state, row_ws,  row_ws_bytes, fused ? &slots : nullptr, path,  st};
         rc = run_pass(h, a);
         if (rc) return rc;
     }
-    if (allreduce) {
+    if (!fused) {
         rc = comm_allreduce_f64(h, h->red, (int64_t)len, st);
         if (rc) return rc;
+        return launch_finalize(h, h->red, C, C, C_prev, k, d, dtype, use_tol, tol_cmp, shift2_out, state, st);
     }
-    return launch_finalize(h, h->red, C, C, C_prev, k, d, dtype, use_tol, tol_cmp, shift2_out, state, st);
+    FinishParams fp{};
+    fp.fsum = slots.fsum;
+    fp.fcnt = slots.fcnt;
+    fp.nslots = slots.nslots;
+    fp.slot_stride = slots.slot_stride;
+    fp.nblocks = slots.nblocks;
+    fp.partials_in = h->red;
+    fp.k = k;
+    fp.d = d;
+    fp.red = h->red;
+    fp.partials_out = nullptr;
+    fp.nranks = exchange ? h->nranks : 1;
+    fp.rank = exchange ? h->rank : 0;
+    for (int r = 0; r < fp.nranks && exchange; ++r) {
+        fp.mbox[r] = h->peer_mbox[r];
+        fp.flags[r] = h->peer_flags[r];
+    }
+    fp.cap = h->peer_cap;
+    fp.ticket = h->fin_sync;
+    fp.epoch = h->fin_sync + 1;
+    fp.C_in = C;
+    fp.C_out = C;
+    fp.C_prev = C_prev;
+    fp.use_tol = use_tol;
+    fp.tol_cmp = tol_cmp;
+    fp.shift2_out = shift2_out;
+    fp.state = state;
+    return launch_finish(h, fp, dtype, st);
+}
+
+int hk_lloyd_step(hk_handle_t hh, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, void* C,
+                  void* C_prev, int k, void* labels, int label_kind, int use_tol, double tol_cmp,
+                  void* shift2_out, int32_t* state, int allreduce, void* row_ws, int64_t row_ws_bytes, int path,
+                  void* stream) {
+    int rc = check_common("hk_lloyd_step", hh, X, n_local, d, ldx, dtype, C, k);
+    if (rc) return rc;
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    HK_CUDA(cudaSetDevice(h->device));
+    return step_impl(h, X, n_local, d, ldx, dtype, C, C_prev, k, labels, label_kind, use_tol, tol_cmp, shift2_out, state,
+                     allreduce, row_ws, row_ws_bytes, path, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// `iters` Lloyd steps enqueued by one call.  The first step runs eagerly (it may grow scratch buffers and fills the
+// row workspace); the remaining ones are captured ONCE into a CUDA graph (2 kernel nodes per step) that is cached in the
+// handle and replayed for as long as the call shape stays the same, so a fit costs one graph launch per `sync_every`
+// iterations instead of 2 x sync_every kernel launches from Python.
+int hk_lloyd_run(hk_handle_t hh, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, void* C, void* C_prev,
+                 int k, int use_tol, double tol_cmp, void* shift2_out, int32_t* state, int allreduce, void* row_ws,
+                 int64_t row_ws_bytes, int path, int iters, void* stream) {
+    int rc = check_common("hk_lloyd_run", hh, X, n_local, d, ldx, dtype, C, k);
+    if (rc) return rc;
+    HK_ARG(iters >= 0, "hk_lloyd_run: iters < 0");
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    HK_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    auto one = [&]() {
+        return step_impl(h, X, n_local, d, ldx, dtype, C, C_prev, k, nullptr, HK_LABEL_NONE, use_tol, tol_cmp, shift2_out,
+                         state, allreduce, row_ws, row_ws_bytes, path, st);
+    };
+    const size_t len = (size_t)k * (d + 1);
+    const bool exchange = allreduce && h->nranks > 1;
+    const bool graphable = !h->profile && !h->no_graph && iters >= 3 && st != nullptr &&
+                           (!exchange || (h->peer_ready && len <= h->peer_cap));
+    if (!graphable) {
+        for (int i = 0; i < iters; ++i) {
+            rc = one();
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    uint64_t tol_bits;
+    memcpy(&tol_bits, &tol_cmp, sizeof(tol_bits));
+    std::vector<uint64_t> key = {(uint64_t)(uintptr_t)X, (uint64_t)n_local, (uint64_t)d, (uint64_t)ldx, (uint64_t)dtype,
+                                 (uint64_t)(uintptr_t)C, (uint64_t)(uintptr_t)C_prev, (uint64_t)k, (uint64_t)use_tol,
+                                 tol_bits, (uint64_t)(uintptr_t)shift2_out, (uint64_t)(uintptr_t)state,
+                                 (uint64_t)allreduce, (uint64_t)(uintptr_t)row_ws, (uint64_t)row_ws_bytes, (uint64_t)path,
+                                 (uint64_t)(uintptr_t)st, (uint64_t)h->nranks, (uint64_t)(uintptr_t)h->part,
+                                 (uint64_t)(uintptr_t)h->red};
+    int done = 0;
+    if (!(h->run_graph && h->run_graph_key == key)) {
+        rc = one();  // eager: allocations, function attributes, row workspace
+        if (rc) return rc;
+        done = 1;
+        key[18] = (uint64_t)(uintptr_t)h->part;
+        key[19] = (uint64_t)(uintptr_t)h->red;
+    }
+    const int chunk = iters - done;
+    if (chunk <= 0) return 0;
+    if (!(h->run_graph && h->run_graph_key == key && h->run_graph_iters == chunk)) {
+        if (h->run_graph) {
+            cudaGraphExecDestroy(h->run_graph);
+            h->run_graph = nullptr;
+        }
+        cudaGraph_t g = nullptr;
+        HK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < chunk && rc == 0; ++i) rc = one();
+        const cudaError_t ce = cudaStreamEndCapture(st, &g);
+        if (rc || ce != cudaSuccess) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            if (rc) return rc;
+            set_error("hk_lloyd_run: stream capture failed: %s", cudaGetErrorString(ce));
+            return 1000 + (int)ce;
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&h->run_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) {
+            h->run_graph = nullptr;
+            set_error("hk_lloyd_run: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+            return 1000 + (int)ie;
+        }
+        h->run_graph_key = key;
+        h->run_graph_iters = chunk;
+        h->graph_builds++;
+    }
+    HK_CUDA(cudaGraphLaunch(h->run_graph, st));
+    h->launches += 2 * (int64_t)chunk;
+    h->graph_launches++;
+    return 0;
 }
 
 int hk_assign(hk_handle_t hh, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, const void* C,
-              int k, void* labels, int label_kind, double* min_d2_sum, int path, void* stream) {
+              int k, void* labels, int label_kind, double* min_d2_sum, void* row_ws, int64_t row_ws_bytes, int path,
+              void* stream) {
     int rc = check_common("hk_assign", hh, X, n_local, d, ldx, dtype, C, k);
     if (rc) return rc;
     Handle* h = reinterpret_cast<Handle*>(hh);
@@ -194,7 +335,8 @@ int hk_assign(hk_handle_t hh, const void* X, int64_t n_local, int d, int64_t ldx
         h->variant = "empty";
         return 0;
     }
-    LloydArgs a{X, n_local, d, ldx, dtype, C, k, labels, label_kind, nullptr, min_d2_sum, nullptr, path, st};
+    LloydArgs a{X,       n_local, d,            ldx,     dtype, C,  k, labels, label_kind, nullptr, min_d2_sum,
+                nullptr, row_ws,  row_ws_bytes, nullptr, path,  st};
     return run_pass(h, a);
 }
 
@@ -222,6 +364,20 @@ int hk_comm_init(hk_handle_t hh, int nranks, int rank, const void* id128) {
     HK_ARG(nranks == 1 || id128 != nullptr, "hk_comm_init: null id");
     return comm_init(reinterpret_cast<Handle*>(hh), nranks, rank, id128);
 }
+int hk_comm_peer_export(hk_handle_t hh, int64_t cap_doubles, void* handle64) {
+    HK_ARG(hh != nullptr, "hk_comm_peer_export: null handle");
+    return comm_peer_export(reinterpret_cast<Handle*>(hh), cap_doubles, handle64);
+}
+int hk_comm_peer_import(hk_handle_t hh, const void* handles) {
+    HK_ARG(hh != nullptr, "hk_comm_peer_import: null handle");
+    return comm_peer_import(reinterpret_cast<Handle*>(hh), handles);
+}
+int hk_comm_mode(hk_handle_t hh) {
+    if (!hh) return 0;
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (h->nranks <= 1) return 0;
+    return h->peer_ready ? 2 : 1;
+}
 int hk_comm_destroy(hk_handle_t hh) {
     if (!hh) return 0;
     return comm_destroy(reinterpret_cast<Handle*>(hh));
@@ -232,14 +388,34 @@ int hk_allreduce_f64(hk_handle_t hh, double* buf, int64_t count, void* stream) {
                               reinterpret_cast<cudaStream_t>(stream));
 }
 
+int hk_graph_enable(hk_handle_t hh, int enable) {
+    HK_ARG(hh != nullptr, "hk_graph_enable: null handle");
+    reinterpret_cast<Handle*>(hh)->no_graph = enable == 0;
+    return 0;
+}
+int64_t hk_graph_launch_count(hk_handle_t hh) { return hh ? reinterpret_cast<Handle*>(hh)->graph_launches : 0; }
+
 int64_t hk_launch_count(hk_handle_t hh) { return hh ? reinterpret_cast<Handle*>(hh)->launches : 0; }
 const char* hk_last_variant(hk_handle_t hh) {
     return hh ? reinterpret_cast<Handle*>(hh)->variant.c_str() : "";
 }
 
-int hk_cache_reset(hk_handle_t hh) {
-    HK_ARG(hh != nullptr, "hk_cache_reset: null handle");
-    reinterpret_cast<Handle*>(hh)->xb_X = nullptr;
+int64_t hk_row_ws_bytes(int64_t n_local) {
+    if (n_local < 0) return 0;
+    return (int64_t)(((n_local + 127) / 128 + 4) * sizeof(float));
+}
+
+int hk_stats_read(hk_handle_t hh, int64_t* out6) {
+    HK_ARG(hh != nullptr && out6 != nullptr, "hk_stats_read: null argument");
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    for (int i = 0; i < 6; ++i) out6[i] = 0;
+    if (!h->stats) return 0;
+    HK_CUDA(cudaSetDevice(h->device));
+    HK_CUDA(cudaDeviceSynchronize());
+    unsigned long long v[6];
+    HK_CUDA(cudaMemcpy(v, h->stats, sizeof(v), cudaMemcpyDeviceToHost));
+    HK_CUDA(cudaMemset(h->stats, 0, sizeof(v)));
+    for (int i = 0; i < 6; ++i) out6[i] = (int64_t)v[i];
     return 0;
 }
 

@@ -1,10 +1,14 @@
-// NCCL plumbing for the single per-iteration allreduce of the k x (d+1) partials.
+// Communicator of the Lloyd path: (a) the peer-memory mailbox the fused finish kernel exchanges the k x (d+1)
+// partials through (hk_finalize.cu; cudaIpc-mapped device memory of every rank of the box, NVLink/NVSwitch stores,
+// no collective call on the critical path) and (b) NCCL plumbing for the generic hk_allreduce_f64 (functional value,
+// unfused mixed-dtype path) and as the fallback when peer mapping is unavailable.
 // Replaces MPICommunication.Allreduce(MPI.IN_PLACE, t, MPI.SUM) as issued 2k times per Lloyd
 // iteration by heat/core/_operations.py:505-510 (heat/core/communication.py:1089-1110), which
 // stages CUDA tensors through the host.  Here: one ncclAllReduce on the kernel's stream, device
 // resident, over NVLink/NVSwitch.  libnccl is resolved with dlopen so that the library loads (and
 // its symbols can be checked) on machines without NCCL or a GPU.
 #include <dlfcn.h>
+#include <string.h>
 
 #include "hk_common.cuh"
 
@@ -74,6 +78,8 @@ int load_nccl() {
 
 }  // namespace
 
+int comm_destroy(Handle* h);
+
 int comm_unique_id(void* id128) {
     int rc = load_nccl();
     if (rc) return rc;
@@ -83,6 +89,7 @@ int comm_unique_id(void* id128) {
 
 int comm_init(Handle* h, int nranks, int rank, const void* id128) {
     HK_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "hk_comm_init: bad rank %d of %d", rank, nranks);
+    comm_destroy(h);  // a re-initialisation must not leak the previous communicator / mailbox
     h->nranks = nranks;
     h->rank = rank;
     if (nranks == 1) return 0;
@@ -97,7 +104,76 @@ int comm_init(Handle* h, int nranks, int rank, const void* id128) {
     return 0;
 }
 
+static void peer_release(Handle* h) {
+    for (int r = 0; r < HK_MAX_RANKS; ++r) {
+        if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->peer_opened[r]);
+        h->peer_opened[r] = nullptr;
+        h->peer_mbox[r] = nullptr;
+        h->peer_flags[r] = nullptr;
+    }
+    if (h->peer_base) cudaFree(h->peer_base);
+    h->peer_base = nullptr;
+    h->peer_cap = 0;
+    h->peer_ready = false;
+}
+
+static size_t peer_mbox_bytes(int nranks, size_t cap) { return (size_t)2 * nranks * cap * sizeof(double); }
+
+// allocate this rank's mailbox (cap doubles per [parity][source rank] slot) and export its IPC handle (64 bytes)
+int comm_peer_export(Handle* h, int64_t cap, void* handle64) {
+    HK_ARG(h->nranks > 1 && h->nranks <= HK_MAX_RANKS, "hk_comm_peer_export: needs 2..%d ranks (have %d)", HK_MAX_RANKS,
+           h->nranks);
+    HK_ARG(cap >= 1 && handle64 != nullptr, "hk_comm_peer_export: bad argument");
+    HK_CUDA(cudaSetDevice(h->device));
+    peer_release(h);
+    const size_t mb = peer_mbox_bytes(h->nranks, (size_t)cap);
+    const size_t total = mb + (size_t)2 * h->nranks * sizeof(uint32_t) + 256;
+    HK_CUDA(cudaMalloc(&h->peer_base, total));
+    HK_CUDA(cudaMemset(h->peer_base, 0, total));
+    HK_CUDA(cudaDeviceSynchronize());
+    h->peer_cap = (size_t)cap;
+    cudaIpcMemHandle_t ih;
+    HK_CUDA(cudaIpcGetMemHandle(&ih, h->peer_base));
+    static_assert(sizeof(ih) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &ih, 64);
+    return 0;
+}
+
+// map every peer's mailbox: handles = nranks x 64 bytes in rank order (as gathered by the host)
+int comm_peer_import(Handle* h, const void* handles) {
+    HK_ARG(h->peer_base != nullptr && handles != nullptr, "hk_comm_peer_import: export first");
+    HK_CUDA(cudaSetDevice(h->device));
+    const size_t mb = peer_mbox_bytes(h->nranks, h->peer_cap);
+    for (int r = 0; r < h->nranks; ++r) {
+        char* base = nullptr;
+        if (r == h->rank) {
+            base = reinterpret_cast<char*>(h->peer_base);
+        } else {
+            cudaIpcMemHandle_t ih;
+            memcpy(&ih, reinterpret_cast<const char*>(handles) + (size_t)r * 64, 64);
+            void* ptr = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+                cudaGetLastError();
+                for (int q = 0; q < h->nranks; ++q) {
+                    if (h->peer_opened[q]) cudaIpcCloseMemHandle(h->peer_opened[q]);
+                    h->peer_opened[q] = nullptr;
+                }
+                return 1000 + (int)e;
+            }
+            h->peer_opened[r] = ptr;
+            base = reinterpret_cast<char*>(ptr);
+        }
+        h->peer_mbox[r] = reinterpret_cast<double*>(base);
+        h->peer_flags[r] = reinterpret_cast<uint32_t*>(base + mb);
+    }
+    h->peer_ready = true;
+    return 0;
+}
+
 int comm_destroy(Handle* h) {
+    peer_release(h);
     if (h->nccl_comm && g_nccl.CommDestroy) {
         g_nccl.CommDestroy((NcclComm)h->nccl_comm);
         h->nccl_comm = nullptr;

@@ -30,6 +30,8 @@ void set_error(const char* fmt, ...);
         }                                  \
     } while (0)
 
+constexpr int HK_MAX_RANKS = 16;
+
 // ---- handle ------------------------------------------------------------------------------------
 struct Handle {
     int device = 0;
@@ -44,17 +46,29 @@ struct Handle {
     // tensor-core path scratch (TMA descriptors etc.)
     void* tc_scratch = nullptr;
     size_t tc_scratch_bytes = 0;
-    // per-tile |x|^2 bound cache of the tensor-core path, keyed by the matrix it was computed from
-    float* xb = nullptr;
-    size_t xb_bytes = 0;
-    const void* xb_X = nullptr;
-    int64_t xb_n = 0;
-    int xb_d = 0;
-    int64_t xb_ld = 0;
+    // cold-path counters of the tensor-core passes since the last hk_stats_read (device, 6 x u64)
+    unsigned long long* stats = nullptr;
     // communicator
     void* nccl_comm = nullptr;
     int nranks = 1;
     int rank = 0;
+    // peer-memory exchange of the fused finish (hk_finalize.cu): this rank's mailbox [2][nranks][peer_cap] doubles +
+    // flags [2][nranks] u32 in ONE allocation that is IPC-mapped by every peer; peer_mbox[r] / peer_flags[r] are the
+    // addresses of rank r's copy in THIS process (own entry = local pointers).  peer_ready: all peers are mapped.
+    void* peer_base = nullptr;
+    size_t peer_cap = 0;
+    double* peer_mbox[HK_MAX_RANKS] = {};
+    uint32_t* peer_flags[HK_MAX_RANKS] = {};
+    void* peer_opened[HK_MAX_RANKS] = {};
+    bool peer_ready = false;
+    // ticket + executed-exchange counter of the finish kernel (device, 2 x u32)
+    unsigned int* fin_sync = nullptr;
+    // CUDA graph of the last hk_lloyd_run call shape
+    cudaGraphExec_t run_graph = nullptr;
+    int run_graph_iters = 0;
+    bool no_graph = false;
+    int64_t graph_builds = 0, graph_launches = 0;
+    std::vector<uint64_t> run_graph_key;
     int64_t launches = 0;
     std::string variant;
     // optional event timing of the dominant kernel
@@ -78,8 +92,17 @@ inline void prof_end(Handle* h, cudaStream_t st) {
 
 int ensure_part(Handle* h, size_t bytes);
 int ensure_red(Handle* h, size_t bytes);
+int ensure_stats(Handle* h);
 
 // ---- kernel launchers (each returns an hk error code) -------------------------------------------
+// filled by the tensor-core pass when the caller asks it to leave the cross-CTA reduction to the finish kernel
+struct SlotInfo {
+    const double* fsum = nullptr;
+    const double* fcnt = nullptr;
+    int nslots = 0, slot_stride = 0, nblocks = 0;
+};
+
+
 struct LloydArgs {
     const void* X;
     int64_t n;
@@ -93,6 +116,9 @@ struct LloydArgs {
     double* partials;  // k*(d+1) doubles out (nullptr for assign-only)
     double* fv_out;    // optional: sum over rows of min d^2
     const int32_t* state;  // optional: state[0] != 0 -> the pass is skipped (fit already converged)
+    void* row_ws;          // optional caller-owned per-matrix workspace (hk_row_ws_bytes), zeroed when X changes
+    int64_t row_ws_bytes;
+    SlotInfo* slots;       // optional: the pass may leave its per-CTA slots unreduced and describe them here
     int path;
     cudaStream_t stream;
 };
@@ -104,6 +130,34 @@ int launch_lloyd_row128(Handle* h, const LloydArgs& a);  // exact FMA, rows of e
 bool row128_supported(const Handle* h, const LloydArgs& a);
 int launch_lloyd_bigk(Handle* h, const LloydArgs& a);  // fp32, k too large for the fused kernel: multi-pass
 bool bigk_supported(const Handle* h, const LloydArgs& a);
+
+// one launch for slot reduce -> cross-GPU sum over peer memory -> finalize (hk_finalize.cu)
+struct FinishParams {
+    // this rank's contribution: per-CTA slots of the tensor-core pass (fsum != nullptr) or a reduced vector
+    const double* fsum;
+    const double* fcnt;
+    int nslots, slot_stride, nblocks;
+    const double* partials_in;
+    int k, d;
+    double* red;           // [k*(d+1)] this rank's reduced partials
+    double* partials_out;  // optional: the globally reduced partials
+    // exchange (nranks == 1: none)
+    int nranks, rank;
+    double* mbox[HK_MAX_RANKS];
+    uint32_t* flags[HK_MAX_RANKS];
+    size_t cap;
+    unsigned int* ticket;
+    unsigned int* epoch;
+    // finalize
+    const void* C_in;
+    void* C_out;
+    void* C_prev;
+    int use_tol;
+    double tol_cmp;
+    void* shift2_out;
+    int32_t* state;
+};
+int launch_finish(Handle* h, FinishParams& p, int dtype, cudaStream_t stream);
 
 int launch_finalize(Handle* h, const double* partials, const void* C_in, void* C_out, void* C_prev,
                     int k, int d, int dtype, int use_tol, double tol_cmp, void* shift2_out,

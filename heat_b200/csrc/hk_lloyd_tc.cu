@@ -5,11 +5,18 @@
 // Why a filter: at k=64, d=32 the distance contraction costs 2*k = 128 FLOP per 4-byte element, three
 // times what the FP32 pipes can sustain at HBM speed, so x.c^T runs on the 5th-gen tensor cores
 // (tcgen05.mma kind::tf32 reads the fp32 tile in shared memory directly and ignores the low 13 mantissa
-// bits).  The TF32 result has a rigorous error bound  |s_j - (|c_j|^2 - 2 x.c_j)| <= E(x)  with
-//      E = 2*beta*|x|*max_j|c_j| + (d+3)*2^-23*(|x|^2 + max_j|c_j|^2),   beta = 1.05 * 2^-9,
-// so a row whose runner-up is more than 2E above the minimum has a certain label (identical to what the
-// exact fp32 formula of heat/spatial/distance.py:59-64 + first-index argmin would give); every other row
-// (near-ties, NaN/Inf) is re-evaluated with that exact formula over all centroids.  Labels are therefore
+// bits).  Distances are translation invariant in the centroid index: with mu = mean_j c_j and c'_j = c_j - mu,
+//      |c_j|^2 - 2 x.c_j  =  (|c_j|^2 - 2 x.c'_j) - 2 x.mu,   and  -2 x.mu  does not depend on j,
+// so the MMA operand holds the CENTRED centroids (the filter error scales with |x| * max|c'| instead of
+// |x| * max|c|, which is what matters for data far from the origin) while every exact evaluation uses the raw
+// values.  s_j = |c_j|^2 - 2 x.c'_j (TF32) differs from the exact fp32 formula value of
+// heat/spatial/distance.py:59-64 (minus terms constant in j) by at most
+//      E = 2*beta*|x|*max_j|c'_j| + (2d+6)*2^-23*(|x|^2 + max_j|c_j|^2 + max_j|c'_j|^2),   beta = 1.05 * 2^-9
+// (TF32 truncation of both operands; fp32 rounding of the reference formula and of the tensor-core accumulation),
+// so a row whose runner-up is more than 2E above the minimum has a certain label (identical to what the exact
+// formula + first-index argmin would give).  For every other row the exact argmin provably lies in the CANDIDATE
+// set {j : s_j < min + 2E}; only those (row, centroid) pairs are re-evaluated with the exact formula, spread over
+// the lanes of the warp.  Rows with NaN/Inf go through the exact formula over all centroids.  Labels are therefore
 // those of the exact-FMA path, the tensor cores only remove work.
 //
 // Warp roles per CTA (1 CTA per SM, persistent, static tile -> CTA map); all hand-offs are mbarriers with
@@ -80,8 +87,9 @@ struct TcParams {
     int num_tiles;
     const int32_t* state;
     uint32_t tmem_cols;
-    float* bounds;   // [num_tiles] per-tile max |x|^2, followed by one int "filled" flag
-    int want_write;  // 1: this launch fills `bounds`
+    float* bounds;   // caller-owned [num_tiles] per-tile max |x| + one int "filled" flag, or nullptr (no cache)
+    unsigned long long* stats;  // [6] cumulative counters: undecided rows, exact (row, centroid) pairs, rows sent through
+                                // the all-centroid formula, warps that entered the cold path, rows seen, passes
     // shared-memory layout (byte offsets from the 1024-aligned base), computed on the host
     uint32_t o_stages, o_B, o_Aext, o_Bext, o_cn, o_acc, o_lab, o_cnt, o_snap, o_bars, o_misc;
     unsigned long long* dbg;  // optional [grid][32 warps][8] cycle counters (HK_TC_DEBUG=1)
@@ -117,8 +125,8 @@ __host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sum
     if (sums) o += 32 * 4 * 4;
     L.bars = o;
     o += 8 * 96;  // mbarriers
-    L.misc = o;
-    o += 512;
+    L.misc = o;  // tmem slot, maxima, flags, fv partials, cold-path counters, mu[d]
+    o += 1024;
     L.total = o + 1024;  // slack for manual 1024-byte alignment of the base
     return L;
 }
@@ -132,21 +140,27 @@ __device__ __forceinline__ void store_label_tc(void* labels, int kind, int64_t r
         reinterpret_cast<unsigned char*>(labels)[row] = (unsigned char)lab;
 }
 
-// exact fp32 squared distance of the reference formula for (row, centroid j): operands come from the
-// swizzled tiles in shared memory (Bt holds -2*c, so the dot already carries the factor), features are
-// accumulated in ascending order.  fl(-2*dot) == -2*fl(dot): scaling by two is exact.
-__device__ __noinline__ float exact_d2(uint32_t xt, int row, uint32_t Bt, int nk, int j, int d, float xn,
-                                       float cnj) {
-    float dotm2 = 0.f;
+// exact fp32 squared distance of the reference formula (heat/spatial/distance.py:59-64) for (row, centroid j):
+// fl(fl(|x|^2 + |c_j|^2) - 2 fl(x.c_j)), features accumulated in ascending order with FMAs (the arithmetic of the
+// exact-FMA kernels).  x comes from the swizzled tile in shared memory, c from global memory (raw values, L1/L2
+// resident: the MMA operand in shared memory holds the centred ones).
+__device__ __forceinline__ float exact_pair(uint32_t xt, int row, const float* __restrict__ C, int j, int d, float cnj) {
+    float dot = 0.f, xn = 0.f;
+    const float4* cr = reinterpret_cast<const float4*>(C + (size_t)j * d);
     for (int f = 0; f < d; f += 4) {
         const float4 xv = lds_f4(xt + sw128_off(TM, row, f));
-        const float4 cv = lds_f4(Bt + sw128_off(nk, j, f));
-        dotm2 = fmaf(xv.x, cv.x, dotm2);
-        dotm2 = fmaf(xv.y, cv.y, dotm2);
-        dotm2 = fmaf(xv.z, cv.z, dotm2);
-        dotm2 = fmaf(xv.w, cv.w, dotm2);
+        const float4 cv = __ldg(cr + (f >> 2));
+        xn = fmaf(xv.x, xv.x, xn);
+        xn = fmaf(xv.y, xv.y, xn);
+        xn = fmaf(xv.z, xv.z, xn);
+        xn = fmaf(xv.w, xv.w, xn);
+        dot = fmaf(xv.x, cv.x, dot);
+        dot = fmaf(xv.y, cv.y, dot);
+        dot = fmaf(xv.z, cv.z, dot);
+        dot = fmaf(xv.w, cv.w, dot);
     }
-    return (xn + cnj) + dotm2;
+    const float d2 = fmaf(-2.f, dot, xn + cnj);
+    return d2 < 0.f ? 0.f : d2;
 }
 
 __device__ __noinline__ float row_norm2(uint32_t xt, int row, int d) {
@@ -161,6 +175,14 @@ __device__ __noinline__ float row_norm2(uint32_t xt, int row, int d) {
     return xn;
 }
 
+// torch.min semantics: a strictly smaller value wins, the first NaN wins and sticks
+__device__ __forceinline__ void take_min(float v, int j, float& best, int& bl) {
+    if (v < best || (v != v && best == best)) {
+        best = v;
+        bl = j;
+    }
+}
+
 enum { XN_COMPUTE = 0, XN_WRITE = 1, XN_READ = 2 };
 
 // cycle counters per role / per-tile timeline of CTA 0: compiled in with -DHK_TC_TIMING only, the hot loops of the
@@ -171,22 +193,112 @@ enum { XN_COMPUTE = 0, XN_WRITE = 1, XN_READ = 2 };
 #define TC_T(...)
 #endif
 
-// Cold path of the epilogue (rows the filter cannot decide, and the functional value): exact fp32 formula over
-// all centroids with torch.min tie/NaN semantics.  Out of line so that the hot loop stays small.
-__device__ __noinline__ int exact_label(uint32_t xt, int row, uint32_t a_B, int nk, int k, int d, float xr,
-                                        const float* cn, float* best_out) {
+// ---- cold path of the epilogue (out of line so that the hot loop stays small) ----------------------------------
+// Every lane hands in the candidate set of its row as two 32-column masks (mlo at column clo, mhi at column chi,
+// clo < chi; both zero: the lane has nothing to refine) or `full` (NaN/Inf, or candidates in more than two chunks:
+// exact formula over all k centroids).  Returns the first-index argmin of the exact formula over the candidates and
+// its value.  The (row, candidate) pairs of the whole warp are flattened over the lanes, so a warp with a few
+// undecided rows of a few candidates each pays for ONE exact evaluation, not for the longest per-lane chain.
+__device__ __noinline__ void refine_rows(uint32_t xt, int q, int lane, const float* __restrict__ C,
+                                         const float* __restrict__ cn, int k, int d, unsigned mlo, int clo,
+                                         unsigned mhi, int chi, bool full, int& lab, float& best_out, uint32_t a_stat) {
+    constexpr unsigned FULLM = 0xffffffffu;
+    const int row = q * 32 + lane;
+    const int cnt = __popc(mlo) + __popc(mhi);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULLM, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int excl = incl - cnt;
+    const int total = __shfl_sync(FULLM, incl, 31);
+    const int maxc = __reduce_max_sync(FULLM, cnt);
+    const int npass = (total + 31) >> 5;
     float best = INFINITY;
-    int bl = 0;
-    for (int j = 0; j < k; ++j) {
-        float d2 = exact_d2(xt, row, a_B, nk, j, d, xr, cn[j]);
-        d2 = d2 < 0.f ? 0.f : d2;
-        if (d2 < best || (d2 != d2 && best == best)) {
-            best = d2;
-            bl = j;
+    int bl = mlo ? clo + __ffs(mlo) - 1 : chi + __ffs(mhi) - 1;
+    unsigned rlo = mlo, rhi = mhi;  // candidates of this lane's row not consumed yet (ascending column order)
+    if (maxc * 5 <= npass * 12) {
+        // few candidates per row, many rows (e.g. predict: one candidate in every row): each lane walks its own
+        while (rlo | rhi) {
+            int j;
+            if (rlo) {
+                j = clo + __ffs(rlo) - 1;
+                rlo &= rlo - 1;
+            } else {
+                j = chi + __ffs(rhi) - 1;
+                rhi &= rhi - 1;
+            }
+            take_min(exact_pair(xt, row, C, j, d, cn[j]), j, best, bl);
+        }
+    } else {
+        for (int base = 0; base < total; base += 32) {
+            // lane p evaluates pair (base + p): its owner is the lane `own` with excl <= pair < incl
+            const int pr = base + lane;
+            int own = 0;
+#pragma unroll
+            for (int st = 16; st > 0; st >>= 1) {
+                const int t = __shfl_sync(FULLM, incl, own + st - 1);
+                if (t <= pr) own += st;
+            }
+            const bool valid = pr < total;
+            own &= 31;
+            const unsigned omlo = __shfl_sync(FULLM, mlo, own), omhi = __shfl_sync(FULLM, mhi, own);
+            const int oclo = __shfl_sync(FULLM, clo, own), ochi = __shfl_sync(FULLM, chi, own);
+            int idx = pr - __shfl_sync(FULLM, excl, own);
+            float v = INFINITY;
+            if (valid) {
+                unsigned m = omlo;
+                int cb = oclo;
+                const int nlo = __popc(omlo);
+                if (idx >= nlo) {
+                    idx -= nlo;
+                    m = omhi;
+                    cb = ochi;
+                }
+                for (int i = 0; i < idx; ++i) m &= m - 1;
+                const int j = cb + __ffs(m) - 1;
+                v = exact_pair(xt, q * 32 + own, C, j, d, cn[j]);
+            }
+            __syncwarp();
+            // hand the values back: the owner consumes its pairs of this pass in order
+            const int lo_p = max(excl, base), hi_p = min(incl, base + 32);
+            const int mine = max(hi_p - lo_p, 0);
+            const int np = __reduce_max_sync(FULLM, mine);
+            for (int i = 0; i < np; ++i) {
+                const float w = __shfl_sync(FULLM, v, (lo_p + i - base) & 31);
+                if (i < mine) {
+                    int j;
+                    if (rlo) {
+                        j = clo + __ffs(rlo) - 1;
+                        rlo &= rlo - 1;
+                    } else {
+                        j = chi + __ffs(rhi) - 1;
+                        rhi &= rhi - 1;
+                    }
+                    take_min(w, j, best, bl);
+                }
+            }
         }
     }
-    *best_out = best;
-    return bl;
+    if (full) {
+        best = INFINITY;
+        bl = 0;
+        for (int j = 0; j < k; ++j) take_min(exact_pair(xt, row, C, j, d, cn[j]), j, best, bl);
+    }
+    if (cnt > 0 || full) {
+        lab = bl;
+        best_out = best;
+    }
+    // counters (shared memory, this CTA): undecided rows, exact pairs, all-centroid rows, cold warps
+    const int nfull = __popc(__ballot_sync(FULLM, full));
+    const int nund = __popc(__ballot_sync(FULLM, cnt > 1 || full));
+    if (lane == 0) {
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_stat), "r"(nund) : "memory");
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_stat + 4), "r"(total + nfull * k) : "memory");
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_stat + 8), "r"(nfull) : "memory");
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_stat + 12), "r"(1) : "memory");
+    }
 }
 
 // SUMS: accumulate per-cluster sums (adds the accumulator warps); FQL2 = log2(d/4): lanes per row in the
@@ -213,9 +325,12 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     const uint32_t b_tfull = b_full + 48 * 8;
     const uint32_t b_tempty = b_full + 64 * 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.o_misc);
-    float* cmax_s = reinterpret_cast<float*>(smem + p.o_misc + 16);
+    float* cmax_s = reinterpret_cast<float*>(smem + p.o_misc + 16);   // max_j |c_j|
+    float* cpmax_s = reinterpret_cast<float*>(smem + p.o_misc + 20);  // max_j |c_j - mu|
     int* force_exact_s = reinterpret_cast<int*>(smem + p.o_misc + 32);
     double* fvred = reinterpret_cast<double*>(smem + p.o_misc + 64);  // [E_WARPS]
+    uint32_t* stat_s = reinterpret_cast<uint32_t*>(smem + p.o_misc + 256);  // [4] cold-path counters of this CTA
+    float* mu_s = reinterpret_cast<float*>(smem + p.o_misc + 512);    // [d] mean of the centroids
 
     const int tid = threadIdx.x;
     // warp-uniform for the compiler: the role code below computes addresses and descriptors in uniform registers
@@ -223,8 +338,9 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     const int lane = tid & 31;
     const uint32_t stage_bytes = (uint32_t)TM * d * 4;
     const int ntiles = p.num_tiles;
-    const int xn_mode =
-        p.want_write ? XN_WRITE : (reinterpret_cast<const int*>(p.bounds)[p.num_tiles] != 0 ? XN_READ : XN_COMPUTE);
+    const int xn_mode = p.bounds == nullptr
+                            ? XN_COMPUTE
+                            : (reinterpret_cast<const int*>(p.bounds)[p.num_tiles] != 0 ? XN_READ : XN_WRITE);
 
     // ---------------- one-time setup -------------------------------------------------------------------
     if (tid == 0) {
@@ -240,23 +356,13 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         mbar_fence_init();
         tma_prefetch_desc(&xmap);
         *cmax_s = 0.f;
+        *cpmax_s = 0.f;
         *force_exact_s = 0;
+        stat_s[0] = stat_s[1] = stat_s[2] = stat_s[3] = 0u;
     }
     if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
-    // operand B = -2*C: K-blocked, 128B-swizzled, rows >= k zero
-    for (int e = tid; e < nk * (d >> 2); e += blockDim.x) {
-        const int j = e / (d >> 2), f = (e - j * (d >> 2)) << 2;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < k) {
-            v = *reinterpret_cast<const float4*>(p.C + (size_t)j * d + f);
-            v.x *= -2.f;
-            v.y *= -2.f;
-            v.z *= -2.f;
-            v.w *= -2.f;
-        }
-        *reinterpret_cast<float4*>(smem + p.o_B + sw128_off(nk, j, f)) = v;
-    }
-    // seed operands: A_ext[r] = (1,1,1,0,...), B_ext[j] = three exact TF32 pieces of |c_j|^2
+    for (int f = tid; f < d; f += blockDim.x) mu_s[f] = 0.f;
+    // seed operand A_ext[r] = (1,1,1,0,...)
     for (int e = tid; e < 8 * 8; e += blockDim.x) {
         const int r = e >> 3, ch = e & 7;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -270,16 +376,34 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         for (int i = tid; i < E_WARPS * (2 * k + 1); i += blockDim.x) cz[i] = 0;
     }
     __syncthreads();
+    // mu = mean of the centroids (any vector would do: it only tightens the filter bound, so the summation order
+    // of the shared-memory float atomics does not matter)
+    {
+        const int nw = blockDim.x >> 5;
+        const float invk = 1.f / (float)k;
+        for (int f = lane; f < d; f += 32) {
+            float s = 0.f;
+            for (int j = warp; j < k; j += nw) s += p.C[(size_t)j * d + f];
+            atomicAdd(mu_s + f, s * invk);
+        }
+    }
+    __syncthreads();
+    // |c_j|^2 (raw: the exact formula and the seed use it) and |c_j - mu|^2; B_ext[j] = three exact TF32 pieces of |c_j|^2
     for (int j = tid; j < nk; j += blockDim.x) {
         float s = 3.0e38f;  // padded centroids can never win
         if (j < k) {
             s = 0.f;
+            float sp = 0.f;
             for (int f = 0; f < d; ++f) {
                 const float c = p.C[(size_t)j * d + f];
+                const float cp = c - mu_s[f];
                 s = fmaf(c, c, s);
+                sp = fmaf(cp, cp, sp);
             }
             if (!(s < INFINITY)) atomicExch(force_exact_s, 1);  // NaN/Inf centroid: exact path decides
-            atomicMax(reinterpret_cast<int*>(cmax_s), __float_as_int(sqrtf(s)));  // s >= 0: int order == float order
+            // s, sp >= 0: int order == float order
+            atomicMax(reinterpret_cast<int*>(cmax_s), __float_as_int(sqrtf(s) * 1.000001f));
+            atomicMax(reinterpret_cast<int*>(cpmax_s), __float_as_int(sqrtf(sp) * 1.000001f));
         }
         cn[j] = s;
         const float p1 = __uint_as_float(__float_as_uint(s) & 0xFFFFE000u);
@@ -292,13 +416,37 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             *reinterpret_cast<float4*>(smem + p.o_Bext + sw128_off(nk, j, ch << 2)) = v;
         }
     }
+    __syncthreads();
+    const float cmax = *cmax_s;
+    const bool force_exact = *force_exact_s != 0;
+    // centre only when it helps (it always does unless the centroids straddle the origin already)
+    const bool use_mu = !force_exact && (*cpmax_s < cmax);
+    const float cpmax = use_mu ? *cpmax_s : cmax;
+    // operand B = -2 * (c - mu): K-blocked, 128B-swizzled, rows >= k zero
+    for (int e = tid; e < nk * (d >> 2); e += blockDim.x) {
+        const int j = e / (d >> 2), f = (e - j * (d >> 2)) << 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < k) {
+            v = *reinterpret_cast<const float4*>(p.C + (size_t)j * d + f);
+            if (use_mu) {
+                const float4 m = *reinterpret_cast<const float4*>(mu_s + f);
+                v.x -= m.x;
+                v.y -= m.y;
+                v.z -= m.z;
+                v.w -= m.w;
+            }
+            v.x *= -2.f;
+            v.y *= -2.f;
+            v.z *= -2.f;
+            v.w *= -2.f;
+        }
+        *reinterpret_cast<float4*>(smem + p.o_B + sw128_off(nk, j, f)) = v;
+    }
     fence_proxy_async();  // operands were written with st.shared, tcgen05.mma reads them through the async proxy
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const float cmax = *cmax_s;
-    const bool force_exact = *force_exact_s != 0;
     TC_T(long long tw0 = 0, tw1 = 0, tw2 = 0; long long t0 = 0, t1 = 0, t2 = 0;)
 
     if (warp == 0) {
@@ -394,8 +542,9 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         const int row = q * 32 + lane;
         const uint32_t tlane = __shfl_sync(0xffffffffu, tmem_base, 0) + ((uint32_t)(q * 32) << 16);
         const float beta2 = 2.f * 1.05f * 0.001953125f;
-        const float gam = (float)(d + 3) * 1.1920929e-7f;
-        const float cmax2 = cmax * cmax;
+        const float gam = (float)(2 * d + 6) * 1.1920929e-7f;
+        const float cmax2 = cmax * cmax + cpmax * cpmax;
+        const uint32_t a_stat = sbase + p.o_misc + 256;
         const uint32_t a_ecnt = sbase + p.o_cnt + (uint32_t)we * (uint32_t)(k * 4);
         const uint32_t a_hist = sbase + p.o_cnt + (uint32_t)(E_WARPS * k * 4) + (uint32_t)we * (uint32_t)((k + 1) * 4);
         const uint32_t a_mmax_q = sbase + p.o_snap + (uint32_t)q * 4;
@@ -420,33 +569,34 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             // below order the accumulator warps after the TMA writes without a wait of their own.
             warp_wait(b_full + s * 8, ph, lane);
             if (xn_mode == XN_READ) {
-                xs = __ldg(p.bounds + tile);  // the cache holds sqrt(max |x|^2)
+                xs = __ldg(p.bounds + tile);  // the cache holds an upper bound of max |x| over the tile
                 xn = xs * xs;
             } else {
                 xn = row_norm2(xt, row, d);
-                xs = sqrtf(xn);
+                xs = sqrtf(xn) * 1.0000002f;
                 if (xn_mode == XN_WRITE) {
-                    float wm = xs * 1.0000002f;  // xs*xs must not round below xn
+                    float wm = xs * 1.0000002f;  // wm*wm must not round below xn
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
                     if (!(wm == wm)) wm = INFINITY;  // NaN rows: make the cached bound useless, not wrong
                     if (lane == 0) atomicMax(reinterpret_cast<int*>(p.bounds) + tile, __float_as_int(wm));
                 }
             }
-            const float E2 = 2.002f * (beta2 * xs * cmax + gam * (xn + cmax2));
+            const float E2 = 2.002f * (beta2 * xs * cpmax + gam * (xn + cmax2));
 
-            warp_wait(b_tfull + b * 8, bph, lane);  // accumulator ready: s_j = |c_j|^2 - 2 x.c_j (TF32)
+            warp_wait(b_tfull + b * 8, bph, lane);  // accumulator ready: s_j = |c_j|^2 - 2 x.c'_j (TF32)
             TC_T(t1 = clock64();
                  if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && i < 512) p.tl[i * 8 + 2] = clock64();)
             tc_fence_after();
             const uint32_t taddr = tlane + (uint32_t)(b * nk);
             // one sweep over the accumulator, 32 columns in registers at a time.  Per chunk: its minimum m_c and
-            // the mask of columns below m_c + 2E.  The chunk holding the global minimum has the right mask; the
-            // other chunks hold no candidate iff their minimum is at least 2E above it (else the row is
-            // ambiguous anyway: at least one candidate per such chunk).
-            float m_best = INFINITY, m_second = INFINITY;
-            unsigned mk_best = 0;
-            int c_best = 0;
+            // the mask of columns below m_c + 2E.  The two chunks with the smallest minima are kept: the chunk
+            // holding the global minimum has the exact candidate mask, the runner-up chunk a superset of its
+            // candidates (it holds none iff its minimum is at least 2E above the global one); candidates in a
+            // third chunk (m_third) send the row through the all-centroid formula.
+            float m_best = INFINITY, m_second = INFINITY, m_third = INFINITY;
+            unsigned mk_best = 0, mk_second = 0;
+            int c_best = 0, c_second = 0;
             for (int c0 = 0; c0 < nk; c0 += 32) {
                 uint32_t a[32];
                 tmem_ld32(taddr + (uint32_t)c0, a);
@@ -454,12 +604,20 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 const float mc = min32(a);
                 const unsigned mk = below_mask32(a, mc + E2);
                 if (mc < m_best) {
+                    m_third = m_second;
                     m_second = m_best;
+                    mk_second = mk_best;
+                    c_second = c_best;
                     m_best = mc;
                     mk_best = mk;
                     c_best = c0;
+                } else if (mc < m_second) {
+                    m_third = m_second;
+                    m_second = mc;
+                    mk_second = mk;
+                    c_second = c0;
                 } else {
-                    m_second = fminf(m_second, mc);
+                    m_third = fminf(m_third, mc);
                 }
             }
             tc_fence_before();
@@ -468,22 +626,36 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             TC_T(t2 = clock64();)
 
             // NaN minima compare false everywhere: the row is then undecided and the exact path takes it
-            const bool decided =
-                (m_second >= m_best + E2) && (__popc(mk_best) == 1) && !force_exact && (xn < INFINITY);
+            const float thr = m_best + E2;
+            const bool sec_in = m_second < thr;
+            const bool decided = !sec_in && (__popc(mk_best) == 1) && !force_exact && (E2 < INFINITY);
             int lab = c_best + __ffs(mk_best) - 1;
             if (!active) lab = k;
-            if (active && (!decided || want_fv)) {
-                // cold: undecided row (near-tie within the TF32 bound, NaN/Inf) or the functional value is wanted
+            const bool cold = active && (!decided || want_fv);
+            if (__any_sync(0xffffffffu, cold)) {
+                // cold: undecided rows (near-ties within the TF32 bound, NaN/Inf) or the functional value is wanted
                 mbar_wait_a(b_full + s * 8, ph);  // this thread is about to read the x tile itself
-                const float xr = row_norm2(xt, row, d);  // exact |x|^2 (the cached value is only a bound)
-                float best;
-                if (!decided) {
-                    lab = exact_label(xt, row, a_B, nk, k, d, xr, cn, &best);
-                } else {
-                    best = exact_d2(xt, row, a_B, nk, lab, d, xr, cn[lab]);
-                    best = best < 0.f ? 0.f : best;
+                const bool full = cold && (force_exact || !(E2 < INFINITY) || !(fabsf(m_best) < INFINITY) ||
+                                           (m_third < thr) || mk_best == 0u);
+                unsigned mlo = 0u, mhi = 0u;
+                int clo = 0, chi = 0;
+                if (cold && !full) {
+                    mlo = mk_best;
+                    clo = c_best;
+                    if (sec_in) {
+                        mhi = mk_second;
+                        chi = c_second;
+                        if (chi < clo) {
+                            mlo = mk_second;
+                            clo = c_second;
+                            mhi = mk_best;
+                            chi = c_best;
+                        }
+                    }
                 }
-                if (want_fv) {
+                float best = 0.f;
+                refine_rows(xt, q, lane, p.C, cn, k, d, mlo, clo, mhi, chi, full, lab, best, a_stat);
+                if (want_fv && cold) {
                     const float sq = sqrtf(best);
                     fv_acc += (double)(sq * sq);
                 }
@@ -706,6 +878,14 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             p.fv_part[blockIdx.x] = t;
         }
         if (xn_mode == XN_WRITE && blockIdx.x == 0) reinterpret_cast<int*>(p.bounds)[p.num_tiles] = 1;
+        if (p.stats != nullptr) {
+            for (int c = 0; c < 4; ++c)
+                if (stat_s[c]) atomicAdd(p.stats + c, (unsigned long long)stat_s[c]);
+            if (blockIdx.x == 0) {
+                atomicAdd(p.stats + 4, (unsigned long long)p.n);
+                atomicAdd(p.stats + 5, 1ull);
+            }
+        }
     }
 }
 
@@ -848,27 +1028,21 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
         p.o_misc = (uint32_t)L.misc;
     }
 
-    // per-tile |x| bound cache, keyed by the matrix identity (reset with hk_cache_reset)
-    const size_t need = ((size_t)p.num_tiles + 4) * sizeof(float);
-    const bool same = h->xb != nullptr && h->xb_X == a.X && h->xb_n == a.n && h->xb_d == a.d && h->xb_ld == a.ldx;
-    if (!same) {
-        if (h->xb_bytes < need) {
-            if (h->xb) HK_CUDA(cudaFree(h->xb));
-            h->xb = nullptr;
-            h->xb_bytes = 0;
-            HK_CUDA(cudaMalloc(&h->xb, need));
-            h->xb_bytes = need;
+    // per-tile |x| bound cache: caller-owned and tied to the content of X (see hk_row_ws_bytes); none -> per-row
+    // norms are recomputed in every pass
+    p.bounds = nullptr;
+    if (a.row_ws != nullptr) {
+        const size_t need = ((size_t)p.num_tiles + 4) * sizeof(float);
+        if ((size_t)a.row_ws_bytes < need || (reinterpret_cast<uintptr_t>(a.row_ws) & 3) != 0) {
+            set_error("lloyd_tc: row workspace too small or misaligned (%lld bytes given, %zu needed)",
+                      (long long)a.row_ws_bytes, need);
+            return -1;
         }
-        HK_CUDA(cudaMemsetAsync(h->xb, 0, need, a.stream));  // bounds are built with atomicMax; flag = 0
-        h->xb_X = a.X;
-        h->xb_n = a.n;
-        h->xb_d = a.d;
-        h->xb_ld = a.ldx;
-        p.want_write = 1;
-    } else {
-        p.want_write = 0;
+        p.bounds = reinterpret_cast<float*>(a.row_ws);
     }
-    p.bounds = h->xb;
+    rc = ensure_stats(h);
+    if (rc) return rc;
+    p.stats = h->stats;
 
     int grid = h->num_sms;
     if (grid > p.num_tiles) grid = p.num_tiles;
@@ -900,7 +1074,7 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
 
     char name[112];
     snprintf(name, sizeof(name), "tc<f32,d=%d,k=%d,S=%d,nbuf=%d,NA=%d,%s,%s>", a.d, a.k, pl.S, pl.nbuf, pl.NA,
-             sums ? "sums" : "assign", p.want_write ? "xn-write" : "xn-cached");
+             sums ? "sums" : "assign", p.bounds ? "xn-ws" : "xn-row");
     h->variant = name;
 
     if (!sums) {
@@ -950,7 +1124,14 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
             fprintf(stderr, "  A warp %2d: wait %.0f [%.0f per own tile]  rows %.0f [%.0f]  flush %.0f [%.0f]\n", w, acc[w][0],
                     acc[w][0] / an, acc[w][1], acc[w][1] / an, acc[w][2], acc[w][2] / an);
     }
-    if (sums) {
+    if (sums && a.slots != nullptr) {
+        // the caller's finish kernel reduces the slots (one launch for reduce + exchange + finalize)
+        a.slots->fsum = p.fsum;
+        a.slots->fcnt = p.fcnt;
+        a.slots->nslots = grid;
+        a.slots->slot_stride = pl.NA;
+        a.slots->nblocks = grid;
+    } else if (sums) {
         const int len = a.k * (a.d + 1);
         reduce_tc_kernel<<<(len + 31) / 32, 256, 0, a.stream>>>(p.fsum, p.fcnt, grid, pl.NA, grid, a.k, a.d, a.partials,
                                                                 a.state);

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import numpy as np
 import torch
 
-from .communication import Communication, get_comm, sanitize_comm
+from .communication import IN_PLACE, Communication, get_comm, sanitize_comm
 
 
 class DNDarray:
@@ -150,7 +150,7 @@ def array(obj, dtype: Optional[torch.dtype] = None, split: Optional[int] = None,
         n = torch.tensor([t.shape[0]], dtype=torch.int64)
         if comm.is_distributed():
             n = n.to(t.device if t.is_cuda else "cpu")
-            comm.Allreduce("IN_PLACE", n)
+            comm.Allreduce(IN_PLACE, n)
         gshape = (int(n.item()),) + tuple(t.shape[1:])
         return DNDarray(t, gshape, t.dtype, 0, t.device, comm, None)
     return DNDarray(t, tuple(t.shape), t.dtype, None, t.device, comm, True)

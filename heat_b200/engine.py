@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -40,6 +41,7 @@ class CudaEngine:
         check(self.lib.hk_create(ctypes.byref(h), idx), "hk_create")
         self.h = h
         self.comm_size = 1
+        self.comm_key = None
 
     def close(self):
         if getattr(self, "h", None):
@@ -53,9 +55,15 @@ class CudaEngine:
             pass
 
     # -- communicator ----------------------------------------------------------------------------------
+    #: partial vectors of up to this many doubles go through the peer-memory mailbox (k*(d+1) <= 256K covers
+    #: k=1024, d=128); longer ones use ncclAllReduce
+    PEER_CAP = 1 << 18
+
     def init_comm(self, comm) -> None:
-        """Create the NCCL communicator matching ``comm`` (rank/size); id travels over torch.distributed."""
-        if comm.size == self.comm_size:
+        """Create the communicator matching ``comm``: NCCL (id travels over torch.distributed) plus the
+        peer-memory mailbox of the fused finish kernel (cudaIpc handles gathered over torch.distributed)."""
+        key = (id(comm), comm.rank, comm.size)
+        if key == self.comm_key:
             return
         ident = None
         if comm.rank == 0:
@@ -64,12 +72,35 @@ class CudaEngine:
             ident = buf.raw
         ident = comm.bcast_bytes(ident, root=0)
         check(self.lib.hk_comm_init(self.h, comm.size, comm.rank, ctypes.c_char_p(ident)), "hk_comm_init")
+        self.comm_key = key
         self.comm_size = comm.size
+        if comm.size > 1 and os.environ.get("HK_NO_PEER", "0") != "1":
+            mine = ctypes.create_string_buffer(64)
+            rc = self.lib.hk_comm_peer_export(self.h, self.PEER_CAP, mine)
+            handles = comm.allgather_bytes(mine.raw if rc == 0 else b"\0" * 64)
+            oks = comm.allgather_bytes(bytes([1 if rc == 0 else 0]))
+            if all(o == b"\x01" for o in oks):
+                rc = self.lib.hk_comm_peer_import(self.h, ctypes.c_char_p(b"".join(handles)))
+            else:
+                rc = 1
+            oks = comm.allgather_bytes(bytes([1 if rc == 0 else 0]))  # also the barrier the mailbox needs
+            if not all(o == b"\x01" for o in oks):
+                # some rank could not map its peers: every rank drops to NCCL (the decision must be collective)
+                check(self.lib.hk_comm_init(self.h, comm.size, comm.rank, ctypes.c_char_p(ident)), "hk_comm_init")
+
+    def comm_mode(self) -> str:
+        return {0: "single", 1: "nccl", 2: "peer"}[int(self.lib.hk_comm_mode(self.h))]
 
     def allreduce_f64(self, buf: torch.Tensor) -> None:
         assert buf.dtype == torch.float64 and buf.is_contiguous()
         check(self.lib.hk_allreduce_f64(self.h, _ptr(buf), buf.numel(), _stream(self.device)),
               "hk_allreduce_f64")
+
+    def row_workspace(self, n_local: int) -> torch.Tensor:
+        """Zeroed per-matrix workspace for ``row_ws=`` (tied to the CONTENT of one matrix: make a new one, or
+        ``zero_()`` it, when the rows change)."""
+        nbytes = int(self.lib.hk_row_ws_bytes(int(n_local)))
+        return torch.zeros(max(nbytes, 4), dtype=torch.uint8, device=self.device)
 
     # -- hot path ----------------------------------------------------------------------------------------
     @staticmethod
@@ -85,13 +116,20 @@ class CudaEngine:
         if not c.is_contiguous():
             raise ValueError("centroids must be contiguous")
 
-    def lloyd_accumulate(self, x, c, partials, labels=None, path="auto"):
+    @staticmethod
+    def _ws(row_ws):
+        if row_ws is None:
+            return ctypes.c_void_p(0), 0
+        return ctypes.c_void_p(row_ws.data_ptr()), row_ws.numel() * row_ws.element_size()
+
+    def lloyd_accumulate(self, x, c, partials, labels=None, path="auto", row_ws=None):
         self._check_x(x, c)
         n, d = x.shape
         ldx = x.stride(0) if n > 1 else d
         lk = HK_LABEL_NONE if labels is None else _LK[labels.dtype]
+        wp, wb = self._ws(row_ws)
         check(self.lib.hk_lloyd_accumulate(self.h, _ptr(x), n, d, ldx, _DT[x.dtype], _ptr(c), c.shape[0],
-                                           _ptr(labels), lk, _ptr(partials), PATHS[path],
+                                           _ptr(labels), lk, _ptr(partials), wp, wb, PATHS[path],
                                            _stream(self.device)), "hk_lloyd_accumulate")
 
     def lloyd_finalize(self, partials, c_in, c_out, use_tol, tol_cmp, shift2, state):
@@ -100,22 +138,35 @@ class CudaEngine:
                                          _DT[c_in.dtype], int(use_tol), float(tol_cmp), _ptr(shift2),
                                          _ptr(state), _stream(self.device)), "hk_lloyd_finalize")
 
-    def lloyd_step(self, x, c, c_prev, use_tol, tol_cmp, shift2, state, allreduce, labels=None, path="auto"):
+    def lloyd_step(self, x, c, c_prev, use_tol, tol_cmp, shift2, state, allreduce, labels=None, path="auto",
+                   row_ws=None):
         self._check_x(x, c)
         n, d = x.shape
         ldx = x.stride(0) if n > 1 else d
         lk = HK_LABEL_NONE if labels is None else _LK[labels.dtype]
+        wp, wb = self._ws(row_ws)
         check(self.lib.hk_lloyd_step(self.h, _ptr(x), n, d, ldx, _DT[x.dtype], _ptr(c), _ptr(c_prev),
                                      c.shape[0], _ptr(labels), lk, int(use_tol), float(tol_cmp),
-                                     _ptr(shift2), _ptr(state), int(allreduce), PATHS[path],
+                                     _ptr(shift2), _ptr(state), int(allreduce), wp, wb, PATHS[path],
                                      _stream(self.device)), "hk_lloyd_step")
 
-    def assign(self, x, c, labels, fv=None, path="auto"):
+    def lloyd_run(self, x, c, c_prev, use_tol, tol_cmp, shift2, state, allreduce, iters, path="auto", row_ws=None):
+        """``iters`` Lloyd steps with one call (CUDA-graph replay inside the library)."""
         self._check_x(x, c)
         n, d = x.shape
         ldx = x.stride(0) if n > 1 else d
+        wp, wb = self._ws(row_ws)
+        check(self.lib.hk_lloyd_run(self.h, _ptr(x), n, d, ldx, _DT[x.dtype], _ptr(c), _ptr(c_prev), c.shape[0],
+                                    int(use_tol), float(tol_cmp), _ptr(shift2), _ptr(state), int(allreduce), wp, wb,
+                                    PATHS[path], int(iters), _stream(self.device)), "hk_lloyd_run")
+
+    def assign(self, x, c, labels, fv=None, path="auto", row_ws=None):
+        self._check_x(x, c)
+        n, d = x.shape
+        ldx = x.stride(0) if n > 1 else d
+        wp, wb = self._ws(row_ws)
         check(self.lib.hk_assign(self.h, _ptr(x), n, d, ldx, _DT[x.dtype], _ptr(c), c.shape[0], _ptr(labels),
-                                 _LK[labels.dtype] if labels is not None else HK_LABEL_NONE, _ptr(fv),
+                                 _LK[labels.dtype] if labels is not None else HK_LABEL_NONE, _ptr(fv), wp, wb,
                                  PATHS[path], _stream(self.device)), "hk_assign")
 
     def cdist(self, x, y, out, quadratic_expansion: bool, sqrt: bool = True):
@@ -126,13 +177,24 @@ class CudaEngine:
                                 _DT[x.dtype], int(quadratic_expansion), int(sqrt), _stream(self.device)),
               "hk_cdist")
 
-    def cache_reset(self) -> None:
-        """Forget cached per-matrix bounds (call when a matrix changes in place under the same pointer)."""
-        check(self.lib.hk_cache_reset(self.h), "hk_cache_reset")
-
     # -- introspection -------------------------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self.lib.hk_launch_count(self.h))
+
+    def stats(self) -> dict:
+        """Cold-path counters of the tensor-core passes since the previous call (synchronises)."""
+        out = (ctypes.c_int64 * 6)()
+        check(self.lib.hk_stats_read(self.h, out), "hk_stats_read")
+        names = ("undecided_rows", "exact_pairs", "all_centroid_rows", "cold_warps", "rows", "passes")
+        st = dict(zip(names, [int(v) for v in out]))
+        st["undecided_frac"] = st["undecided_rows"] / st["rows"] if st["rows"] else 0.0
+        return st
+
+    def graph(self, enable: bool) -> None:
+        check(self.lib.hk_graph_enable(self.h, int(enable)), "hk_graph_enable")
+
+    def graph_launch_count(self) -> int:
+        return int(self.lib.hk_graph_launch_count(self.h))
 
     def last_variant(self) -> str:
         return self.lib.hk_last_variant(self.h).decode()

@@ -59,17 +59,22 @@ def install() -> bool:
     def fit(self, x, oversampling=2, iter_multiplier=1):
         if not isinstance(x, DNDarray) or not _eligible(x):
             return _ORIG["fit"](self, x, oversampling, iter_multiplier)
+        init = self.init
+        if isinstance(init, DNDarray) and init.larray.dtype != x.larray.dtype:
+            return _ORIG["fit"](self, x, oversampling, iter_multiplier)  # mixed dtypes: reference path (decided before init runs)
+        if int(self.max_iter) < 1:
+            return _ORIG["fit"](self, x, oversampling, iter_multiplier)
         self._initialize_cluster_centers(x, oversampling, iter_multiplier)  # reference code (init runs once)
         c0 = self._cluster_centers.larray
         if c0.dtype != x.larray.dtype:
-            return _ORIG["fit"](self, x, oversampling, iter_multiplier)  # mixed dtypes: reference path
+            c0 = c0.to(x.larray.dtype)  # string initialisers sample rows of x: same dtype in practice
         xl = x.larray if x.larray.stride(1) == 1 else x.larray.contiguous()
         dev = xl.device
         eng = _engine.get_engine(dev)
         distributed = x.split is not None and x.comm.size > 1
         if distributed:
             eng.init_comm(_pg(x))
-        eng.cache_reset()
+        row_ws = eng.row_workspace(xl.shape[0])
         c = c0.to(dev).contiguous().clone()
         c_prev = torch.empty_like(c)
         shift2 = torch.zeros((), dtype=c.dtype, device=dev)
@@ -79,14 +84,13 @@ def install() -> bool:
         done, chunk = 0, (8 if use_tol else self.max_iter)
         while done < self.max_iter:
             todo = min(chunk, self.max_iter - done)
-            for _ in range(todo):
-                eng.lloyd_step(xl, c, c_prev, use_tol, tol_cmp, shift2, state, distributed)
+            eng.lloyd_run(xl, c, c_prev, use_tol, tol_cmp, shift2, state, distributed, todo, row_ws=row_ws)
             done += todo
             if use_tol and done < self.max_iter and int(state[0].item()):
                 break
         self._n_iter = int(state[1].item())
         labels = torch.empty((xl.shape[0], 1), dtype=torch.int64, device=dev)
-        eng.assign(xl, c_prev, labels)
+        eng.assign(xl, c_prev, labels, row_ws=row_ws)
         self._cluster_centers = _wrap(c, tuple(c.shape), self._cluster_centers.dtype, None, x)
         self._inertia = _wrap(shift2, (), self._cluster_centers.dtype, None, x)
         self._labels = DNDarray(labels, (x.shape[0], 1), ht.int64, x.split, x.device, x.comm, x.balanced)
@@ -101,8 +105,6 @@ def install() -> bool:
         eng = _engine.get_engine(dev)
         labels = torch.empty((xl.shape[0], 1), dtype=torch.int64, device=dev)
         fv = torch.zeros(1, dtype=torch.float64, device=dev) if eval_functional_value else None
-        if eval_functional_value:
-            eng.cache_reset()  # predict: x may have been rewritten in place since the fit (bounds are cached per address)
         eng.assign(xl, c.to(dev).contiguous(), labels, fv)
         if eval_functional_value:
             if x.split is not None and x.comm.size > 1:

@@ -15,10 +15,13 @@
  *   hk_cdist
  *        <- cdist -> _dist -> _euclidian_fast / _euclidian (X split 0|None, Y replicated)
  *                                           heat/spatial/distance.py:32-64, 136-156, 409-414
- *   hk_comm_* / hk_allreduce_f64
+ *   hk_comm_* / hk_allreduce_f64 (and the peer-memory exchange inside hk_lloyd_step / hk_lloyd_run)
  *        <- MPICommunication.Allreduce(MPI.IN_PLACE, t, MPI.SUM) as issued by __reduce_op
  *                                           heat/core/communication.py:1089-1110,
  *                                           heat/core/_operations.py:505-510
+ *   hk_lloyd_run
+ *        <- the `for epoch in range(max_iter)` loop of KMeans.fit between two convergence checks
+ *                                           heat/cluster/kmeans.py:131-144
  *   hk_chunk
  *        <- MPICommunication.chunk          heat/core/communication.py:197-254
  *
@@ -77,7 +80,7 @@ int hk_chunk(int64_t n_global, int nranks, int rank, int64_t* offset, int64_t* r
  */
 int hk_lloyd_accumulate(hk_handle_t h, const void* X, int64_t n_local, int d, int64_t ldx, int dtype,
                         const void* C, int k, void* labels, int label_kind, double* partials,
-                        int path, void* stream);
+                        void* row_ws, int64_t row_ws_bytes, int path, void* stream);
 
 /* partials (already summed over ranks) -> new centroids, shift^2, convergence flag.
  *   C_out[c] = cast( sums[c] / double(float(max(count[c],1))) )      (quirks Q1-Q3)
@@ -93,22 +96,35 @@ int hk_lloyd_finalize(hk_handle_t h, const double* partials, const void* C_in, v
                       int d, int dtype, int use_tol, double tol_cmp, void* shift2_out,
                       int32_t* state, void* stream);
 
-/* fused: accumulate -> (allreduce over the handle's communicator, if any) -> finalize.
+/* fused: accumulate -> (sum over the ranks of the handle's communicator, if `allreduce`) -> finalize, as TWO kernel
+ * launches: the pass over X and one "finish" kernel that reduces the pass's per-CTA slots, exchanges the k x (d+1)
+ * partials with the other ranks through peer-mapped GPU memory (see hk_comm_peer_*; falls back to ncclAllReduce +
+ * separate kernels when the peers are not mapped) and runs the finalize arithmetic.
  * C is updated IN PLACE (C_prev receives the pre-update centroids when not NULL). */
 int hk_lloyd_step(hk_handle_t h, const void* X, int64_t n_local, int d, int64_t ldx, int dtype,
                   void* C, void* C_prev, int k, void* labels, int label_kind, int use_tol,
-                  double tol_cmp, void* shift2_out, int32_t* state, int allreduce, int path,
-                  void* stream);
+                  double tol_cmp, void* shift2_out, int32_t* state, int allreduce, void* row_ws,
+                  int64_t row_ws_bytes, int path, void* stream);
 
-/* The tensor-core path caches a per-tile upper bound of |x|^2 (it enters only the error bound that decides
- * which rows need exact re-evaluation, never a result), keyed by (X, n, d, ldx).  Call this when the
- * CONTENT of a matrix changes under the same pointer; KMeans.fit calls it once per fit. */
-int hk_cache_reset(hk_handle_t h);
+/* `iters` consecutive hk_lloyd_step calls (no labels) enqueued by one call; all but the first are replayed from a CUDA
+ * graph cached in the handle while the arguments stay the same.  With `state`, steps after convergence are no-ops, so
+ * the host may enqueue a chunk of iterations, read state once, and still obtain the exact n_iter_. */
+int hk_lloyd_run(hk_handle_t h, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, void* C,
+                 void* C_prev, int k, int use_tol, double tol_cmp, void* shift2_out, int32_t* state,
+                 int allreduce, void* row_ws, int64_t row_ws_bytes, int path, int iters, void* stream);
+
+/* Optional per-matrix workspace (`row_ws`, `row_ws_bytes` of hk_lloyd_* / hk_assign): the tensor-core path keeps a
+ * per-tile upper bound of |x| in it (like sklearn's x_squared_norms; it enters only the error bound that decides which
+ * rows need exact re-evaluation, never a result).  The buffer is OWNED BY THE CALLER and tied to the CONTENT of X:
+ * allocate hk_row_ws_bytes(n_local) bytes of device memory, ZERO them (cudaMemsetAsync) whenever the rows of X change,
+ * and pass the same buffer with every pass over that X; the first pass fills it, later passes read it.  NULL is
+ * always valid: the bounds are then recomputed from the rows in every pass.  The library keeps no per-matrix state. */
+int64_t hk_row_ws_bytes(int64_t n_local);
 
 /* labels (+ optional sum over rows of min_j d^2, one double) — predict */
 int hk_assign(hk_handle_t h, const void* X, int64_t n_local, int d, int64_t ldx, int dtype,
-              const void* C, int k, void* labels, int label_kind, double* min_d2_sum, int path,
-              void* stream);
+              const void* C, int k, void* labels, int label_kind, double* min_d2_sum, void* row_ws,
+              int64_t row_ws_bytes, int path, void* stream);
 
 /* out[i,j] = dist(X[i], Y[j]); quadratic_expansion != 0 -> sqrt(clamp(|x|^2+|y|^2-2xy,0)),
  * else direct sqrt(sum (x-y)^2).  sqrt_flag = 0 returns squared distances. */
@@ -120,16 +136,31 @@ int hk_cdist(hk_handle_t h, const void* X, int64_t m, int f, int64_t ldx, const 
 int hk_comm_unique_id(void* id128);                      /* 128-byte ncclUniqueId            */
 int hk_comm_init(hk_handle_t h, int nranks, int rank, const void* id128);
 int hk_comm_destroy(hk_handle_t h);
+/* Peer-memory mailbox of the fused finish kernel (ranks = processes of ONE box, one GPU each).  After hk_comm_init:
+ * every rank calls hk_comm_peer_export (allocates its mailbox for partial vectors of up to cap_doubles values and
+ * writes a 64-byte cudaIpcMemHandle_t), the host gathers the handles in rank order (torch.distributed all_gather),
+ * every rank calls hk_comm_peer_import with the nranks x 64 bytes, then a host barrier.  Until then (or if the import
+ * fails) hk_lloyd_step uses ncclAllReduce.  hk_comm_mode: 0 single rank, 1 NCCL, 2 peer memory. */
+int hk_comm_peer_export(hk_handle_t h, int64_t cap_doubles, void* handle64);
+int hk_comm_peer_import(hk_handle_t h, const void* handles);
+int hk_comm_mode(hk_handle_t h);
 int hk_allreduce_f64(hk_handle_t h, double* buf, int64_t count, void* stream);
 
 /* ---- introspection for tests/bench ------------------------------------------------------- */
-/* kernels launched by this handle since creation */
+/* CUDA-graph replay inside hk_lloyd_run: on by default; hk_graph_enable(h, 0) makes it enqueue plain launches */
+int hk_graph_enable(hk_handle_t h, int enable);
+int64_t hk_graph_launch_count(hk_handle_t h);
+/* kernels launched by this handle since creation (graph replays count their kernel nodes) */
 int64_t hk_launch_count(hk_handle_t h);
 /* name of the kernel variant the last hk_lloyd_accumulate / hk_assign call selected */
 const char* hk_last_variant(hk_handle_t h);
 /* CUDA-event timing of the dominant kernel (the Lloyd pass / the cdist kernel) on its own stream:
  * enable != 0 brackets every such launch with an event pair; hk_profile_read synchronises, returns the
  * summed device time in ms and the number of launches measured, and clears the list. */
+/* cold-path counters of the tensor-core passes of this handle since the previous call (synchronises the device, then
+ * clears them): out6 = rows the TF32 filter could not decide, exact (row, centroid) evaluations, rows sent through the
+ * all-centroid formula (NaN/Inf), warps that entered the cold path, rows processed, passes. */
+int hk_stats_read(hk_handle_t h, int64_t* out6);
 int hk_profile_enable(hk_handle_t h, int enable);
 int hk_profile_read(hk_handle_t h, double* total_ms, int64_t* launches);
 

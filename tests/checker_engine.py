@@ -16,12 +16,14 @@ class CheckerEngine:
     def init_comm(self, comm):
         self.comm = comm
 
-    def cache_reset(self):
-        pass
+    def row_workspace(self, n_local):
+        return None
 
     def allreduce_f64(self, buf):
         if self.comm is not None and self.comm.is_distributed():
-            self.comm.Allreduce("IN_PLACE", buf)
+            from heat_b200.communication import IN_PLACE
+
+            self.comm.Allreduce(IN_PLACE, buf)
 
     def _partials(self, x, c):
         k, d = c.shape
@@ -32,7 +34,7 @@ class CheckerEngine:
             part[:, d] += torch.bincount(lab, minlength=k).double()
         return part.view(-1)
 
-    def lloyd_accumulate(self, x, c, partials, labels=None, path="auto"):
+    def lloyd_accumulate(self, x, c, partials, labels=None, path="auto", row_ws=None):
         partials.copy_(self._partials(x, c))
 
     def lloyd_finalize(self, partials, c_in, c_out, use_tol, tol_cmp, shift2, state):
@@ -49,7 +51,12 @@ class CheckerEngine:
         if use_tol and bool(s <= torch.tensor(tol_cmp, dtype=torch.float32).to(s.dtype)):
             state[0] = 1
 
-    def lloyd_step(self, x, c, c_prev, use_tol, tol_cmp, shift2, state, allreduce, labels=None, path="auto"):
+    def lloyd_run(self, x, c, c_prev, use_tol, tol_cmp, shift2, state, allreduce, iters, path="auto", row_ws=None):
+        for _ in range(iters):
+            self.lloyd_step(x, c, c_prev, use_tol, tol_cmp, shift2, state, allreduce)
+
+    def lloyd_step(self, x, c, c_prev, use_tol, tol_cmp, shift2, state, allreduce, labels=None, path="auto",
+                   row_ws=None):
         self.steps += 1
         if int(state[0]):
             return
@@ -59,7 +66,7 @@ class CheckerEngine:
         c_prev.copy_(c)
         self.lloyd_finalize(part, c.clone(), c, use_tol, tol_cmp, shift2, state)
 
-    def assign(self, x, c, labels, fv=None, path="auto"):
+    def assign(self, x, c, labels, fv=None, path="auto", row_ws=None):
         if x.shape[0] == 0:
             if fv is not None:
                 fv.zero_()
