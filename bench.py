@@ -2,6 +2,7 @@
 """Benchmark of the k-means Lloyd hot path (BASELINE.json metric: Lloyd iter/s at 100M x 32, k=64).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config3|config5|config2|config4]
+                    [--data blobs|overlap|randn|uncentred]
 
 * a "step" is one Lloyd iteration (fused assign + accumulate pass, allreduce of the k x (d+1) partials,
   finalize) over the whole 100M-row matrix, sharded split=0 over N ranks (strong scaling).
@@ -10,8 +11,13 @@
   is copied from pinned host memory to the device, one step runs, centroids + shift come back.
 * ``roofline``: algorithmic bytes (N*d*4 per iteration) / mean duration of the pass kernel (event pairs
   recorded inside the library around that kernel) against MEASURED_PEAKS.json's HBM copy bandwidth.
-* ``cpu_baseline`` / ``--impl reference``: the oracle port of the reference (torch CPU) on a bounded row
-  sample, extrapolated linearly in N (stated in ``sample``).
+* ``cpu_baseline`` / ``--impl reference``: the UNMODIFIED reference (``heat.cluster.KMeans`` / ``ht.spatial.cdist`` from
+  ``baseline/_ref`` under ``oracle/mpi4py_shim``; torch CPU, all host threads) on a bounded row sample, extrapolated
+  linearly in N (stated in ``sample``); the oracle port only if the reference cannot be imported.
+* ``parity``: after the timed loop every rank checks that its centroids are bit-equal to rank 0's, and a fixed
+  200 003-row problem (a row count no rank count divides) goes through the same sharded path for 3 steps and is compared with
+  the oracle on rank 0; a mismatch fails the run.
+* ``filter``: what fraction of rows the TF32 filter of the tensor-core pass could not decide (exact re-evaluation).
 """
 from __future__ import annotations
 
@@ -120,34 +126,97 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def timed_cpu_reference(n_sample: int, d: int, k: int, dtype, steps: int, warmup: int, kind: str):
-    """The oracle port (torch CPU, all host threads) on a bounded sample; returns (sec/step, threads)."""
-    from heat_b200.synthetic import blobs_shard, initial_centroids
-    from oracle import kmeans_oracle as orc
+SAMPLE_ROWS = {"config3": 250_000, "config5": 1_000_000, "config4": 8_000, "config2": 20_000}
+
+
+def _import_reference():
+    """The unmodified reference from baseline/_ref under the mpi4py stand-in, or None."""
+    shim = os.path.join(ROOT, "oracle", "mpi4py_shim")
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "heat")):
+        return None
+    for q in (ref, shim):
+        if q not in sys.path:
+            sys.path.insert(0, q)
+    try:
+        import heat as ht
+
+        return ht
+    except Exception:
+        return None
+
+
+def timed_cpu_reference(n_sample: int, d: int, k: int, dtype, steps: int, warmup: int, kind: str, data: str = "blobs"):
+    """One step of the reference's own CPU implementation on a bounded sample -> (sec/step, threads, kind)."""
+    from heat_b200.synthetic import dataset_init, dataset_shard
 
     # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank; only rank 0 runs this)
     try:
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     except (AttributeError, RuntimeError):
         torch.set_num_threads(max(1, os.cpu_count() or 1))
-    x, _ = blobs_shard(n_sample, d, k if kind == "kmeans" else 16, dtype=dtype)
-    if kind == "cdist":
-        y = torch.randn(k, d, dtype=dtype)
-        fn = lambda: orc.cdist(x, y, quadratic_expansion=True)
+    x, _ = dataset_shard(data, n_sample, d, k if kind == "kmeans" else 16, dtype=dtype)
+    ht = _import_reference()
+    if ht is not None:
+        impl = "reference"
+        hx = ht.array(x, split=0)
+        if kind == "cdist":
+            hy = ht.array(torch.randn(k, d, dtype=dtype))
+            fn = lambda: ht.spatial.cdist(hx, hy, quadratic_expansion=True)
+        else:
+            hc = ht.array(dataset_init(data, k, d, dtype=dtype))
+            # one Lloyd iteration = fit(max_iter=1, tol=None) with supplied centroids (kmeans.py:131-144)
+            fn = lambda: ht.cluster.KMeans(n_clusters=k, init=hc, max_iter=1, tol=None).fit(hx)
     else:
-        c = initial_centroids(k, d, dtype=dtype)
+        from oracle import kmeans_oracle as orc
 
-        def fn():
-            lab = orc.assign_to_cluster(x, c)
-            new = orc.update_centroids([x], [lab], c)
-            return ((c - new) ** 2).sum()
+        impl = "port"
+        if kind == "cdist":
+            y = torch.randn(k, d, dtype=dtype)
+            fn = lambda: orc.cdist(x, y, quadratic_expansion=True)
+        else:
+            c = dataset_init(data, k, d, dtype=dtype)
+
+            def fn():
+                lab = orc.assign_to_cluster(x, c)
+                new = orc.update_centroids([x], [lab], c)
+                return ((c - new) ** 2).sum()
 
     for _ in range(warmup):
         fn()
     t0 = time.perf_counter()
     for _ in range(steps):
         fn()
-    return (time.perf_counter() - t0) / max(steps, 1), torch.get_num_threads()
+    return (time.perf_counter() - t0) / max(steps, 1), torch.get_num_threads(), impl
+
+
+def reference_on_gpu(n_rows: int, d: int, k: int, dtype, dev, data: str):
+    """Second bar: the unmodified reference on one B200 through torch CUDA (np=1), or None."""
+    ht = _import_reference()
+    if ht is None:
+        return None
+    from heat_b200.synthetic import dataset_init, dataset_shard
+
+    try:
+        x, _ = dataset_shard(data, n_rows, d, k, device=dev, dtype=dtype)
+        hx = ht.array(x, split=0, device="gpu")
+        hc = ht.array(dataset_init(data, k, d, dtype=dtype).to(dev), device="gpu")
+        fn = lambda: ht.cluster.KMeans(n_clusters=k, init=hc, max_iter=1, tol=None).fit(hx)
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        sec = (time.perf_counter() - t0) / reps
+        del hx, x
+        torch.cuda.empty_cache()
+        return {"rows": n_rows, "sec_per_iter": sec,
+                "what": "unmodified heat.cluster.KMeans (baseline/_ref), torch CUDA on this B200, np=1, fit(max_iter=1)"}
+    except Exception as ex:  # out of memory etc.: reported, not hidden
+        torch.cuda.empty_cache()
+        return {"rows": n_rows, "error": str(ex)[:160]}
 
 
 def run_reference(args, wl):
@@ -155,19 +224,21 @@ def run_reference(args, wl):
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
     n, d, k, dtype = wl["n"], wl["d"], wl["k"], DT[wl["dtype"]]
-    # bounded sample: about 1.5 s of CPU work per step on ~8 cores (k full passes in fp64)
-    n_sample = {"config3": 100_000, "config5": 1_000_000, "config4": 8_000, "config2": 20_000}[args.workload]
-    sec, thr = timed_cpu_reference(n_sample, d, k, dtype, args.steps, args.warmup, wl["kind"])
+    # bounded sample: about 1-2 s of CPU work per step (k full passes in fp64)
+    n_sample = SAMPLE_ROWS[args.workload]
+    sec, thr, impl = timed_cpu_reference(n_sample, d, k, dtype, args.steps, args.warmup, wl["kind"], args.data)
     scale = n / n_sample
     value = 1.0 / (sec * scale)
-    sample = (f"oracle port of the reference (torch CPU, {thr} threads) on {n_sample} of {n} rows, "
-              f"{sec * 1e3:.1f} ms/step, extrapolated linearly in N (x{scale:.0f})")
+    what = ("unmodified reference (heat 1.9.0-dev from baseline/_ref under oracle/mpi4py_shim, torch CPU"
+            if impl == "reference" else "oracle port of the reference (torch CPU")
+    sample = (f"{what}, {thr} threads) on {n_sample} of {n} rows, {sec * 1e3:.1f} ms/step, "
+              f"extrapolated linearly in N (x{scale:.0f})")
     line = {
         "impl": "reference", "metric": metric_name(wl), "value": value, "unit": unit_name(wl),
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * scale * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": wl["dtype"],
-        "data": "synthetic", "config": {"workload": wl["desc"], "n_sample": n_sample},
-        "cpu_baseline": {"value": value, "unit": unit_name(wl), "cores": thr, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": {"workload": wl["desc"], "n_sample": n_sample, "dataset": args.data},
+        "cpu_baseline": {"value": value, "unit": unit_name(wl), "cores": thr, "kind": impl, "sample": sample},
         "e2e": {"value": value, "unit": unit_name(wl), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "host_cores": os.cpu_count(),
     }
@@ -182,11 +253,63 @@ def unit_name(wl):
     return "iter/s" if wl["kind"] == "kmeans" else "calls/s"
 
 
+def parity_check(eng, world, rank, dev, wl, args, c_timed):
+    """(i) the centroids of the timed run are bit-equal on every rank; (ii) a fixed 200 003-row problem (not divisible
+    by any rank count used) goes through the same sharded path for 3 steps and matches the oracle on rank 0 within the
+    north-star tolerance.  Raises on a mismatch (the run fails)."""
+    import torch.distributed as dist
+
+    from heat_b200.synthetic import dataset_init, dataset_shard
+
+    k, d, dtype = wl["k"], wl["d"], DT[wl["dtype"]]
+    res = {"ranks_bit_equal": True}
+    if world > 1:
+        parts = [torch.empty_like(c_timed) for _ in range(world)]
+        dist.all_gather(parts, c_timed.contiguous())
+        res["ranks_bit_equal"] = all(torch.equal(p.view(torch.uint8), parts[0].view(torch.uint8)) for p in parts)
+    n_par = 200_003
+    # generated on the host: the CPU and CUDA generators give different streams, and rank 0 rebuilds the global matrix
+    x, _ = dataset_shard("blobs", n_par, d, k, rank, world, device="cpu", dtype=dtype, seed=5)
+    x = x.to(dev)
+    c = dataset_init("blobs", k, d, dtype=dtype, seed=5).to(dev)
+    cp, sh = torch.empty_like(c), torch.zeros((), dtype=dtype, device=dev)
+    st = torch.zeros(4, dtype=torch.int32, device=dev)
+    ws = eng.row_workspace(x.shape[0])
+    for _ in range(3):
+        eng.lloyd_step(x, c, cp, False, 0.0, sh, st, world > 1, path=args.path, row_ws=ws)
+    torch.cuda.synchronize()
+    if world > 1:
+        parts = [torch.empty_like(c) for _ in range(world)]
+        dist.all_gather(parts, c)
+        res["ranks_bit_equal"] = res["ranks_bit_equal"] and all(
+            torch.equal(p.view(torch.uint8), parts[0].view(torch.uint8)) for p in parts)
+    res.update({"rows": n_par, "steps": 3, "rows_per_rank": int(x.shape[0]), "comm": eng.comm_mode()})
+    if rank == 0:
+        from oracle import kmeans_oracle as orc  # the checker, never the thing measured
+
+        xf, _ = dataset_shard("blobs", n_par, d, k, device="cpu", dtype=dtype, seed=5)
+        cc = dataset_init("blobs", k, d, dtype=dtype, seed=5)
+        for _ in range(3):
+            lab = orc.assign_to_cluster(xf, cc)
+            cc = orc.update_centroids_fast([xf], [lab], cc)
+        err = orc.centers_rel_err(cc, c.cpu())
+        tol = 1e-5 if dtype == torch.float32 else 1e-12
+        res.update({"centroid_rel_err_vs_oracle": err, "tol": tol, "ok": bool(err <= tol and res["ranks_bit_equal"])})
+    else:
+        res["ok"] = bool(res["ranks_bit_equal"])
+    ok = torch.tensor([1 if res["ok"] else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) != 1:
+        raise SystemExit(f"bench.py parity check FAILED on rank {rank}: {res}")
+    return res
+
+
 def run_ours(args, wl):
     import torch.distributed as dist
 
     import heat_b200 as hb
-    from heat_b200.synthetic import blobs_shard, initial_centroids
+    from heat_b200.synthetic import dataset_init, dataset_shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -221,17 +344,20 @@ def run_ours(args, wl):
 
     sampler = ClockSampler(torch.cuda.current_device())
 
+    row_ws = None
     if wl["kind"] == "kmeans":
-        x, off = blobs_shard(n, d, k, rank, world, device=dev, dtype=dtype)
-        c0 = initial_centroids(k, d, dtype=dtype).to(dev)
+        x, off = dataset_shard(args.data, n, d, k, rank, world, device=dev, dtype=dtype)
+        c0 = dataset_init(args.data, k, d, dtype=dtype).to(dev)
         c = c0.clone()
         c_prev = torch.empty_like(c)
         shift2 = torch.zeros((), dtype=dtype, device=dev)
         state = torch.zeros(4, dtype=torch.int32, device=dev)
         n_loc = x.shape[0]
+        # per-matrix workspace (|x| bounds of the tensor-core pass), exactly as KMeans.fit allocates it
+        row_ws = None if args.no_row_ws else eng.row_workspace(n_loc)
 
         def step():
-            eng.lloyd_step(x, c, c_prev, False, 0.0, shift2, state, world > 1, path=args.path)
+            eng.lloyd_step(x, c, c_prev, False, 0.0, shift2, state, world > 1, path=args.path, row_ws=row_ws)
 
         alg_bytes_rank = n_loc * d * esz
     else:
@@ -250,8 +376,10 @@ def run_ours(args, wl):
     for _ in range(args.warmup):
         step()
     barrier()
-    # a fit starts cold: drop the cached per-tile |x| bounds so that the first timed step rebuilds them
-    eng.cache_reset()
+    # a fit starts cold: the first timed step fills the row workspace, as the first iteration of a fit does
+    if row_ws is not None:
+        row_ws.zero_()
+    eng.stats()  # clear the cold-path counters
     eng.profile(True)
     eng.profile_read()
     l0 = eng.launch_count()
@@ -271,9 +399,33 @@ def run_ours(args, wl):
     ms_step = ms_total / args.steps
     value = 1e3 / ms_step
     kern_ms_avg = max_over_ranks(kern_ms / max(kern_n, 1))
+    filt = None
+    parity = None
+    graph = None
     if wl["kind"] == "kmeans":
         iters_done = int(state.cpu()[1])
         assert iters_done == args.warmup + args.steps, (iters_done, args.warmup + args.steps)
+        st = eng.stats()
+        if st["passes"]:
+            filt = {"undecided_frac": st["undecided_frac"], "undecided_rows_per_pass": st["undecided_rows"] / st["passes"],
+                    "exact_pairs_per_undecided_row": (st["exact_pairs"] / st["undecided_rows"]) if st["undecided_rows"] else 0.0,
+                    "all_centroid_rows": st["all_centroid_rows"], "passes": st["passes"],
+                    "what": "rows of the timed passes the TF32 filter could not decide (re-evaluated with the exact formula)"}
+        # the same K steps through hk_lloyd_run (one call, CUDA-graph replay): what KMeans.fit uses
+        c_keep = c.clone()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.lloyd_run(x, c, c_prev, False, 0.0, shift2, state, world > 1, args.steps, path=args.path, row_ws=row_ws)
+        barrier()
+        gl0 = eng.graph_launch_count()
+        g0.record()
+        eng.lloyd_run(x, c, c_prev, False, 0.0, shift2, state, world > 1, args.steps, path=args.path, row_ws=row_ws)
+        g1.record()
+        barrier()
+        graph = {"ms_per_step": max_over_ranks(g0.elapsed_time(g1)) / args.steps,
+                 "graph_launches": eng.graph_launch_count() - gl0,
+                 "what": "the same K steps enqueued by ONE hk_lloyd_run call (CUDA-graph replay), not the headline"}
+        parity = parity_check(eng, world, rank, dev, wl, args, c)
+        c.copy_(c_keep)
 
     # ---- end to end from host buffers -------------------------------------------------------------------
     e2e = None
@@ -287,11 +439,19 @@ def run_ours(args, wl):
                 sh = torch.empty((), dtype=dtype, pin_memory=True)
                 c.copy_(c0)
 
+                cbox = [c0.clone()]
+
                 def e2e_step():
+                    # the call a user makes: host rows -> device DNDarray -> KMeans.fit (one Lloyd iteration, labels,
+                    # inertia) -> centroids back on the host
                     x.copy_(xh, non_blocking=True)
-                    eng.lloyd_step(x, c, c_prev, False, 0.0, shift2, state, world > 1, path=args.path)
-                    ch.copy_(c, non_blocking=True)
-                    sh.copy_(shift2, non_blocking=True)
+                    xd = hb.dndarray.DNDarray(x, (n, d), x.dtype, 0, dev, comm, True)
+                    km = hb.cluster.KMeans(n_clusters=k, init=hb.array(cbox[0]), max_iter=1, tol=None)
+                    km.kernel_path = args.path
+                    km.fit(xd)
+                    cbox[0] = km.cluster_centers_.larray
+                    ch.copy_(cbox[0], non_blocking=True)
+                    sh.copy_(km.inertia_.larray, non_blocking=True)
 
                 d2h = k * d * esz + esz
             else:
@@ -317,7 +477,10 @@ def run_ours(args, wl):
             e2e = {"value": 1e3 / e2e_ms, "unit": unit_name(wl), "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": int(sum_over_ranks(n_loc * d * esz)),
                    "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "steps": e2e_steps,
-                   "api": "heat_b200 engine.lloyd_step -> hk_lloyd_step (C ABI), pinned host X copied every step"}
+                   "api": ("heat_b200.cluster.KMeans(init=centroids, max_iter=1, tol=None).fit(DNDarray) -> hk_lloyd_run + "
+                           "hk_assign (C ABI); pinned host X copied to the device every step, centroids + inertia read back"
+                           if wl["kind"] == "kmeans" else
+                           "heat_b200 engine.cdist -> hk_cdist (C ABI); pinned host X copied every step, distances read back")}
             del xh
         except RuntimeError as ex:  # pinned allocation failure is reported, not hidden
             e2e = {"value": None, "unit": unit_name(wl), "error": str(ex)[:200], "h2d_bytes_per_step": 0,
@@ -352,17 +515,33 @@ def run_ours(args, wl):
         "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
         "config": {"workload": wl["desc"], "n_global": n, "d": d, "k": k, "rows_per_rank": n_loc,
                    "l2": "inputs larger than L2 (per-rank shard %.1f GB vs 126 MB)" % (alg_bytes_rank / 1e9),
-                   "parallelism": f"split0 x{world}", "path": args.path},
+                   "parallelism": f"split0 x{world}", "path": args.path, "dataset": args.data,
+                   "comm": eng.comm_mode()},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
     }
+    if filt is not None:
+        line["filter"] = filt
+    if parity is not None:
+        line["parity"] = parity
+    if graph is not None:
+        line["graph_replay"] = graph
     if world == 1 and not args.no_cpu:
-        n_sample = {"config3": 100_000, "config5": 1_000_000, "config4": 8_000, "config2": 20_000}[args.workload]
-        sec, thr = timed_cpu_reference(n_sample, d, k, dtype, 3, 1, wl["kind"])
+        n_sample = SAMPLE_ROWS[args.workload]
+        sec, thr, impl = timed_cpu_reference(n_sample, d, k, dtype, 3, 1, wl["kind"], args.data)
         scale = n / n_sample
+        what = ("unmodified reference (heat from baseline/_ref under oracle/mpi4py_shim, torch CPU" if impl == "reference"
+                else "oracle port of the reference (torch CPU")
         line["cpu_baseline"] = {
-            "value": 1.0 / (sec * scale), "unit": unit_name(wl), "cores": thr, "kind": "port",
-            "sample": (f"oracle port of the reference (torch CPU, {thr} threads of {os.cpu_count()} host cores) on "
+            "value": 1.0 / (sec * scale), "unit": unit_name(wl), "cores": thr, "kind": impl,
+            "sample": (f"{what}, {thr} threads of {os.cpu_count()} host cores) on "
                        f"{n_sample} of {n} rows, {sec * 1e3:.1f} ms/step, extrapolated linearly in N (x{scale:.0f})")}
+        if wl["kind"] == "kmeans" and args.ref_gpu_rows > 0:
+            torch.cuda.empty_cache()
+            rg = reference_on_gpu(args.ref_gpu_rows, d, k, dtype, dev, args.data)
+            if rg is not None:
+                if "sec_per_iter" in rg:
+                    rg["iter_per_s_extrapolated"] = 1.0 / (rg["sec_per_iter"] * n / rg["rows"])
+                line["reference_gpu"] = rg
     print(json.dumps(line), flush=True)
 
 
@@ -374,6 +553,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=list(WORKLOADS))
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "tc", "generic"])
+    ap.add_argument("--data", default="blobs", choices=["blobs", "overlap", "randn", "uncentred"],
+                    help="input distribution (blobs = the benchmark's; the others show the path off its best case)")
+    ap.add_argument("--no-row-ws", action="store_true", help="run without the per-matrix |x| bound workspace")
+    ap.add_argument("--ref-gpu-rows", type=int, default=4_000_000,
+                    help="rows for the second bar: the unmodified reference on this GPU through torch CUDA (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--rows", type=int, default=None, help="override the global row count (experiments only)")

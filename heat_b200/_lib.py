@@ -11,10 +11,10 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_void_
 
 HK_F32, HK_F64 = 0, 1
 HK_LABEL_NONE, HK_LABEL_U8, HK_LABEL_I32, HK_LABEL_I64 = 0, 1, 2, 3
-HK_PATH_AUTO, HK_PATH_SIMT, HK_PATH_TC, HK_PATH_GENERIC = 0, 1, 2, 3
+HK_PATH_AUTO, HK_PATH_SIMT, HK_PATH_TC, HK_PATH_GENERIC, HK_PATH_ROW128 = 0, 1, 2, 3, 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhkmeans.so")
+LIB_PATH = os.environ.get("HK_LIB") or os.path.join(_HERE, "libhkmeans.so")  # HK_LIB: experiment builds only
 
 #: every symbol include/hkmeans.h declares: name -> (restype, argtypes)
 SIGNATURES = {

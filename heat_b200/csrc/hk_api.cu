@@ -80,7 +80,12 @@ static int run_pass(Handle* h, const LloydArgs& a) {
         }
         return launch_lloyd_tc(h, a);
     }
-    if (path == HK_PATH_SIMT && row128_supported(h, a)) return launch_lloyd_row128(h, a);
+    if (path == HK_PATH_SIMT && dmma_supported(h, a)) return launch_lloyd_dmma(h, a);
+    if ((path == HK_PATH_SIMT || path == HK_PATH_ROW128) && row128_supported(h, a)) return launch_lloyd_row128(h, a);
+    if (path == HK_PATH_ROW128) {
+        set_error("128-byte-row path does not support dtype=%d d=%d k=%d", a.dtype, a.d, a.k);
+        return -2;
+    }
     return launch_lloyd_simt(h, a);
 }
 

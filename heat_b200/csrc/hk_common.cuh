@@ -128,6 +128,8 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a);   // fp32 tensor-core path; 
 bool tc_supported(const Handle* h, const LloydArgs& a);
 int launch_lloyd_row128(Handle* h, const LloydArgs& a);  // exact FMA, rows of exactly 128 bytes
 bool row128_supported(const Handle* h, const LloydArgs& a);
+int launch_lloyd_dmma(Handle* h, const LloydArgs& a);  // fp64, d = 16, k <= 16: FP64 tensor cores, register accumulators
+bool dmma_supported(const Handle* h, const LloydArgs& a);
 int launch_lloyd_bigk(Handle* h, const LloydArgs& a);  // fp32, k too large for the fused kernel: multi-pass
 bool bigk_supported(const Handle* h, const LloydArgs& a);
 

@@ -42,7 +42,9 @@ __global__ void centroid_norms_kernel(const float* __restrict__ C, int k, int d,
         s = fmaf(c, c, s);
     }
     cn[j] = s;
-    if (s == s) atomicMax(reinterpret_cast<int*>(cmax2), __float_as_int(s));  // s >= 0: int order == float order
+    // s >= 0: int order == float order.  A NaN/Inf centroid makes the bound infinite: every row then goes through the
+    // exact kernel, which applies torch.min's NaN rule over all centroids
+    atomicMax(reinterpret_cast<int*>(cmax2), s == s ? __float_as_int(s) : 0x7f800000);
 }
 
 struct Cand {

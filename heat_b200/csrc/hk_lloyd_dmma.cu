@@ -1,0 +1,411 @@
+// fp64 Lloyd pass for the small-k, 128-byte-row regime (BASELINE config 5: N=50M, d=16, k=8, fp64): HBM-bound.
+//
+// The first version of this path (hk_lloyd_row128.cu: thread == row, centroids streamed from shared memory, private
+// shared-memory accumulators) ran at 49 % of the HBM roofline because it was bound by shared-memory bandwidth
+// (ncu: LSU wavefronts 80 % of peak): ~800 wavefronts per 128-row tile against the 728 cycles the tile's 16 KB take at
+// HBM speed.  Here nothing but the row tile itself lives in shared memory:
+//   * distances:  x.c^T on the FP64 tensor cores (mma.sync.m8n8k4.f64, 8 rows x 8 centroids x 4 features per
+//                 instruction); the centroids are four B-fragment registers per lane for the whole kernel,
+//                 d2 = fl(fl(|x|^2 + |c|^2) - 2 x.c) as heat/spatial/distance.py:59-64, first-index argmin with
+//                 torch.min NaN semantics (heat/core/statistics.py:177) inside each quad of lanes;
+//   * cluster sums: onehot(labels)^T . X on the same tensor cores (products by 0/1 are exact, the accumulation is
+//                 fp64 with round-to-nearest per step), accumulators = four C-fragment registers per lane for the
+//                 whole kernel: no shared-memory read-modify-write, no label hand-off between warps, no flushes;
+//   * counts:     integer adds of the one-hot fragments.
+// Each row is read from shared memory twice (once per fragment layout) = 256 B per row, 256 wavefronts per tile.
+// Warp roles: warp 0 = TMA producer (128-byte swizzle, EVICT_FIRST) into an S-stage ring; 16 compute warps, warp (q, r)
+// owns rows [32q, 32q+32) of the tiles i == r (mod 4).  Per-warp results go to per-warp fp64 slots in global memory and
+// are reduced in a fixed order (deterministic).
+// Replaces _assign_to_cluster + KMeans._update_centroids for one shard
+// (heat/cluster/_kcluster.py:352-370, heat/cluster/kmeans.py:76-103).
+#include <math.h>
+
+#include "hk_tma.cuh"
+
+namespace hk {
+namespace {
+
+constexpr int TM = 128;
+constexpr int C_WARPS = 16;
+constexpr int ER = 4;  // tile residues (4 warps each)
+constexpr int STAGE_BYTES = TM * 128;
+constexpr int D = 16;
+
+struct DmmaParams {
+    int64_t n;
+    int k;
+    const double* C;
+    void* labels;
+    int label_kind;
+    double* fsum;     // [grid*C_WARPS][k*16] or nullptr (assign only)
+    double* fcnt;     // [grid*C_WARPS][k]
+    double* fv_part;  // [grid] or nullptr
+    int S;
+    int num_tiles;
+    const int32_t* state;
+};
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void store_label_d(void* labels, int kind, int64_t row, int lab) {
+    if (kind == HK_LABEL_I64)
+        reinterpret_cast<long long*>(labels)[row] = lab;
+    else if (kind == HK_LABEL_I32)
+        reinterpret_cast<int*>(labels)[row] = lab;
+    else if (kind == HK_LABEL_U8)
+        reinterpret_cast<unsigned char*>(labels)[row] = (unsigned char)lab;
+}
+// sequential torch.min semantics when merging (value, index) pairs that cover disjoint index sets: the first NaN wins,
+// otherwise the smallest value, ties to the smaller index
+__device__ __forceinline__ void merge_min(double& v, int& j, double ov, int oj) {
+    const bool on = ov != ov, bn = v != v;
+    const bool take = (on && bn) ? (oj < j) : (on ? true : (bn ? false : (ov < v || (ov == v && oj < j))));
+    if (take) {
+        v = ov;
+        j = oj;
+    }
+}
+
+// NB = number of 8-centroid blocks (k <= 8 * NB)
+template <int NB, bool SUMS>
+__global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
+    lloyd_dmma_kernel(const __grid_constant__ CUtensorMap xmap, const DmmaParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    if (p.state != nullptr && p.state[0] != 0) return;  // uniform across the grid
+    unsigned char* smem =
+        reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int S = p.S, k = p.k;
+    const uint32_t a_stages = sbase;
+    const uint32_t o_bars = (uint32_t)S * STAGE_BYTES;
+    const uint32_t b_full = sbase + o_bars;  // full[S] | empty[S]  (16 slots each)
+    const uint32_t b_empty = b_full + 16 * 8;
+    double* fvred = reinterpret_cast<double*>(smem + o_bars + 32 * 8);  // [C_WARPS]
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int ntiles = p.num_tiles;
+
+    if (tid == 0) {
+        uint64_t* bars = reinterpret_cast<uint64_t*>(smem + o_bars);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(bars + s, 1);
+            mbar_init(bars + 16 + s, 4);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&xmap);
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                mbar_wait_a(b_empty + s * 8, ph ^ 1);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_full + s * 8),
+                             "r"((uint32_t)STAGE_BYTES)
+                             : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+                    " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(a_stages + s * STAGE_BYTES),
+                    "l"(&xmap), "r"(b_full + s * 8), "r"(0), "r"(tile * TM), "l"(kEvictFirst)
+                    : "memory");
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+    } else {
+        // ================= compute warps =================
+        const int we = warp - 1;
+        const int q = we & 3;
+        const int r = we >> 2;
+        const int g = lane >> 2;  // row of an 8-row group / centroid of a B fragment / cluster of an accumulator row
+        const int t = lane & 3;
+        // centroid fragments of the distance MMA: B[f][j] = c[j][f], this lane holds (f = 4 kb + t, j = 8 nb + g)
+        double bc[NB][4];
+        double cn0[NB], cn1[NB];  // |c_j|^2 of this lane's two D columns j = 8 nb + 2 t + {0, 1}
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+            const int j = nb * 8 + g;
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) bc[nb][kb] = j < k ? p.C[(size_t)j * D + kb * 4 + t] : 0.0;
+            const int j0 = nb * 8 + 2 * t;
+            double s0 = INFINITY, s1 = INFINITY;  // padded centroids can never win
+            if (j0 < k) {
+                s0 = 0.0;
+                for (int f = 0; f < D; ++f) s0 = fma(p.C[(size_t)j0 * D + f], p.C[(size_t)j0 * D + f], s0);
+            }
+            if (j0 + 1 < k) {
+                s1 = 0.0;
+                for (int f = 0; f < D; ++f) s1 = fma(p.C[(size_t)(j0 + 1) * D + f], p.C[(size_t)(j0 + 1) * D + f], s1);
+            }
+            cn0[nb] = s0;
+            cn1[nb] = s1;
+        }
+        // accumulators of onehot^T . X: acc[mb][nbf] = (cluster 8 mb + g, features 8 nbf + 2 t + {0, 1})
+        double acc0[NB][2], acc1[NB][2];
+        int cnt[NB];
+#pragma unroll
+        for (int mb = 0; mb < NB; ++mb) {
+            acc0[mb][0] = acc0[mb][1] = acc1[mb][0] = acc1[mb][1] = 0.0;
+            cnt[mb] = 0;
+        }
+        double fv_acc = 0.0;
+        const bool want_fv = p.fv_part != nullptr;
+        const int label_kind = p.label_kind;
+
+        int s = r % S;
+        uint32_t ph = (uint32_t)((r / S) & 1);
+        for (int tile = blockIdx.x + r * gridDim.x; tile < ntiles; tile += ER * gridDim.x) {
+            const uint32_t xt = a_stages + s * STAGE_BYTES + (uint32_t)(q * 32 * 128);
+            const int64_t row0 = (int64_t)tile * TM + q * 32;
+            warp_wait(b_full + s * 8, ph, lane);
+#pragma unroll
+            for (int grp = 0; grp < 4; ++grp) {
+                // ---- distances of rows 8 grp .. 8 grp + 7: A[row g][f = 4 kb + t] ------------------------------------
+                const int ra = grp * 8 + g;
+                const uint32_t xa = xt + (uint32_t)ra * 128;
+                double a[4];
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb) {
+                    const int f = kb * 4 + t;
+                    a[kb] = lds_f64(xa + (uint32_t)((((f >> 1) ^ (ra & 7)) << 4) | ((f & 1) << 3)));
+                }
+                double xn = 0.0;
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb) xn = fma(a[kb], a[kb], xn);
+                xn += __shfl_xor_sync(0xffffffffu, xn, 1);
+                xn += __shfl_xor_sync(0xffffffffu, xn, 2);
+                double best = INFINITY;
+                int lab = 0;
+                bool have = false;
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) dmma(d0, d1, a[kb], bc[nb][kb]);
+                    double e0 = (xn + cn0[nb]) - 2.0 * d0;
+                    double e1 = (xn + cn1[nb]) - 2.0 * d1;
+                    e0 = e0 < 0.0 ? 0.0 : e0;  // clamp(d2, 0, inf); NaN stays NaN
+                    e1 = e1 < 0.0 ? 0.0 : e1;
+                    const int j0 = nb * 8 + 2 * t;
+                    if (!have || e0 < best || (e0 != e0 && best == best)) {
+                        best = e0;
+                        lab = j0;
+                        have = true;
+                    }
+                    if (e1 < best || (e1 != e1 && best == best)) {
+                        best = e1;
+                        lab = j0 + 1;
+                    }
+                }
+                // the four lanes of a quad hold disjoint centroid subsets of the same row
+#pragma unroll
+                for (int o = 1; o <= 2; o <<= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int ol = __shfl_xor_sync(0xffffffffu, lab, o);
+                    merge_min(best, lab, ob, ol);
+                }
+                const bool active = row0 + ra < p.n;
+                if (active && t == 0) {
+                    if (label_kind != HK_LABEL_NONE) store_label_d(p.labels, label_kind, row0 + ra, lab);
+                    if (want_fv) {
+                        const double sq = sqrt(best);
+                        fv_acc += sq * sq;
+                    }
+                }
+                if (SUMS) {
+                    // ---- sums += onehot^T . X: A[cluster g][row 4 kb + t], B[row 4 kb + t][feature 8 nbf + g] --------
+                    const int mylab = active ? lab : -1;  // rows past the end belong to no cluster
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const int rr = kb * 4 + t;                                            // row inside the group
+                        const int rl = __shfl_sync(0xffffffffu, mylab, rr * 4);               // its label
+                        const int rb = grp * 8 + rr;
+                        const uint32_t xb = xt + (uint32_t)rb * 128;
+                        const double b0 = lds_f64(xb + (uint32_t)((((g >> 1) ^ (rb & 7)) << 4) | ((g & 1) << 3)));
+                        const double b1 =
+                            lds_f64(xb + (uint32_t)(((((8 + g) >> 1) ^ (rb & 7)) << 4) | ((g & 1) << 3)));
+#pragma unroll
+                        for (int mb = 0; mb < NB; ++mb) {
+                            const bool hit = rl == mb * 8 + g;
+                            const double oh = hit ? 1.0 : 0.0;
+                            cnt[mb] += hit ? 1 : 0;
+                            dmma(acc0[mb][0], acc0[mb][1], oh, b0);
+                            dmma(acc1[mb][0], acc1[mb][1], oh, b1);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(b_empty + s * 8);
+            s += ER;
+            while (s >= S) {
+                s -= S;
+                ph ^= 1;
+            }
+        }
+        if (SUMS) {
+            // this warp's slot: sums[cluster][feature] and counts (the 4 lanes of a quad saw different rows)
+            double* slot = p.fsum + ((size_t)blockIdx.x * C_WARPS + we) * (size_t)(k * D);
+            double* cslot = p.fcnt + ((size_t)blockIdx.x * C_WARPS + we) * (size_t)k;
+#pragma unroll
+            for (int mb = 0; mb < NB; ++mb) {
+                const int c = mb * 8 + g;
+                int ct = cnt[mb];
+                ct += __shfl_xor_sync(0xffffffffu, ct, 1);
+                ct += __shfl_xor_sync(0xffffffffu, ct, 2);
+                if (c < k) {
+                    slot[(size_t)c * D + 2 * t] = acc0[mb][0];
+                    slot[(size_t)c * D + 2 * t + 1] = acc0[mb][1];
+                    slot[(size_t)c * D + 8 + 2 * t] = acc1[mb][0];
+                    slot[(size_t)c * D + 8 + 2 * t + 1] = acc1[mb][1];
+                    if (t == 0) cslot[c] = (double)ct;
+                }
+            }
+        }
+        if (want_fv) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) fv_acc += __shfl_xor_sync(0xffffffffu, fv_acc, o);
+            if (lane == 0) fvred[we] = fv_acc;
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && p.fv_part != nullptr) {
+        double tsum = 0.0;
+        for (int w = 0; w < C_WARPS; ++w) tsum += fvred[w];
+        p.fv_part[blockIdx.x] = tsum;
+    }
+}
+
+// partials[c][0..d) / [d]: sums and counts over all warp slots in a fixed order
+__global__ void __launch_bounds__(256) reduce_dmma_kernel(const double* __restrict__ fsum, const double* __restrict__ fcnt,
+                                                          int nslots, int k, double* __restrict__ out, const int32_t* state) {
+    if (state != nullptr && state[0] != 0) return;
+    __shared__ double sh[8][33];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const int len = k * (D + 1);
+    double t = 0.0;
+    if (i < len) {
+        const int c = i / (D + 1), f = i - c * (D + 1);
+        const int per = (nslots + 7) / 8;
+        const int b1 = min(nslots, (grp + 1) * per);
+        if (f < D) {
+            for (int b = grp * per; b < b1; ++b) t += fsum[(size_t)b * k * D + (size_t)c * D + f];
+        } else {
+            for (int b = grp * per; b < b1; ++b) t += fcnt[(size_t)b * k + c];
+        }
+    }
+    sh[grp][lane] = t;
+    __syncthreads();
+    if (grp == 0 && i < len) {
+        double r = sh[0][lane];
+#pragma unroll
+        for (int g2 = 1; g2 < 8; ++g2) r += sh[g2][lane];
+        out[i] = r;
+    }
+}
+__global__ void reduce_scalar_dmma_kernel(const double* __restrict__ v, int n, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0.0;
+        for (int b = 0; b < n; ++b) t += v[b];
+        *out = t;
+    }
+}
+
+template <int NB, bool SUMS>
+int launch_dmma_inst(Handle* h, const CUtensorMap& map, const DmmaParams& p, size_t smem, int grid, cudaStream_t st) {
+    auto kern = lloyd_dmma_kernel<NB, SUMS>;
+    HK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin(h, st);
+    kern<<<grid, (1 + C_WARPS) * 32, smem, st>>>(map, p);
+    prof_end(h, st);
+    HK_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+}  // namespace
+
+bool dmma_supported(const Handle* h, const LloydArgs& a) {
+    (void)h;
+    if (a.dtype != HK_F64 || a.d != D) return false;
+    if (a.k < 1 || a.k > 16) return false;
+    if ((a.ldx * 8) % 16 != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(a.X) & 15) != 0) return false;
+    if (a.n >= (int64_t)1 << 31) return false;
+    return true;
+}
+
+int launch_lloyd_dmma(Handle* h, const LloydArgs& a) {
+    const bool sums = a.partials != nullptr;
+    const int S = 12;  // 12 x 16 KB row tiles in flight per SM
+    const size_t smem = (size_t)S * STAGE_BYTES + 32 * 8 + C_WARPS * 8 + 1024;
+    CUtensorMap map;
+    int rc = make_tensor_map_2d(&map, a.X, 8, (uint64_t)a.n, (uint64_t)a.d, (uint64_t)a.ldx, (uint32_t)a.d, TM, 128);
+    if (rc) return rc;
+    DmmaParams p{};
+    p.n = a.n;
+    p.k = a.k;
+    p.C = reinterpret_cast<const double*>(a.C);
+    p.labels = a.labels;
+    p.label_kind = a.labels ? a.label_kind : HK_LABEL_NONE;
+    p.S = S;
+    p.num_tiles = (int)((a.n + TM - 1) / TM);
+    p.state = a.state;
+    int grid = h->num_sms;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    const int nslots = grid * C_WARPS;
+    const size_t kd = (size_t)a.k * D;
+    rc = ensure_part(h, ((size_t)nslots * kd + (size_t)nslots * a.k + grid) * sizeof(double));
+    if (rc) return rc;
+    p.fsum = sums ? h->part : nullptr;
+    p.fcnt = h->part + (size_t)nslots * kd;
+    p.fv_part = a.fv_out ? h->part + (size_t)nslots * kd + (size_t)nslots * a.k : nullptr;
+
+    char name[96];
+    snprintf(name, sizeof(name), "dmma<f64,d=16,k=%d,S=%d,%s>", a.k, S, sums ? "sums" : "assign");
+    h->variant = name;
+    const bool two = a.k > 8;
+    if (sums)
+        rc = two ? launch_dmma_inst<2, true>(h, map, p, smem, grid, a.stream)
+                 : launch_dmma_inst<1, true>(h, map, p, smem, grid, a.stream);
+    else
+        rc = two ? launch_dmma_inst<2, false>(h, map, p, smem, grid, a.stream)
+                 : launch_dmma_inst<1, false>(h, map, p, smem, grid, a.stream);
+    if (rc) return rc;
+    if (sums && a.slots != nullptr) {
+        a.slots->fsum = p.fsum;
+        a.slots->fcnt = p.fcnt;
+        a.slots->nslots = nslots;
+        a.slots->slot_stride = 1;
+        a.slots->nblocks = nslots;
+    } else if (sums) {
+        const int len = a.k * (D + 1);
+        reduce_dmma_kernel<<<(len + 31) / 32, 256, 0, a.stream>>>(p.fsum, p.fcnt, nslots, a.k, a.partials, a.state);
+        HK_CUDA(cudaGetLastError());
+        h->launches++;
+    }
+    if (a.fv_out) {
+        reduce_scalar_dmma_kernel<<<1, 32, 0, a.stream>>>(p.fv_part, grid, a.fv_out);
+        HK_CUDA(cudaGetLastError());
+        h->launches++;
+    }
+    return 0;
+}
+
+}  // namespace hk

@@ -91,13 +91,13 @@ struct TcParams {
     unsigned long long* stats;  // [6] cumulative counters: undecided rows, exact (row, centroid) pairs, rows sent through
                                 // the all-centroid formula, warps that entered the cold path, rows seen, passes
     // shared-memory layout (byte offsets from the 1024-aligned base), computed on the host
-    uint32_t o_stages, o_B, o_Aext, o_Bext, o_cn, o_acc, o_lab, o_cnt, o_snap, o_bars, o_misc;
+    uint32_t o_stages, o_B, o_Aext, o_Bext, o_cn, o_acc, o_lab, o_cnt, o_snap, o_bars, o_misc, o_ring;
     unsigned long long* dbg;  // optional [grid][32 warps][8] cycle counters (HK_TC_DEBUG=1)
     unsigned long long* tl;   // optional timeline of CTA 0: [512 local tiles][8 events] clock64 stamps
 };
 
 struct TcLayout {
-    size_t stages, B, Aext, Bext, cn, acc, lab, cnt, snap, bars, misc, total;
+    size_t stages, B, Aext, Bext, cn, acc, lab, cnt, snap, bars, misc, ring, total;
 };
 
 __host__ inline size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -125,8 +125,10 @@ __host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sum
     if (sums) o += 32 * 4 * 4;
     L.bars = o;
     o += 8 * 96;  // mbarriers
-    L.misc = o;  // tmem slot, maxima, flags, fv partials, cold-path counters, mu[d]
+    L.misc = o;  // tmem slot, maxima, flags, fv partials, cold-path counters, ring control words, mu[d]
     o += 1024;
+    L.ring = o;  // undecided-row ring of the refine warp
+    o += (size_t)256 * 16;
     L.total = o + 1024;  // slack for manual 1024-byte alignment of the base
     return L;
 }
@@ -144,7 +146,7 @@ __device__ __forceinline__ void store_label_tc(void* labels, int kind, int64_t r
 // fl(fl(|x|^2 + |c_j|^2) - 2 fl(x.c_j)), features accumulated in ascending order with FMAs (the arithmetic of the
 // exact-FMA kernels).  x comes from the swizzled tile in shared memory, c from global memory (raw values, L1/L2
 // resident: the MMA operand in shared memory holds the centred ones).
-__device__ __forceinline__ float exact_pair(uint32_t xt, int row, const float* __restrict__ C, int j, int d, float cnj) {
+__device__ __forceinline__ float exact_pair_inl(uint32_t xt, int row, const float* __restrict__ C, int j, int d, float cnj) {
     float dot = 0.f, xn = 0.f;
     const float4* cr = reinterpret_cast<const float4*>(C + (size_t)j * d);
     for (int f = 0; f < d; f += 4) {
@@ -161,6 +163,10 @@ __device__ __forceinline__ float exact_pair(uint32_t xt, int row, const float* _
     }
     const float d2 = fmaf(-2.f, dot, xn + cnj);
     return d2 < 0.f ? 0.f : d2;
+}
+
+__device__ __forceinline__ float exact_pair(uint32_t xt, int row, const float* __restrict__ C, int j, int d, float cnj) {
+    return exact_pair_inl(xt, row, C, j, d, cnj);
 }
 
 __device__ __noinline__ float row_norm2(uint32_t xt, int row, int d) {
@@ -193,47 +199,100 @@ enum { XN_COMPUTE = 0, XN_WRITE = 1, XN_READ = 2 };
 #define TC_T(...)
 #endif
 
-// ---- cold path of the epilogue (out of line so that the hot loop stays small) ----------------------------------
-// Every lane hands in the candidate set of its row as two 32-column masks (mlo at column clo, mhi at column chi,
-// clo < chi; both zero: the lane has nothing to refine) or `full` (NaN/Inf, or candidates in more than two chunks:
-// exact formula over all k centroids).  Returns the first-index argmin of the exact formula over the candidates and
-// its value.  The (row, candidate) pairs of the whole warp are flattened over the lanes, so a warp with a few
-// undecided rows of a few candidates each pays for ONE exact evaluation, not for the longest per-lane chain.
-__device__ __noinline__ void refine_rows(uint32_t xt, int q, int lane, const float* __restrict__ C,
-                                         const float* __restrict__ cn, int k, int d, unsigned mlo, int clo,
-                                         unsigned mhi, int chi, bool full, int& lab, float& best_out, uint32_t a_stat) {
+// ---- exact refinement of the rows the filter cannot decide -------------------------------------------------------
+// The epilogue warps never evaluate the exact formula themselves (a call inside their loop costs the whole hot path
+// its uniform registers: +25 % on decided-only data).  They push one 16-byte entry per undecided row into a ring in
+// shared memory and move on; the otherwise idle warp 2 drains the ring, POOLING the rows of all four lane quarters
+// (and of consecutive tiles): the (row, candidate) pairs of up to 32 rows are flattened over its lanes, so a tile with
+// a few undecided rows of a few candidates each costs about one exact evaluation per lane instead of one long chain in
+// each of four warps.  The accumulator warps cannot start on a tile before its undecided rows have their final label:
+// the pushing warp raises the transaction count of the tile's "labels published" mbarrier by the number of rows it
+// defers, the refine warp completes them one by one.
+//
+// ring entry: word0 = tag (low 16 bits of slot index + 1) | stage << 16 | chunk_lo << 20 | chunk_hi << 23 | full << 26,
+//             word1 = global row, word2/3 = candidate masks of columns [32 chunk_lo, +32) / [32 chunk_hi, +32)
+constexpr int RING = 256;
+
+__device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32_volatile(uint32_t a, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t n) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+}
+__device__ __forceinline__ void mbar_complete_tx_a(uint32_t bar, uint32_t n) {
+    asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+}
+
+// refine warp (warp 2): runs until every epilogue warp has signed off and the ring is empty
+// (force-inlined on purpose: as a noinline function this loop - never executed on decided-only data - made the whole
+// kernel 25 % slower; measured A/B, see profiles/README.md)
+__device__ __forceinline__ void refine_warp_loop(int k, int d, const float* __restrict__ C, void* labels, int label_kind,
+                                              bool sums, bool want_fv, uint32_t a_ring, uint32_t a_qalloc,
+                                              uint32_t a_stages, uint32_t a_lab, uint32_t b_lfull, uint32_t a_ecnt0,
+                                              int lane, const float* cn, uint32_t* stat_out, double* fv_out) {
     constexpr unsigned FULLM = 0xffffffffu;
-    const int row = q * 32 + lane;
-    const int cnt = __popc(mlo) + __popc(mhi);
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULLM, incl, o);
-        if (lane >= o) incl += t;
-    }
-    const int excl = incl - cnt;
-    const int total = __shfl_sync(FULLM, incl, 31);
-    const int maxc = __reduce_max_sync(FULLM, cnt);
-    const int npass = (total + 31) >> 5;
-    float best = INFINITY;
-    int bl = mlo ? clo + __ffs(mlo) - 1 : chi + __ffs(mhi) - 1;
-    unsigned rlo = mlo, rhi = mhi;  // candidates of this lane's row not consumed yet (ascending column order)
-    if (maxc * 5 <= npass * 12) {
-        // few candidates per row, many rows (e.g. predict: one candidate in every row): each lane walks its own
-        while (rlo | rhi) {
-            int j;
-            if (rlo) {
-                j = clo + __ffs(rlo) - 1;
-                rlo &= rlo - 1;
-            } else {
-                j = chi + __ffs(rhi) - 1;
-                rhi &= rhi - 1;
+    const uint32_t a_qhead = a_qalloc + 4, a_qdone = a_qalloc + 8;
+    const uint32_t stage_bytes = (uint32_t)TM * d * 4;
+    uint32_t head = 0;
+    unsigned n_und = 0, n_pairs = 0, n_full = 0, n_batches = 0;
+    double fv_acc = 0.0;
+    for (;;) {
+        // leading run of published entries among slots head .. head + 31
+        const uint32_t idx = head + (uint32_t)lane;
+        const uint32_t ea = a_ring + (idx & (RING - 1)) * 16;
+        const uint32_t w0 = lds_u32_volatile(ea);
+        const unsigned ready = __ballot_sync(FULLM, (w0 & 0xffffu) == ((idx + 1u) & 0xffffu));
+        const int n = __ffs(~ready) - 1 < 0 ? 32 : __ffs(~ready) - 1;
+        if (n == 0) {
+            // nothing published: finished when all epilogue warps have signed off and every allocated slot is consumed
+            uint32_t done = 0, alloc = 0;
+            if (lane == 0) {
+                done = lds_u32_volatile(a_qdone);
+                __threadfence_block();
+                alloc = lds_u32_volatile(a_qalloc);
             }
-            take_min(exact_pair(xt, row, C, j, d, cn[j]), j, best, bl);
+            done = __shfl_sync(FULLM, done, 0);
+            alloc = __shfl_sync(FULLM, alloc, 0);
+            if (done == (uint32_t)E_WARPS && alloc == head) break;
+            __nanosleep(64);
+            continue;
         }
-    } else {
+        __threadfence_block();  // payload words were written before the tag
+        const bool mine = lane < n;
+        uint32_t grow = 0;
+        unsigned mlo = 0u, mhi = 0u;
+        if (mine) {
+            grow = lds_u32_volatile(ea + 4);
+            mlo = lds_u32_volatile(ea + 8);
+            mhi = lds_u32_volatile(ea + 12);
+        }
+        const int stage = (int)((w0 >> 16) & 15u);
+        const int clo = (int)((w0 >> 20) & 7u) * 32, chi = (int)((w0 >> 23) & 7u) * 32;
+        const bool full = mine && ((w0 >> 26) & 1u);
+        if (full || !mine) mlo = mhi = 0u;
+        const int row = (int)(grow & (TM - 1));
+        const uint32_t xt = a_stages + (uint32_t)stage * stage_bytes;
+
+        // ---- flatten the (row, candidate) pairs of the batch over the lanes ------------------------------------
+        const int cnt = __popc(mlo) + __popc(mhi);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULLM, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int excl = incl - cnt;
+        const int total = __shfl_sync(FULLM, incl, 31);
+        float best = INFINITY;
+        int bl = mlo ? clo + __ffs(mlo) - 1 : chi + __ffs(mhi) - 1;
+        unsigned rlo = mlo, rhi = mhi;  // candidates of this lane's row not consumed yet (ascending column order)
         for (int base = 0; base < total; base += 32) {
-            // lane p evaluates pair (base + p): its owner is the lane `own` with excl <= pair < incl
+            // lane p evaluates pair (base + p); its owner is the lane `own` with excl <= pair < incl
             const int pr = base + lane;
             int own = 0;
 #pragma unroll
@@ -245,29 +304,31 @@ __device__ __noinline__ void refine_rows(uint32_t xt, int q, int lane, const flo
             own &= 31;
             const unsigned omlo = __shfl_sync(FULLM, mlo, own), omhi = __shfl_sync(FULLM, mhi, own);
             const int oclo = __shfl_sync(FULLM, clo, own), ochi = __shfl_sync(FULLM, chi, own);
-            int idx = pr - __shfl_sync(FULLM, excl, own);
+            const int orow = __shfl_sync(FULLM, row, own);
+            const uint32_t oxt = __shfl_sync(FULLM, xt, own);
+            int pi = pr - __shfl_sync(FULLM, excl, own);
             float v = INFINITY;
             if (valid) {
                 unsigned m = omlo;
                 int cb = oclo;
                 const int nlo = __popc(omlo);
-                if (idx >= nlo) {
-                    idx -= nlo;
+                if (pi >= nlo) {
+                    pi -= nlo;
                     m = omhi;
                     cb = ochi;
                 }
-                for (int i = 0; i < idx; ++i) m &= m - 1;
+                for (int i = 0; i < pi; ++i) m &= m - 1;
                 const int j = cb + __ffs(m) - 1;
-                v = exact_pair(xt, q * 32 + own, C, j, d, cn[j]);
+                v = exact_pair(oxt, orow, C, j, d, cn[j]);
             }
             __syncwarp();
             // hand the values back: the owner consumes its pairs of this pass in order
             const int lo_p = max(excl, base), hi_p = min(incl, base + 32);
-            const int mine = max(hi_p - lo_p, 0);
-            const int np = __reduce_max_sync(FULLM, mine);
+            const int own_n = max(hi_p - lo_p, 0);
+            const int np = __reduce_max_sync(FULLM, own_n);
             for (int i = 0; i < np; ++i) {
                 const float w = __shfl_sync(FULLM, v, (lo_p + i - base) & 31);
-                if (i < mine) {
+                if (i < own_n) {
                     int j;
                     if (rlo) {
                         j = clo + __ffs(rlo) - 1;
@@ -280,24 +341,45 @@ __device__ __noinline__ void refine_rows(uint32_t xt, int q, int lane, const flo
                 }
             }
         }
+        if (full) {  // NaN/Inf, or candidates in more than two chunks: every centroid (rare)
+            best = INFINITY;
+            bl = 0;
+            for (int j = 0; j < k; ++j) take_min(exact_pair(xt, row, C, j, d, cn[j]), j, best, bl);
+        }
+        // ---- publish: final label, cluster count, functional value; then release the row ------------------------
+        if (mine) {
+            if (label_kind != HK_LABEL_NONE) store_label_tc(labels, label_kind, (int64_t)grow, bl);
+            if (sums) {
+                sts_u16(a_lab + (uint32_t)stage * (TM * 2) + (uint32_t)row * 2, (uint32_t)bl);
+                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a_ecnt0 + (uint32_t)bl * 4) : "memory");
+            }
+            if (want_fv) {
+                const float sq = sqrtf(best);
+                fv_acc += (double)(sq * sq);
+            }
+            if (sums) {
+                __threadfence_block();  // the label store is ordered before the completion the accumulator warps wait on
+                mbar_complete_tx_a(b_lfull + (uint32_t)stage * 8, 1u);
+            }
+        }
+        n_und += (unsigned)n;
+        n_pairs += (unsigned)total + (unsigned)__popc(__ballot_sync(FULLM, full)) * (unsigned)k;
+        n_full += (unsigned)__popc(__ballot_sync(FULLM, full));
+        n_batches += 1u;
+        head += (uint32_t)n;
+        __syncwarp();
+        if (lane == 0) sts_u32_volatile(a_qhead, head);  // the slots may be reused
     }
-    if (full) {
-        best = INFINITY;
-        bl = 0;
-        for (int j = 0; j < k; ++j) take_min(exact_pair(xt, row, C, j, d, cn[j]), j, best, bl);
+    if (want_fv) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) fv_acc += __shfl_xor_sync(FULLM, fv_acc, o);
     }
-    if (cnt > 0 || full) {
-        lab = bl;
-        best_out = best;
-    }
-    // counters (shared memory, this CTA): undecided rows, exact pairs, all-centroid rows, cold warps
-    const int nfull = __popc(__ballot_sync(FULLM, full));
-    const int nund = __popc(__ballot_sync(FULLM, cnt > 1 || full));
     if (lane == 0) {
-        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_stat), "r"(nund) : "memory");
-        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_stat + 4), "r"(total + nfull * k) : "memory");
-        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_stat + 8), "r"(nfull) : "memory");
-        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_stat + 12), "r"(1) : "memory");
+        stat_out[0] = n_und;
+        stat_out[1] = n_pairs;
+        stat_out[2] = n_full;
+        stat_out[3] = n_batches;
+        *fv_out = fv_acc;
     }
 }
 
@@ -362,6 +444,8 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     }
     if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
     for (int f = tid; f < d; f += blockDim.x) mu_s[f] = 0.f;
+    for (int e = tid; e < RING * 4; e += blockDim.x) reinterpret_cast<uint32_t*>(smem + p.o_ring)[e] = 0u;  // no tag matches
+    if (tid < 3) reinterpret_cast<uint32_t*>(smem + p.o_misc + 272)[tid] = 0u;  // q_alloc, q_head, q_done
     // seed operand A_ext[r] = (1,1,1,0,...)
     for (int e = tid; e < 8 * 8; e += blockDim.x) {
         const int r = e >> 3, ch = e & 7;
@@ -420,7 +504,11 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     const float cmax = *cmax_s;
     const bool force_exact = *force_exact_s != 0;
     // centre only when it helps (it always does unless the centroids straddle the origin already)
+#ifdef HK_NO_MU
+    const bool use_mu = false;
+#else
     const bool use_mu = !force_exact && (*cpmax_s < cmax);
+#endif
     const float cpmax = use_mu ? *cpmax_s : cmax;
     // operand B = -2 * (c - mu): K-blocked, 128B-swizzled, rows >= k zero
     for (int e = tid; e < nk * (d >> 2); e += blockDim.x) {
@@ -542,9 +630,15 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         const int row = q * 32 + lane;
         const uint32_t tlane = __shfl_sync(0xffffffffu, tmem_base, 0) + ((uint32_t)(q * 32) << 16);
         const float beta2 = 2.f * 1.05f * 0.001953125f;
+#ifdef HK_OLD_E
+        const float gam = (float)(d + 3) * 1.1920929e-7f;
+        const float cmax2 = cmax * cmax;
+#else
         const float gam = (float)(2 * d + 6) * 1.1920929e-7f;
         const float cmax2 = cmax * cmax + cpmax * cpmax;
-        const uint32_t a_stat = sbase + p.o_misc + 256;
+#endif
+        const uint32_t a_qalloc = sbase + p.o_misc + 272;  // ring control: allocated slots | consumed slots | warps done
+        const uint32_t a_ring = sbase + p.o_ring;
         const uint32_t a_ecnt = sbase + p.o_cnt + (uint32_t)we * (uint32_t)(k * 4);
         const uint32_t a_hist = sbase + p.o_cnt + (uint32_t)(E_WARPS * k * 4) + (uint32_t)we * (uint32_t)((k + 1) * 4);
         const uint32_t a_mmax_q = sbase + p.o_snap + (uint32_t)q * 4;
@@ -590,13 +684,12 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             tc_fence_after();
             const uint32_t taddr = tlane + (uint32_t)(b * nk);
             // one sweep over the accumulator, 32 columns in registers at a time.  Per chunk: its minimum m_c and
-            // the mask of columns below m_c + 2E.  The two chunks with the smallest minima are kept: the chunk
-            // holding the global minimum has the exact candidate mask, the runner-up chunk a superset of its
-            // candidates (it holds none iff its minimum is at least 2E above the global one); candidates in a
-            // third chunk (m_third) send the row through the all-centroid formula.
-            float m_best = INFINITY, m_second = INFINITY, m_third = INFINITY;
-            unsigned mk_best = 0, mk_second = 0;
-            int c_best = 0, c_second = 0;
+            // the mask of columns below m_c + 2E.  The chunk holding the global minimum has the right mask; the
+            // other chunks hold no candidate iff their minimum is at least 2E above it (else the row is
+            // undecided anyway: at least one candidate per such chunk).
+            float m_best = INFINITY, m_second = INFINITY;
+            unsigned mk_best = 0;
+            int c_best = 0;
             for (int c0 = 0; c0 < nk; c0 += 32) {
                 uint32_t a[32];
                 tmem_ld32(taddr + (uint32_t)c0, a);
@@ -604,66 +697,101 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 const float mc = min32(a);
                 const unsigned mk = below_mask32(a, mc + E2);
                 if (mc < m_best) {
-                    m_third = m_second;
                     m_second = m_best;
-                    mk_second = mk_best;
-                    c_second = c_best;
                     m_best = mc;
                     mk_best = mk;
                     c_best = c0;
-                } else if (mc < m_second) {
-                    m_third = m_second;
-                    m_second = mc;
-                    mk_second = mk;
-                    c_second = c0;
                 } else {
-                    m_third = fminf(m_third, mc);
+                    m_second = fminf(m_second, mc);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_a(b_tempty + b * 8);  // accumulator b may be overwritten
-            TC_T(t2 = clock64();)
-
             // NaN minima compare false everywhere: the row is then undecided and the exact path takes it
             const float thr = m_best + E2;
-            const bool sec_in = m_second < thr;
-            const bool decided = !sec_in && (__popc(mk_best) == 1) && !force_exact && (E2 < INFINITY);
+            const bool decided = (m_second >= thr) && (__popc(mk_best) == 1) && !force_exact && (E2 < INFINITY);
             int lab = c_best + __ffs(mk_best) - 1;
             if (!active) lab = k;
-            const bool cold = active && (!decided || want_fv);
-            if (__any_sync(0xffffffffu, cold)) {
-                // cold: undecided rows (near-ties within the TF32 bound, NaN/Inf) or the functional value is wanted
-                mbar_wait_a(b_full + s * 8, ph);  // this thread is about to read the x tile itself
-                const bool full = cold && (force_exact || !(E2 < INFINITY) || !(fabsf(m_best) < INFINITY) ||
-                                           (m_third < thr) || mk_best == 0u);
-                unsigned mlo = 0u, mhi = 0u;
-                int clo = 0, chi = 0;
-                if (cold && !full) {
-                    mlo = mk_best;
-                    clo = c_best;
-                    if (sec_in) {
-                        mhi = mk_second;
-                        chi = c_second;
-                        if (chi < clo) {
-                            mlo = mk_second;
-                            clo = c_second;
-                            mhi = mk_best;
-                            chi = c_best;
+            const bool cold = active && !decided;
+            int n_cold = 0;
+            if (__builtin_expect(__any_sync(0xffffffffu, cold), 0)) {
+                // undecided rows (near-ties within the TF32 bound, NaN/Inf): hand them to the refine warp.  Candidate set
+                // of a row = columns below min + 2E: the mask of the best chunk is exact; rows with candidates elsewhere
+                // get theirs from a second sweep over the accumulator (still held).  Rows with candidates in more than
+                // two chunks, and NaN/Inf, go through the all-centroid formula.
+                bool full = cold && (force_exact || !(thr < INFINITY) || !(fabsf(m_best) < INFINITY) || mk_best == 0u);
+                const bool und = cold && !full;
+                unsigned mlo = und ? mk_best : 0u, mhi = 0u;
+                int clo = c_best, chi = 0;
+                if (nk > 32 && __any_sync(0xffffffffu, und && m_second < thr)) {
+                    int nch = 0;
+                    unsigned lo = 0u, hi = 0u;
+                    int cl = 0, ch = 0;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < nk; c0 += 32) {
+                        uint32_t a[32];
+                        tmem_ld32(taddr + (uint32_t)c0, a);
+                        tmem_wait_ld();
+                        const unsigned mk = und ? below_mask32(a, thr) : 0u;
+                        if (mk) {
+                            if (nch == 0) {
+                                lo = mk;
+                                cl = c0;
+                            } else if (nch == 1) {
+                                hi = mk;
+                                ch = c0;
+                            }
+                            ++nch;
                         }
                     }
+                    if (und) {
+                        const bool over = nch > 2 || nch == 0;
+                        full = over;
+                        mlo = over ? 0u : lo;
+                        mhi = over ? 0u : hi;
+                        clo = cl;
+                        chi = ch;
+                    }
                 }
-                float best = 0.f;
-                refine_rows(xt, q, lane, p.C, cn, k, d, mlo, clo, mhi, chi, full, lab, best, a_stat);
-                if (want_fv && cold) {
-                    const float sq = sqrtf(best);
-                    fv_acc += (double)(sq * sq);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(b_tempty + b * 8);  // accumulator b may be overwritten
+                const unsigned pm = __ballot_sync(0xffffffffu, cold);
+                n_cold = __popc(pm);
+                uint32_t slot0 = 0;
+                if (lane == 0) {
+                    // the tile's labels are complete only when the refine warp has released these rows
+                    if (SUMS) mbar_expect_tx_a(b_lfull + s * 8, (uint32_t)n_cold);
+                    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(slot0) : "r"(a_qalloc), "r"(n_cold) : "memory");
                 }
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                if (cold) {
+                    const uint32_t idx = slot0 + (uint32_t)__popc(pm & lanemask_lt());
+                    while ((int32_t)(idx - lds_u32_volatile(a_qalloc + 4)) >= RING) __nanosleep(32);  // ring full
+                    const uint32_t ea = a_ring + (idx & (RING - 1)) * 16;
+                    sts_u32_volatile(ea + 4, (uint32_t)grow);
+                    sts_u32_volatile(ea + 8, mlo);
+                    sts_u32_volatile(ea + 12, mhi);
+                    __threadfence_block();  // payload before tag
+                    sts_u32_volatile(ea, ((idx + 1u) & 0xffffu) | ((uint32_t)s << 16) | ((uint32_t)(clo >> 5) << 20) |
+                                             ((uint32_t)(chi >> 5) << 23) | (full ? (1u << 26) : 0u));
+                    lab = k;  // no label yet: the refine warp stores the final one (and counts the row)
+                }
+            } else {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(b_tempty + b * 8);  // accumulator b may be overwritten
             }
-            if (label_kind != HK_LABEL_NONE && active) store_label_tc(p.labels, label_kind, (int64_t)grow, lab);
+            TC_T(t2 = clock64();)
+            if (!SUMS && want_fv && active && !cold) {
+                // functional value of a decided row: exact distance to its centroid
+                mbar_wait_a(b_full + s * 8, ph);  // this thread is about to read the x tile itself
+                const float sq = sqrtf(exact_pair_inl(xt, row, p.C, lab, d, cn[lab]));
+                fv_acc += (double)(sq * sq);
+            }
+            if (label_kind != HK_LABEL_NONE && active && !cold) store_label_tc(p.labels, label_kind, (int64_t)grow, lab);
             if (SUMS) {
-                // hand the labels to the accumulator warp of this lane quarter (rows past the end carry label k)
-                sts_u16(a_lab_row + s * (TM * 2), (uint32_t)lab);
+                // hand the labels to the accumulator warp of this lane quarter (rows past the end carry label k; the
+                // label of an undecided row is stored by the refine warp, possibly before this point)
+                if (!cold) sts_u16(a_lab_row + s * (TM * 2), (uint32_t)lab);
                 __syncwarp();
                 if (lane == 0) mbar_arrive_a(b_lfull + s * 8);  // the accumulator warp can start on these rows
                 TC_T(if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && i < 512) p.tl[i * 8 + 3] = clock64();)
@@ -674,7 +802,8 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 int old;
                 asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(ha) : "memory");
                 if (lab < k) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a_ecnt + (uint32_t)lab * 4) : "memory");
-                const int mm = __reduce_max_sync(0xffffffffu, lab < k ? old + 1 : 0);
+                // (undecided rows sit in the dummy bucket k: each could still join the largest group)
+                const int mm = min(32, __reduce_max_sync(0xffffffffu, lab < k ? old + 1 : 0) + n_cold);
                 sts_s32(ha, 0);
                 if (lane == 0) {
                     // 32-deep ring indexed by the local tile number, read by the accumulator warp when it starts its
@@ -705,6 +834,16 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             for (int o = 16; o > 0; o >>= 1) fv_acc += __shfl_xor_sync(0xffffffffu, fv_acc, o);
             if (lane == 0) fvred[we] = fv_acc;
         }
+        __syncwarp();
+        if (lane == 0) {  // no more entries from this warp
+            __threadfence_block();
+            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a_qalloc + 8) : "memory");
+        }
+    } else if (warp == 2) {
+        // ================= refine warp =================
+        refine_warp_loop(k, d, p.C, p.labels, p.label_kind, SUMS, p.fv_part != nullptr, sbase + p.o_ring,
+                         sbase + p.o_misc + 272, a_stages, a_lab, b_lfull, sbase + p.o_cnt, lane, cn, stat_s,
+                         fvred + E_WARPS);
     } else if (SUMS && warp >= A_FIRST) {
         // ================= accumulator warps =================
         const int a = warp - A_FIRST;
@@ -874,7 +1013,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     if (tid == 0) {
         if (p.fv_part != nullptr) {
             double t = 0.0;
-            for (int w = 0; w < E_WARPS; ++w) t += fvred[w];
+            for (int w = 0; w <= E_WARPS; ++w) t += fvred[w];  // epilogue warps + refine warp
             p.fv_part[blockIdx.x] = t;
         }
         if (xn_mode == XN_WRITE && blockIdx.x == 0) reinterpret_cast<int*>(p.bounds)[p.num_tiles] = 1;
@@ -1026,6 +1165,7 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
         p.o_snap = (uint32_t)L.snap;
         p.o_bars = (uint32_t)L.bars;
         p.o_misc = (uint32_t)L.misc;
+        p.o_ring = (uint32_t)L.ring;
     }
 
     // per-tile |x| bound cache: caller-owned and tied to the content of X (see hk_row_ws_bytes); none -> per-row

@@ -9,11 +9,12 @@ import torch
 
 from . import _lib
 from ._lib import (HK_F32, HK_F64, HK_LABEL_I32, HK_LABEL_I64, HK_LABEL_NONE, HK_LABEL_U8, HK_PATH_AUTO,
-                   HK_PATH_GENERIC, HK_PATH_SIMT, HK_PATH_TC, check)
+                   HK_PATH_GENERIC, HK_PATH_ROW128, HK_PATH_SIMT, HK_PATH_TC, check)
 
 _DT = {torch.float32: HK_F32, torch.float64: HK_F64}
 _LK = {torch.uint8: HK_LABEL_U8, torch.int32: HK_LABEL_I32, torch.int64: HK_LABEL_I64}
-PATHS = {"auto": HK_PATH_AUTO, "simt": HK_PATH_SIMT, "tc": HK_PATH_TC, "generic": HK_PATH_GENERIC}
+PATHS = {"auto": HK_PATH_AUTO, "simt": HK_PATH_SIMT, "tc": HK_PATH_TC, "generic": HK_PATH_GENERIC,
+         "row128": HK_PATH_ROW128}
 
 
 def _ptr(t: Optional[torch.Tensor]):

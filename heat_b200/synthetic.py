@@ -67,3 +67,53 @@ def blobs_shard(n_global: int, d: int, k: int, rank: int = 0, size: int = 1, dev
         out[pos - off : pos - off + (hi - lo)] = blk[lo:hi]
         pos += hi - lo
     return out, off
+
+
+# ---- other input distributions (bench.py --data): how the path behaves off well-separated blobs ---------------------
+KINDS = ("blobs", "overlap", "randn", "uncentred")
+
+
+def dataset_shard(kind: str, n_global: int, d: int, k: int, rank: int = 0, size: int = 1, device="cpu",
+                  dtype=torch.float32, seed: int = 1) -> Tuple[torch.Tensor, int]:
+    """Rows of ``rank`` of the global matrix of the given kind (same chunk-seeded scheme as :func:`blobs_shard`):
+
+    * ``blobs``     unit balls around centres ``4 * randn`` (the benchmark's create_spherical_dataset-style input)
+    * ``overlap``   the same with centres ``0.8 * randn``: heavily overlapping balls
+    * ``randn``     unstructured standard normal rows (no cluster structure at all)
+    * ``uncentred`` uniform [0, 255) rows, far from the origin (image-like, cf. the reference's cityscapes benchmark,
+      benchmarks/2020/kmeans/config.json)
+    """
+    if kind == "blobs":
+        return blobs_shard(n_global, d, k, rank, size, device, dtype, 4.0, 1.0, seed)
+    if kind == "overlap":
+        return blobs_shard(n_global, d, k, rank, size, device, dtype, 0.8, 1.0, seed)
+    if kind not in KINDS:
+        raise ValueError(f"unknown dataset kind {kind}")
+    off, rows = chunk_rows(n_global, size, rank)
+    out = torch.empty((rows, d), dtype=dtype, device=device)
+    pos = off
+    while pos < off + rows:
+        ci = pos // CHUNK
+        c0 = ci * CHUNK
+        crow = min(CHUNK, n_global - c0)
+        g = torch.Generator(device=device).manual_seed(seed + 77 + 1000 * ci)
+        if kind == "randn":
+            blk = torch.randn(crow, d, generator=g, device=device, dtype=torch.float32)
+        else:
+            blk = torch.rand(crow, d, generator=g, device=device, dtype=torch.float32) * 255.0
+        lo, hi = pos - c0, min(crow, off + rows - c0)
+        out[pos - off : pos - off + (hi - lo)] = blk[lo:hi].to(dtype)
+        pos += hi - lo
+    return out, off
+
+
+def dataset_init(kind: str, k: int, d: int, dtype=torch.float32, seed: int = 1) -> torch.Tensor:
+    """Initial centroids matching :func:`dataset_shard`."""
+    if kind == "blobs":
+        return initial_centroids(k, d, 4.0, seed, dtype)
+    if kind == "overlap":
+        return initial_centroids(k, d, 0.8, seed, dtype)
+    g = torch.Generator().manual_seed(seed + 5)
+    if kind == "randn":
+        return torch.randn(k, d, generator=g, dtype=torch.float64).to(dtype)
+    return (torch.rand(k, d, generator=g, dtype=torch.float64) * 255.0).to(dtype)

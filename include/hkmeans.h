@@ -55,10 +55,12 @@ extern "C" {
 
 /* distance path selection for hk_lloyd_* / hk_assign (HK_PATH_AUTO picks by shape) */
 #define HK_PATH_AUTO 0
-#define HK_PATH_SIMT 1   /* exact fp32/fp64 FMA distances (warp-specialised kernel for 128-byte rows,
-                            generic tiled kernel otherwise)                                  */
+#define HK_PATH_SIMT 1   /* exact-formula distances without the TF32 filter: FP64 tensor-core kernel for fp64
+                            d=16 k<=16, warp-specialised FMA kernel for other 128-byte rows, generic tiled
+                            kernel otherwise                                                  */
 #define HK_PATH_TC 2     /* tcgen05 TF32 filter + exact FMA refinement (fp32 only)          */
 #define HK_PATH_GENERIC 3 /* the generic tiled exact-FMA kernel, whatever the shape          */
+#define HK_PATH_ROW128 4  /* the warp-specialised exact-FMA kernel for 128-byte rows (tests)  */
 
 typedef struct hk_handle_s* hk_handle_t;
 

@@ -83,7 +83,10 @@ def test_n_iter_independent_of_sync_interval(sync_every):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("n,d,k", [(1, 1, 1), (5, 3, 2), (257, 7, 3), (1000, 32, 64), (4099, 16, 8), (777, 64, 5),
                                    (3001, 32, 7), (130, 16, 100),
-                                   (3000, 128, 40), (2049, 200, 9), (600, 5, 300), (5000, 33, 1100)])
+                                   (3000, 128, 40), (2049, 200, 9), (600, 5, 300), (5000, 33, 1100),
+                                   # fused tensor-core kernel beyond k=64: multi-chunk TMEM sweep, nbuf 2-5, NA=4 plans
+                                   (3000, 32, 96), (2500, 32, 160), (4000, 32, 256), (2100, 64, 96), (2600, 64, 160),
+                                   (1900, 64, 256), (1500, 128, 96)])
 def test_single_step_against_oracle(dtype, n, d, k):
     """One accumulate+finalize against the oracle for awkward shapes (ragged tiles, odd d, large k)."""
     g = torch.Generator().manual_seed(n * 7 + d * 3 + k)
@@ -103,6 +106,8 @@ def test_single_step_against_oracle(dtype, n, d, k):
         ref_lab = orc.assign_to_cluster(x, c).view(-1)
         par = orc.compare_labels(x, c, ref_lab, lab.cpu().long())
         assert par.hard == 0, (path, par)
+        # rows whose reference label depends on the BLAS summation order: a handful at most on unstructured data
+        assert par.ref_rounding <= max(2, n // 500), (path, par)
         p = part.cpu().view(k, d + 1)
         new_lab = lab.cpu().long()
         exp = torch.zeros(k, d + 1, dtype=torch.float64)
@@ -142,6 +147,112 @@ def test_empty_and_strided_and_unaligned_shards():
         assert float(part.view(k, d + 1)[:, d].sum()) == 3000.0
 
 
+def _nan_inf_matrix(n, d, g):
+    x = torch.randn(n, d, generator=g)
+    x[3, 1] = float("nan")
+    x[n // 2] = float("nan")
+    x[7, 0] = float("inf")
+    x[n - 5, d - 1] = -float("inf")
+    x[11] = 0.0
+    return x
+
+
+@pytest.mark.parametrize("path,n,d,k", [("tc", 1000, 32, 64), ("tc", 700, 64, 160), ("simt", 1000, 32, 64),
+                                        ("auto", 5000, 64, 320), ("auto", 3000, 128, 1024)])
+def test_nan_inf_rows_on_every_path(path, n, d, k):
+    """NaN / Inf rows (and an all-zero row) through the tensor-core filter, the 128-byte-row kernel and the large-k
+    path: labels follow torch.min over clamp(d^2, 0) exactly like the reference (statistics.py:177, quirk Q4)."""
+    g = torch.Generator().manual_seed(17)
+    x = _nan_inf_matrix(n, d, g)
+    c = torch.randn(k, d, generator=g)
+    ref = orc.assign_to_cluster(x, c).view(-1)
+    eng = engine.get_engine(DEV)
+    lab = torch.empty(n, dtype=torch.int64, device=DEV)
+    eng.assign(x.to(DEV), c.to(DEV), lab, path=path)
+    got = lab.cpu()
+    bad = torch.isnan(x).any(1) | torch.isinf(x).any(1)
+    assert got[bad].tolist() == ref[bad].tolist()
+    par = orc.compare_labels(x[~bad], c, ref[~bad], got[~bad])
+    assert par.hard == 0, par
+    # a NaN centroid: every distance to it is NaN and wins every row from its index on (first NaN sticks)
+    c2 = c.clone()
+    c2[k // 3, 2] = float("nan")
+    ref2 = orc.assign_to_cluster(x, c2).view(-1)
+    eng.assign(x.to(DEV), c2.to(DEV), lab, path=path)
+    assert lab.cpu().tolist() == ref2.tolist()
+
+
+@pytest.mark.parametrize("kind", ["randn", "uncentred", "overlap"])
+def test_filter_cold_path_matches_oracle(kind):
+    """Inputs on which the TF32 filter leaves many rows undecided (unstructured, far from the origin, overlapping):
+    the candidate-only refinement must give the labels of the exact formula; the counters say it was exercised."""
+    from heat_b200.synthetic import dataset_init, dataset_shard
+
+    n, d, k = 60_000, 32, 64
+    x, _ = dataset_shard(kind, n, d, k)
+    c = dataset_init(kind, k, d)
+    eng = engine.get_engine(DEV)
+    xd, cd = x.to(DEV), c.to(DEV)
+    ws = eng.row_workspace(n)
+    eng.stats()
+    for it, row_ws in enumerate((ws, ws, None)):  # workspace filled, workspace read, per-row bounds
+        lab = torch.empty(n, dtype=torch.int32, device=DEV)
+        part = torch.empty(k * (d + 1), dtype=torch.float64, device=DEV)
+        fv = torch.zeros(1, dtype=torch.float64, device=DEV)
+        eng.lloyd_accumulate(xd, cd, part, labels=lab, path="tc", row_ws=row_ws)
+        st = eng.stats()
+        ref = orc.assign_to_cluster(x, c).view(-1)
+        par = orc.compare_labels(x, c, ref, lab.cpu().long())
+        assert par.hard == 0, (kind, it, par)
+        assert par.ref_rounding <= n // 2000, (kind, it, par)
+        assert st["passes"] == 1 and st["rows"] == n
+        if kind != "overlap":
+            assert st["undecided_rows"] > 0  # the cold path ran
+        assert st["all_centroid_rows"] == 0
+        lab2 = torch.empty(n, dtype=torch.int32, device=DEV)
+        eng.assign(xd, cd, lab2, fv, path="tc", row_ws=row_ws)
+        assert torch.equal(lab, lab2)
+        want_fv = float((orc.cdist(x, c, True).min(dim=1).values.double() ** 2).sum())
+        np.testing.assert_allclose(float(fv), want_fv, rtol=1e-5)
+        eng.stats()
+    # the exact-FMA twin gives the same labels bit for bit
+    lab3 = torch.empty(n, dtype=torch.int32, device=DEV)
+    eng.assign(xd, cd, lab3, path="simt")
+    assert torch.equal(lab, lab3)
+
+
+def test_bigk_multichunk_and_tail_against_oracle():
+    """Large-k path over more than one 1M-row launch plus a tail below 1024 rows (hk_lloyd_bigk.cu: row_base > 0,
+    the exact-cdist tail branch), and the BASELINE configs[3] shape d=128, k=1024 at 1.1M rows."""
+    eng = engine.get_engine(DEV)
+    for n, d, k in ((2 * (1 << 20) + 500, 64, 320), (1_100_000, 128, 1024)):
+        g = torch.Generator().manual_seed(n % 1000 + k)
+        c = (2.0 * torch.randn(k, d, generator=g))
+        x = c[torch.randint(0, k, (n,), generator=g)] + torch.randn(n, d, generator=g)
+        xd, cd = x.to(DEV), c.to(DEV)
+        part = torch.empty(k * (d + 1), dtype=torch.float64, device=DEV)
+        lab = torch.empty(n, dtype=torch.int32, device=DEV)
+        eng.lloyd_accumulate(xd, cd, part, labels=lab)
+        assert eng.last_variant().startswith("bigk<"), eng.last_variant()
+        got = lab.cpu().long()
+        hard = rr = 0
+        for r0 in range(0, n, 200_000):
+            xs = x[r0 : r0 + 200_000]
+            ref = orc.assign_to_cluster(xs, c).view(-1)
+            par = orc.compare_labels(xs, c, ref, got[r0 : r0 + 200_000])
+            hard += par.hard
+            rr += par.ref_rounding
+        assert hard == 0 and rr <= n // 5000, (n, d, k, hard, rr)
+        p = part.cpu().view(k, d + 1)
+        exp = torch.zeros(k, d + 1, dtype=torch.float64)
+        exp[:, :d].index_add_(0, got, x.double())
+        exp[:, d] = torch.bincount(got, minlength=k).double()
+        assert torch.equal(p[:, d], exp[:, d])
+        scale = x.double().abs().max() * exp[:, d].clamp(min=1).view(-1, 1)
+        assert float(((p[:, :d] - exp[:, :d]).abs() / scale).max()) < 2e-6
+        del xd, x
+
+
 def test_nan_rows_follow_torch_min_semantics():
     # torch.min: a NaN distance wins, first NaN index sticks (quirk Q4)
     x = torch.tensor([[0.0, 0.0], [float("nan"), 1.0], [1.0, 1.0]])
@@ -173,13 +284,25 @@ def test_cdist_matches_reference(dt):
     assert torch.allclose(dd.larray.cpu(), torch.cdist(A.float(), A.float()), atol=1e-3)
 
 
-def test_cdist_large_vs_oracle():
+@pytest.mark.parametrize("m,n,f", [(5000, 300, 64), (3000, 4096, 32), (2100, 4096, 128), (1024, 128, 96)])
+def test_cdist_large_vs_oracle(m, n, f):
+    """tcgen05 3xTF32 cdist kernel: squared distances inside the bound of the scheme (the dropped x_lo.y_lo term,
+    2^-20 |x||y| with the factor 2 of the expansion, plus fp32 rounding of the formula), distances at the reference's
+    own tolerance scale (tests/spatial/test_distances.py:207-265 use atol 1e-5 on O(1) values)."""
     g = torch.Generator().manual_seed(3)
-    X = torch.randn(5000, 64, generator=g)
-    Y = torch.randn(300, 64, generator=g)
-    want = orc.cdist(X, Y, quadratic_expansion=True)
+    X = torch.randn(m, f, generator=g)
+    Y = torch.randn(n, f, generator=g)
     got = hb.spatial.cdist(hb.array(X.to(DEV), split=0), hb.array(Y.to(DEV)), quadratic_expansion=True)
-    assert torch.allclose(got.larray.cpu(), want, atol=2e-4, rtol=1e-5)
+    assert engine.get_engine(DEV).last_variant().startswith("cdist_tc"), engine.get_engine(DEV).last_variant()
+    got = got.larray.cpu().double()
+    xd, yd = X.double(), Y.double()
+    d2 = (xd * xd).sum(1, keepdim=True) + (yd * yd).sum(1) - 2.0 * xd @ yd.T
+    xn, yn = xd.norm(dim=1, keepdim=True), yd.norm(dim=1)
+    bound = 2.0**-19 * xn * yn + (f + 3) * 2.0**-22 * (xn * xn + yn * yn)
+    assert bool(((got * got - d2).abs() <= bound + 1e-30).all()), float(((got * got - d2).abs() / bound).max())
+    want = d2.clamp(min=0).sqrt()
+    # distances here are O(sqrt(2 f)): 1e-5 relative to that scale
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.max()), float((got - want).abs().max())
 
 
 def test_full_size_properties_config3():
