@@ -149,7 +149,8 @@ __device__ __forceinline__ void store_label_tc(void* labels, int kind, int64_t r
 __device__ __forceinline__ float exact_pair_inl(uint32_t xt, int row, const float* __restrict__ C, int j, int d, float cnj) {
     float dot = 0.f, xn = 0.f;
     const float4* cr = reinterpret_cast<const float4*>(C + (size_t)j * d);
-    for (int f = 0; f < d; f += 4) {
+#pragma unroll 8
+    for (int f = 0; f < d; f += 4) {  // d is a multiple of 32: the eight loads of a block are issued before its FMA chains
         const float4 xv = lds_f4(xt + sw128_off(TM, row, f));
         const float4 cv = __ldg(cr + (f >> 2));
         xn = fmaf(xv.x, xv.x, xn);
@@ -213,6 +214,7 @@ enum { XN_COMPUTE = 0, XN_WRITE = 1, XN_READ = 2 };
 //             word1 = global row, word2/3 = candidate masks of columns [32 chunk_lo, +32) / [32 chunk_hi, +32)
 constexpr int RING = 256;
 
+
 __device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t a) {
     uint32_t v;
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -228,55 +230,79 @@ __device__ __forceinline__ void mbar_complete_tx_a(uint32_t bar, uint32_t n) {
     asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(n) : "memory");
 }
 
-// refine warp (warp 2): runs until every epilogue warp has signed off and the ring is empty
-// (force-inlined on purpose: as a noinline function this loop - never executed on decided-only data - made the whole
-// kernel 25 % slower; measured A/B, see profiles/README.md)
-__device__ __forceinline__ void refine_warp_loop(int k, int d, const float* __restrict__ C, void* labels, int label_kind,
-                                              bool sums, bool want_fv, uint32_t a_ring, uint32_t a_qalloc,
-                                              uint32_t a_stages, uint32_t a_lab, uint32_t b_lfull, uint32_t a_ecnt0,
-                                              int lane, const float* cn, uint32_t* stat_out, double* fv_out) {
-    constexpr unsigned FULLM = 0xffffffffu;
-    const uint32_t a_qhead = a_qalloc + 4, a_qdone = a_qalloc + 8;
-    const uint32_t stage_bytes = (uint32_t)TM * d * 4;
-    uint32_t head = 0;
+// addresses and flags a warp needs to drain the ring
+struct RefineCtx {
+    int k, d;
+    const float* C;
+    void* labels;
+    int label_kind;
+    bool sums, want_fv;
+    uint32_t a_ring, a_qalloc, a_stages, a_lab, b_lfull, a_ecnt0;
+    const float* cn;
+};
+struct RefineStats {
     unsigned n_und = 0, n_pairs = 0, n_full = 0, n_batches = 0;
-    double fv_acc = 0.0;
-    for (;;) {
+    double fv = 0.0;
+};
+
+// One batch: under the consumer lock take the leading run of published entries (at most 32, one per lane) and free
+// their slots; then, lock released, evaluate them and publish the labels.  Any warp outside the hot roles may call it
+// (all lanes converged).  Returns the batch size.  (Letting the epilogue warps help between two tiles was measured and
+// dropped: any refine code inside their loop costs the decided-only case 13 %.)
+// (Force-inlined on purpose: as a noinline function this code - never executed on decided-only data - made the whole
+// kernel 25 % slower; measured A/B, see profiles/README.md.)
+__device__ __forceinline__ int refine_batch(const RefineCtx& c, int lane, RefineStats& rs) {
+    constexpr unsigned FULLM = 0xffffffffu;
+    const int k = c.k, d = c.d;
+    const float* __restrict__ C = c.C;
+    const float* cn = c.cn;
+    const uint32_t a_qhead = c.a_qalloc + 4, a_qlock = c.a_qalloc + 12;
+    const uint32_t stage_bytes = (uint32_t)TM * d * 4;
+    uint32_t got = 0;
+    if (lane == 0) {
+        uint32_t old;
+        asm volatile("atom.shared.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "r"(a_qlock) : "memory");
+        got = old == 0u ? 1u : 0u;
+    }
+    if (!__shfl_sync(FULLM, got, 0)) return 0;
+    __threadfence_block();
+    uint32_t head = lane == 0 ? lds_u32_volatile(a_qhead) : 0u;
+    head = __shfl_sync(FULLM, head, 0);
+    int n;
+    uint32_t w0, grow = 0;
+    unsigned mlo = 0u, mhi = 0u;
+    {
         // leading run of published entries among slots head .. head + 31
         const uint32_t idx = head + (uint32_t)lane;
-        const uint32_t ea = a_ring + (idx & (RING - 1)) * 16;
-        const uint32_t w0 = lds_u32_volatile(ea);
+        const uint32_t ea = c.a_ring + (idx & (RING - 1)) * 16;
+        w0 = lds_u32_volatile(ea);
         const unsigned ready = __ballot_sync(FULLM, (w0 & 0xffffu) == ((idx + 1u) & 0xffffu));
-        const int n = __ffs(~ready) - 1 < 0 ? 32 : __ffs(~ready) - 1;
-        if (n == 0) {
-            // nothing published: finished when all epilogue warps have signed off and every allocated slot is consumed
-            uint32_t done = 0, alloc = 0;
-            if (lane == 0) {
-                done = lds_u32_volatile(a_qdone);
-                __threadfence_block();
-                alloc = lds_u32_volatile(a_qalloc);
+        n = ready == FULLM ? 32 : __ffs(~ready) - 1;
+        if (n > 0) {
+            __threadfence_block();  // payload words were written before the tag
+            if (lane < n) {
+                grow = lds_u32_volatile(ea + 4);
+                mlo = lds_u32_volatile(ea + 8);
+                mhi = lds_u32_volatile(ea + 12);
             }
-            done = __shfl_sync(FULLM, done, 0);
-            alloc = __shfl_sync(FULLM, alloc, 0);
-            if (done == (uint32_t)E_WARPS && alloc == head) break;
-            __nanosleep(64);
-            continue;
+            __threadfence_block();  // payload read before the slots are handed back
         }
-        __threadfence_block();  // payload words were written before the tag
+        __syncwarp();
+        if (lane == 0) {
+            if (n > 0) sts_u32_volatile(a_qhead, head + (uint32_t)n);
+            __threadfence_block();
+            sts_u32_volatile(a_qlock, 0u);
+        }
+        if (n == 0) return 0;
+    }
+    {
         const bool mine = lane < n;
-        uint32_t grow = 0;
-        unsigned mlo = 0u, mhi = 0u;
-        if (mine) {
-            grow = lds_u32_volatile(ea + 4);
-            mlo = lds_u32_volatile(ea + 8);
-            mhi = lds_u32_volatile(ea + 12);
-        }
         const int stage = (int)((w0 >> 16) & 15u);
         const int clo = (int)((w0 >> 20) & 7u) * 32, chi = (int)((w0 >> 23) & 7u) * 32;
         const bool full = mine && ((w0 >> 26) & 1u);
         if (full || !mine) mlo = mhi = 0u;
         const int row = (int)(grow & (TM - 1));
-        const uint32_t xt = a_stages + (uint32_t)stage * stage_bytes;
+        const uint32_t xt = c.a_stages + (uint32_t)stage * stage_bytes;
 
         // ---- flatten the (row, candidate) pairs of the batch over the lanes ------------------------------------
         const int cnt = __popc(mlo) + __popc(mhi);
@@ -348,39 +374,27 @@ __device__ __forceinline__ void refine_warp_loop(int k, int d, const float* __re
         }
         // ---- publish: final label, cluster count, functional value; then release the row ------------------------
         if (mine) {
-            if (label_kind != HK_LABEL_NONE) store_label_tc(labels, label_kind, (int64_t)grow, bl);
-            if (sums) {
-                sts_u16(a_lab + (uint32_t)stage * (TM * 2) + (uint32_t)row * 2, (uint32_t)bl);
-                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a_ecnt0 + (uint32_t)bl * 4) : "memory");
+            if (c.label_kind != HK_LABEL_NONE) store_label_tc(c.labels, c.label_kind, (int64_t)grow, bl);
+            if (c.sums) {
+                sts_u16(c.a_lab + (uint32_t)stage * (TM * 2) + (uint32_t)row * 2, (uint32_t)bl);
+                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(c.a_ecnt0 + (uint32_t)bl * 4) : "memory");
             }
-            if (want_fv) {
+            if (c.want_fv) {
                 const float sq = sqrtf(best);
-                fv_acc += (double)(sq * sq);
+                rs.fv += (double)(sq * sq);
             }
-            if (sums) {
+            if (c.sums) {
                 __threadfence_block();  // the label store is ordered before the completion the accumulator warps wait on
-                mbar_complete_tx_a(b_lfull + (uint32_t)stage * 8, 1u);
+                mbar_complete_tx_a(c.b_lfull + (uint32_t)stage * 8, 1u);
             }
         }
-        n_und += (unsigned)n;
-        n_pairs += (unsigned)total + (unsigned)__popc(__ballot_sync(FULLM, full)) * (unsigned)k;
-        n_full += (unsigned)__popc(__ballot_sync(FULLM, full));
-        n_batches += 1u;
-        head += (uint32_t)n;
-        __syncwarp();
-        if (lane == 0) sts_u32_volatile(a_qhead, head);  // the slots may be reused
+        const unsigned nf = (unsigned)__popc(__ballot_sync(FULLM, full));
+        rs.n_und += (unsigned)n;
+        rs.n_pairs += (unsigned)total + nf * (unsigned)k;
+        rs.n_full += nf;
+        rs.n_batches += 1u;
     }
-    if (want_fv) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) fv_acc += __shfl_xor_sync(FULLM, fv_acc, o);
-    }
-    if (lane == 0) {
-        stat_out[0] = n_und;
-        stat_out[1] = n_pairs;
-        stat_out[2] = n_full;
-        stat_out[3] = n_batches;
-        *fv_out = fv_acc;
-    }
+    return n;
 }
 
 // SUMS: accumulate per-cluster sums (adds the accumulator warps); FQL2 = log2(d/4): lanes per row in the
@@ -445,7 +459,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
     for (int f = tid; f < d; f += blockDim.x) mu_s[f] = 0.f;
     for (int e = tid; e < RING * 4; e += blockDim.x) reinterpret_cast<uint32_t*>(smem + p.o_ring)[e] = 0u;  // no tag matches
-    if (tid < 3) reinterpret_cast<uint32_t*>(smem + p.o_misc + 272)[tid] = 0u;  // q_alloc, q_head, q_done
+    if (tid < 4) reinterpret_cast<uint32_t*>(smem + p.o_misc + 272)[tid] = 0u;  // q_alloc, q_head, q_done, q_lock
     // seed operand A_ext[r] = (1,1,1,0,...)
     for (int e = tid; e < 8 * 8; e += blockDim.x) {
         const int r = e >> 3, ch = e & 7;
@@ -841,9 +855,40 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         }
     } else if (warp == 2) {
         // ================= refine warp =================
-        refine_warp_loop(k, d, p.C, p.labels, p.label_kind, SUMS, p.fv_part != nullptr, sbase + p.o_ring,
-                         sbase + p.o_misc + 272, a_stages, a_lab, b_lfull, sbase + p.o_cnt, lane, cn, stat_s,
-                         fvred + E_WARPS);
+        // drains the ring until every epilogue warp has signed off and all allocated slots are consumed
+        const RefineCtx rc{k, d, p.C, p.labels, p.label_kind, SUMS, p.fv_part != nullptr, sbase + p.o_ring,
+                           sbase + p.o_misc + 272, a_stages, a_lab, b_lfull, sbase + p.o_cnt, cn};
+        RefineStats rs;
+        for (;;) {
+            // cheap idle test first: three plain shared-memory loads per poll, no lock traffic while the ring is empty
+            uint32_t done = 0, alloc = 0, head = 0;
+            if (lane == 0) {
+                done = lds_u32_volatile(rc.a_qalloc + 8);
+                alloc = lds_u32_volatile(rc.a_qalloc);
+                head = lds_u32_volatile(rc.a_qalloc + 4);
+            }
+            done = __shfl_sync(0xffffffffu, done, 0);
+            alloc = __shfl_sync(0xffffffffu, alloc, 0);
+            head = __shfl_sync(0xffffffffu, head, 0);
+            if (alloc != head) {
+                refine_batch(rc, lane, rs);
+                continue;
+            }
+            // `done` was read before `alloc`: an epilogue warp signs off after its last allocation
+            if (done == (uint32_t)E_WARPS) break;
+            __nanosleep(200);
+        }
+        if (rc.want_fv) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rs.fv += __shfl_xor_sync(0xffffffffu, rs.fv, o);
+        }
+        if (lane == 0) {
+            atomicAdd(stat_s + 0, rs.n_und);
+            atomicAdd(stat_s + 1, rs.n_pairs);
+            atomicAdd(stat_s + 2, rs.n_full);
+            atomicAdd(stat_s + 3, rs.n_batches);
+            fvred[E_WARPS] = rs.fv;
+        }
     } else if (SUMS && warp >= A_FIRST) {
         // ================= accumulator warps =================
         const int a = warp - A_FIRST;
