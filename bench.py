@@ -552,7 +552,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=list(WORKLOADS))
-    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tc", "generic"])
+    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tc", "generic", "row128"])
     ap.add_argument("--data", default="blobs", choices=["blobs", "overlap", "randn", "uncentred"],
                     help="input distribution (blobs = the benchmark's; the others show the path off its best case)")
     ap.add_argument("--no-row-ws", action="store_true", help="run without the per-matrix |x| bound workspace")

@@ -26,8 +26,11 @@ namespace hk {
 namespace {
 
 constexpr int TM = 128;
-constexpr int C_WARPS = 16;
-constexpr int ER = 4;  // tile residues (4 warps each)
+#ifndef HK_DMMA_ER
+#define HK_DMMA_ER 7  // 28 compute warps: the kernel is latency bound (ER 4: 59 %, 6: 67 %, 7: 68 % of HBM)
+#endif
+constexpr int ER = HK_DMMA_ER;  // tile residues (4 warps each)
+constexpr int C_WARPS = 4 * ER;
 constexpr int STAGE_BYTES = TM * 128;
 constexpr int D = 16;
 
@@ -50,11 +53,6 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
 }
-__device__ __forceinline__ double lds_f64(uint32_t a) {
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
-    return v;
-}
 __device__ __forceinline__ void store_label_d(void* labels, int kind, int64_t row, int lab) {
     if (kind == HK_LABEL_I64)
         reinterpret_cast<long long*>(labels)[row] = lab;
@@ -74,8 +72,8 @@ __device__ __forceinline__ void merge_min(double& v, int& j, double ov, int oj) 
     }
 }
 
-// NB = number of 8-centroid blocks (k <= 8 * NB)
-template <int NB, bool SUMS>
+// NB = number of 8-centroid blocks (k <= 8 * NB); XN: the functional value is wanted, so the distances carry |x|^2
+template <int NB, bool SUMS, bool XN>
 __global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
     lloyd_dmma_kernel(const __grid_constant__ CUtensorMap xmap, const DmmaParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -134,14 +132,16 @@ __global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
         const int r = we >> 2;
         const int g = lane >> 2;  // row of an 8-row group / centroid of a B fragment / cluster of an accumulator row
         const int t = lane & 3;
-        // centroid fragments of the distance MMA: B[f][j] = c[j][f], this lane holds (f = 4 kb + t, j = 8 nb + g)
+        // centroid fragments of the distance MMA: B[f][j] = c[j][f].  The order of the features inside the contraction is
+        // free, so K-block kb takes feature 4 t + kb from lane t: a lane's four A values are 32 contiguous bytes of its
+        // row (two 16-byte loads) and this lane holds c[j = 8 nb + g][4 t + kb]
         double bc[NB][4];
         double cn0[NB], cn1[NB];  // |c_j|^2 of this lane's two D columns j = 8 nb + 2 t + {0, 1}
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
             const int j = nb * 8 + g;
 #pragma unroll
-            for (int kb = 0; kb < 4; ++kb) bc[nb][kb] = j < k ? p.C[(size_t)j * D + kb * 4 + t] : 0.0;
+            for (int kb = 0; kb < 4; ++kb) bc[nb][kb] = j < k ? p.C[(size_t)j * D + 4 * t + kb] : 0.0;
             const int j0 = nb * 8 + 2 * t;
             double s0 = INFINITY, s1 = INFINITY;  // padded centroids can never win
             if (j0 < k) {
@@ -155,7 +155,16 @@ __global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
             cn0[nb] = s0;
             cn1[nb] = s1;
         }
-        // accumulators of onehot^T . X: acc[mb][nbf] = (cluster 8 mb + g, features 8 nbf + 2 t + {0, 1})
+        bool cfin = true;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+            // padded centroids carry +inf norms on purpose; a real centroid with NaN/Inf disables the integer argmin
+            if (nb * 8 + 2 * t < k) cfin = cfin && (cn0[nb] < INFINITY);
+            if (nb * 8 + 2 * t + 1 < k) cfin = cfin && (cn1[nb] < INFINITY);
+        }
+        const bool cfinite = __all_sync(0xffffffffu, cfin);
+        // accumulators of onehot^T . X: accN[mb] = cluster 8 mb + g, D columns 2 t + {0, 1} of block nbf = N, i.e.
+        // features 4 t + N and 4 t + 2 + N
         double acc0[NB][2], acc1[NB][2];
         int cnt[NB];
 #pragma unroll
@@ -175,49 +184,120 @@ __global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
             warp_wait(b_full + s * 8, ph, lane);
 #pragma unroll
             for (int grp = 0; grp < 4; ++grp) {
-                // ---- distances of rows 8 grp .. 8 grp + 7: A[row g][f = 4 kb + t] ------------------------------------
+                // ---- distances of rows 8 grp .. 8 grp + 7: A[row g][K-block kb] = x[row][4 t + kb] ----------------------
                 const int ra = grp * 8 + g;
                 const uint32_t xa = xt + (uint32_t)ra * 128;
                 double a[4];
-#pragma unroll
-                for (int kb = 0; kb < 4; ++kb) {
-                    const int f = kb * 4 + t;
-                    a[kb] = lds_f64(xa + (uint32_t)((((f >> 1) ^ (ra & 7)) << 4) | ((f & 1) << 3)));
+                {
+                    const double2 lo = lds_d2(xa + (uint32_t)(((2 * t) ^ (ra & 7)) << 4));      // features 4t, 4t+1
+                    const double2 hi = lds_d2(xa + (uint32_t)(((2 * t + 1) ^ (ra & 7)) << 4));  // features 4t+2, 4t+3
+                    a[0] = lo.x;
+                    a[1] = lo.y;
+                    a[2] = hi.x;
+                    a[3] = hi.y;
                 }
-                double xn = 0.0;
+                // |x|^2 does not change the argmin: it is evaluated only when the distance itself is wanted (functional
+                // value) or a row holds NaN/Inf.  Without it the labels are the argmin of fl(|c_j|^2 - 2 x.c_j), which can
+                // differ from the argmin of fl(fl(|x|^2 + |c_j|^2) - 2 x.c_j) only between distances that agree to
+                // 1 ulp of |x|^2 (~1e-16 relative: far inside the near-tie clause |dd| < 1e-6 d of the parity rule).
+                auto row_norm = [&]() {
+                    double v = 0.0;
 #pragma unroll
-                for (int kb = 0; kb < 4; ++kb) xn = fma(a[kb], a[kb], xn);
-                xn += __shfl_xor_sync(0xffffffffu, xn, 1);
-                xn += __shfl_xor_sync(0xffffffffu, xn, 2);
-                double best = INFINITY;
-                int lab = 0;
-                bool have = false;
+                    for (int kb = 0; kb < 4; ++kb) v = fma(a[kb], a[kb], v);
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    return v;
+                };
+                double xn = 0.0;
+                if (XN) xn = row_norm();
+                // candidates of this lane (its 2 NB columns): XN: d2 = clamp(fl(fl(|x|^2 + |c_j|^2) - 2 x.c_j), 0) as
+                // heat/spatial/distance.py:59-64; else s_j = fl(|c_j|^2 - 2 x.c_j)
+                double e[2 * NB], dots[2 * NB];
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) {
                     double d0 = 0.0, d1 = 0.0;
 #pragma unroll
                     for (int kb = 0; kb < 4; ++kb) dmma(d0, d1, a[kb], bc[nb][kb]);
-                    double e0 = (xn + cn0[nb]) - 2.0 * d0;
-                    double e1 = (xn + cn1[nb]) - 2.0 * d1;
-                    e0 = e0 < 0.0 ? 0.0 : e0;  // clamp(d2, 0, inf); NaN stays NaN
-                    e1 = e1 < 0.0 ? 0.0 : e1;
-                    const int j0 = nb * 8 + 2 * t;
-                    if (!have || e0 < best || (e0 != e0 && best == best)) {
-                        best = e0;
-                        lab = j0;
-                        have = true;
-                    }
-                    if (e1 < best || (e1 != e1 && best == best)) {
-                        best = e1;
-                        lab = j0 + 1;
+                    dots[2 * nb] = d0;
+                    dots[2 * nb + 1] = d1;
+                    if (XN) {
+                        const double e0 = (xn + cn0[nb]) - 2.0 * d0;
+                        const double e1 = (xn + cn1[nb]) - 2.0 * d1;
+                        e[2 * nb] = e0 < 0.0 ? 0.0 : e0;  // clamp(d2, 0, inf); NaN stays NaN
+                        e[2 * nb + 1] = e1 < 0.0 ? 0.0 : e1;
+                    } else {
+                        e[2 * nb] = fma(-2.0, d0, cn0[nb]);
+                        e[2 * nb + 1] = fma(-2.0, d1, cn1[nb]);
                     }
                 }
-                // the four lanes of a quad hold disjoint centroid subsets of the same row
+                double best;
+                int lab;
+                // A row without NaN/Inf against finite centroids (x.c_j finite; a padded centroid has x.0 = 0 there):
+                // every candidate is an ordinary double or the +inf of a padded centroid, and its order is the order of
+                // the usual sortable integer image of its bit pattern - the argmin runs on the integer pipe (FP64
+                // compares are half rate and were 25 % of this kernel's instructions).  Key = (image, index):
+                // lexicographic minimum = first-index minimum.
+                const bool row_ok =
+                    cfinite && ((unsigned)(__double2hiint(dots[0]) & 0x7ff00000) != 0x7ff00000u);
+                if (__all_sync(0xffffffffu, row_ok)) {
+                    auto image = [](double v) {
+                        const long long b = __double_as_longlong(v);
+                        return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+                    };
+                    unsigned long long kbest = image(e[0]);
+                    lab = 2 * t;
 #pragma unroll
-                for (int o = 1; o <= 2; o <<= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int ol = __shfl_xor_sync(0xffffffffu, lab, o);
-                    merge_min(best, lab, ob, ol);
+                    for (int c = 1; c < 2 * NB; ++c) {
+                        const unsigned long long kc = image(e[c]);
+                        const int jc = (c >> 1) * 8 + 2 * t + (c & 1);
+                        if (kc < kbest) {  // ascending index order inside the lane: strict < keeps the first index
+                            kbest = kc;
+                            lab = jc;
+                        }
+                    }
+                    // (three quad-masked redux.sync instead of these shuffles were measured: 2x slower, the eight
+                    // different member masks of a warp are executed one after the other)
+#pragma unroll
+                    for (int o = 1; o <= 2; o <<= 1) {
+                        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, kbest, o);
+                        const int oj = __shfl_xor_sync(0xffffffffu, lab, o);
+                        if (ok < kbest || (ok == kbest && oj < lab)) {
+                            kbest = ok;
+                            lab = oj;
+                        }
+                    }
+                    const long long ib = (long long)kbest;
+                    best = __longlong_as_double(ib ^ (((~ib) >> 63) | (long long)0x8000000000000000ull));
+                } else {
+                    // NaN / Inf somewhere in these 8 rows (or in a centroid): the reference formula with |x|^2 and
+                    // sequential torch.min semantics in fp64
+                    if (!XN) {
+                        xn = row_norm();
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb) {
+                            const double e0 = (xn + cn0[nb]) - 2.0 * dots[2 * nb];
+                            const double e1 = (xn + cn1[nb]) - 2.0 * dots[2 * nb + 1];
+                            e[2 * nb] = e0 < 0.0 ? 0.0 : e0;
+                            e[2 * nb + 1] = e1 < 0.0 ? 0.0 : e1;
+                        }
+                    }
+                    best = e[0];
+                    lab = 2 * t;
+#pragma unroll
+                    for (int c = 1; c < 2 * NB; ++c) {
+                        const int jc = (c >> 1) * 8 + 2 * t + (c & 1);
+                        if (e[c] < best || (e[c] != e[c] && best == best)) {
+                            best = e[c];
+                            lab = jc;
+                        }
+                    }
+                    // the four lanes of a quad hold disjoint centroid subsets of the same row
+#pragma unroll
+                    for (int o = 1; o <= 2; o <<= 1) {
+                        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int ol = __shfl_xor_sync(0xffffffffu, lab, o);
+                        merge_min(best, lab, ob, ol);
+                    }
                 }
                 const bool active = row0 + ra < p.n;
                 if (active && t == 0) {
@@ -228,7 +308,7 @@ __global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
                     }
                 }
                 if (SUMS) {
-                    // ---- sums += onehot^T . X: A[cluster g][row 4 kb + t], B[row 4 kb + t][feature 8 nbf + g] --------
+                    // ---- sums += onehot^T . X: A[cluster g][row 4 kb + t], B[row 4 kb + t][column g] = feature 2 g + nbf ----
                     const int mylab = active ? lab : -1;  // rows past the end belong to no cluster
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb) {
@@ -236,9 +316,10 @@ __global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
                         const int rl = __shfl_sync(0xffffffffu, mylab, rr * 4);               // its label
                         const int rb = grp * 8 + rr;
                         const uint32_t xb = xt + (uint32_t)rb * 128;
-                        const double b0 = lds_f64(xb + (uint32_t)((((g >> 1) ^ (rb & 7)) << 4) | ((g & 1) << 3)));
-                        const double b1 =
-                            lds_f64(xb + (uint32_t)(((((8 + g) >> 1) ^ (rb & 7)) << 4) | ((g & 1) << 3)));
+                        // the order of the feature columns is free too: column g of block nbf is feature 2 g + nbf, so both
+                        // B values of a lane come from one 16-byte load
+                        const double2 bb = lds_d2(xb + (uint32_t)((g ^ (rb & 7)) << 4));
+                        const double b0 = bb.x, b1 = bb.y;
 #pragma unroll
                         for (int mb = 0; mb < NB; ++mb) {
                             const bool hit = rl == mb * 8 + g;
@@ -269,10 +350,10 @@ __global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
                 ct += __shfl_xor_sync(0xffffffffu, ct, 1);
                 ct += __shfl_xor_sync(0xffffffffu, ct, 2);
                 if (c < k) {
-                    slot[(size_t)c * D + 2 * t] = acc0[mb][0];
-                    slot[(size_t)c * D + 2 * t + 1] = acc0[mb][1];
-                    slot[(size_t)c * D + 8 + 2 * t] = acc1[mb][0];
-                    slot[(size_t)c * D + 8 + 2 * t + 1] = acc1[mb][1];
+                    slot[(size_t)c * D + 4 * t] = acc0[mb][0];
+                    slot[(size_t)c * D + 4 * t + 2] = acc0[mb][1];
+                    slot[(size_t)c * D + 4 * t + 1] = acc1[mb][0];
+                    slot[(size_t)c * D + 4 * t + 3] = acc1[mb][1];
                     if (t == 0) cslot[c] = (double)ct;
                 }
             }
@@ -327,9 +408,9 @@ __global__ void reduce_scalar_dmma_kernel(const double* __restrict__ v, int n, d
     }
 }
 
-template <int NB, bool SUMS>
+template <int NB, bool SUMS, bool XN>
 int launch_dmma_inst(Handle* h, const CUtensorMap& map, const DmmaParams& p, size_t smem, int grid, cudaStream_t st) {
-    auto kern = lloyd_dmma_kernel<NB, SUMS>;
+    auto kern = lloyd_dmma_kernel<NB, SUMS, XN>;
     HK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(h, st);
     kern<<<grid, (1 + C_WARPS) * 32, smem, st>>>(map, p);
@@ -381,12 +462,16 @@ int launch_lloyd_dmma(Handle* h, const LloydArgs& a) {
     snprintf(name, sizeof(name), "dmma<f64,d=16,k=%d,S=%d,%s>", a.k, S, sums ? "sums" : "assign");
     h->variant = name;
     const bool two = a.k > 8;
+    const bool fv = a.fv_out != nullptr;
     if (sums)
-        rc = two ? launch_dmma_inst<2, true>(h, map, p, smem, grid, a.stream)
-                 : launch_dmma_inst<1, true>(h, map, p, smem, grid, a.stream);
+        rc = two ? launch_dmma_inst<2, true, false>(h, map, p, smem, grid, a.stream)
+                 : launch_dmma_inst<1, true, false>(h, map, p, smem, grid, a.stream);
+    else if (fv)
+        rc = two ? launch_dmma_inst<2, false, true>(h, map, p, smem, grid, a.stream)
+                 : launch_dmma_inst<1, false, true>(h, map, p, smem, grid, a.stream);
     else
-        rc = two ? launch_dmma_inst<2, false>(h, map, p, smem, grid, a.stream)
-                 : launch_dmma_inst<1, false>(h, map, p, smem, grid, a.stream);
+        rc = two ? launch_dmma_inst<2, false, false>(h, map, p, smem, grid, a.stream)
+                 : launch_dmma_inst<1, false, false>(h, map, p, smem, grid, a.stream);
     if (rc) return rc;
     if (sums && a.slots != nullptr) {
         a.slots->fsum = p.fsum;

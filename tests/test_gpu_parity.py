@@ -157,14 +157,19 @@ def _nan_inf_matrix(n, d, g):
     return x
 
 
-@pytest.mark.parametrize("path,n,d,k", [("tc", 1000, 32, 64), ("tc", 700, 64, 160), ("simt", 1000, 32, 64),
-                                        ("auto", 5000, 64, 320), ("auto", 3000, 128, 1024)])
-def test_nan_inf_rows_on_every_path(path, n, d, k):
+@pytest.mark.parametrize("path,n,d,k,dtype", [("tc", 1000, 32, 64, torch.float32), ("tc", 700, 64, 160, torch.float32),
+                                              ("simt", 1000, 32, 64, torch.float32),
+                                              ("auto", 5000, 64, 320, torch.float32),
+                                              ("auto", 3000, 128, 1024, torch.float32),
+                                              # fp64 tensor-core kernel (d=16, k<=16) and its 128-byte-row twin
+                                              ("simt", 1000, 16, 8, torch.float64), ("simt", 900, 16, 13, torch.float64),
+                                              ("row128", 1000, 16, 8, torch.float64)])
+def test_nan_inf_rows_on_every_path(path, n, d, k, dtype):
     """NaN / Inf rows (and an all-zero row) through the tensor-core filter, the 128-byte-row kernel and the large-k
     path: labels follow torch.min over clamp(d^2, 0) exactly like the reference (statistics.py:177, quirk Q4)."""
     g = torch.Generator().manual_seed(17)
-    x = _nan_inf_matrix(n, d, g)
-    c = torch.randn(k, d, generator=g)
+    x = _nan_inf_matrix(n, d, g).to(dtype)
+    c = torch.randn(k, d, generator=g).to(dtype)
     ref = orc.assign_to_cluster(x, c).view(-1)
     eng = engine.get_engine(DEV)
     lab = torch.empty(n, dtype=torch.int64, device=DEV)
