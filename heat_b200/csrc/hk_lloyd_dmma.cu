@@ -40,8 +40,8 @@ struct DmmaParams {
     const double* C;
     void* labels;
     int label_kind;
-    double* fsum;     // [grid*C_WARPS][k*16] or nullptr (assign only)
-    double* fcnt;     // [grid*C_WARPS][k]
+    double* fsum;     // [grid][k*16] or nullptr (assign only)
+    double* fcnt;     // [grid][k]
     double* fv_part;  // [grid] or nullptr
     int S;
     int num_tiles;
@@ -340,9 +340,10 @@ __global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
             }
         }
         if (SUMS) {
-            // this warp's slot: sums[cluster][feature] and counts (the 4 lanes of a quad saw different rows)
-            double* slot = p.fsum + ((size_t)blockIdx.x * C_WARPS + we) * (size_t)(k * D);
-            double* cslot = p.fcnt + ((size_t)blockIdx.x * C_WARPS + we) * (size_t)k;
+            // every warp's sums[cluster][feature] and counts go through shared memory (the row tiles are dead by then) and
+            // are added per CTA in a fixed order: one slot per CTA for the cross-CTA reduction
+            __syncthreads();  // all compute warps and the producer are past their last tile
+            double* wsl = reinterpret_cast<double*>(smem) + (size_t)we * (size_t)(k * (D + 1));
 #pragma unroll
             for (int mb = 0; mb < NB; ++mb) {
                 const int c = mb * 8 + g;
@@ -350,11 +351,11 @@ __global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
                 ct += __shfl_xor_sync(0xffffffffu, ct, 1);
                 ct += __shfl_xor_sync(0xffffffffu, ct, 2);
                 if (c < k) {
-                    slot[(size_t)c * D + 4 * t] = acc0[mb][0];
-                    slot[(size_t)c * D + 4 * t + 2] = acc0[mb][1];
-                    slot[(size_t)c * D + 4 * t + 1] = acc1[mb][0];
-                    slot[(size_t)c * D + 4 * t + 3] = acc1[mb][1];
-                    if (t == 0) cslot[c] = (double)ct;
+                    wsl[(size_t)c * D + 4 * t] = acc0[mb][0];
+                    wsl[(size_t)c * D + 4 * t + 2] = acc0[mb][1];
+                    wsl[(size_t)c * D + 4 * t + 1] = acc1[mb][0];
+                    wsl[(size_t)c * D + 4 * t + 3] = acc1[mb][1];
+                    if (t == 0) wsl[(size_t)k * D + c] = (double)ct;
                 }
             }
         }
@@ -364,7 +365,20 @@ __global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
             if (lane == 0) fvred[we] = fv_acc;
         }
     }
+    if (SUMS && warp == 0) __syncthreads();  // the producer's half of the barrier the compute warps take before writing
     __syncthreads();
+    if (SUMS) {
+        const int per = k * (D + 1);
+        const double* all = reinterpret_cast<const double*>(smem);
+        for (int i = tid; i < per; i += blockDim.x) {
+            double tsum = 0.0;
+            for (int w = 0; w < C_WARPS; ++w) tsum += all[(size_t)w * per + i];
+            if (i < k * D)
+                p.fsum[(size_t)blockIdx.x * (k * D) + i] = tsum;
+            else
+                p.fcnt[(size_t)blockIdx.x * k + (i - k * D)] = tsum;
+        }
+    }
     if (tid == 0 && p.fv_part != nullptr) {
         double tsum = 0.0;
         for (int w = 0; w < C_WARPS; ++w) tsum += fvred[w];
@@ -450,7 +464,7 @@ int launch_lloyd_dmma(Handle* h, const LloydArgs& a) {
     p.state = a.state;
     int grid = h->num_sms;
     if (grid > p.num_tiles) grid = p.num_tiles;
-    const int nslots = grid * C_WARPS;
+    const int nslots = grid;  // one slot per CTA (the warps are folded inside the kernel)
     const size_t kd = (size_t)a.k * D;
     rc = ensure_part(h, ((size_t)nslots * kd + (size_t)nslots * a.k + grid) * sizeof(double));
     if (rc) return rc;
