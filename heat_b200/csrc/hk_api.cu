@@ -130,6 +130,8 @@ int hk_destroy(hk_handle_t hh) {
     if (h->stats) cudaFree(h->stats);
     if (h->fin_sync) cudaFree(h->fin_sync);
     if (h->run_graph) cudaGraphExecDestroy(h->run_graph);
+    if (h->run_graph1) cudaGraphExecDestroy(h->run_graph1);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     delete h;
     return 0;
 }
@@ -248,10 +250,12 @@ int hk_lloyd_step(hk_handle_t hh, const void* X, int64_t n_local, int d, int64_t
                      allreduce, row_ws, row_ws_bytes, path, reinterpret_cast<cudaStream_t>(stream));
 }
 
+constexpr int RUN_CHUNK = 8;  // steps per replayed graph (the default sync_every of KMeans.fit)
+
 // `iters` Lloyd steps enqueued by one call.  The first step runs eagerly (it may grow scratch buffers and fills the
-// row workspace); the remaining ones are captured ONCE into a CUDA graph (2 kernel nodes per step) that is cached in the
-// handle and replayed for as long as the call shape stays the same, so a fit costs one graph launch per `sync_every`
-// iterations instead of 2 x sync_every kernel launches from Python.
+// row workspace); the remaining ones are replayed from two CUDA graphs (RUN_CHUNK steps / one step; 2 kernel nodes per
+// step) that are captured once and cached in the handle for as long as the call shape stays the same, so a fit costs
+// one graph launch per `sync_every` iterations instead of 2 x sync_every kernel launches from Python.
 int hk_lloyd_run(hk_handle_t hh, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, void* C, void* C_prev,
                  int k, int use_tol, double tol_cmp, void* shift2_out, int32_t* state, int allreduce, void* row_ws,
                  int64_t row_ws_bytes, int path, int iters, void* stream) {
@@ -267,8 +271,7 @@ int hk_lloyd_run(hk_handle_t hh, const void* X, int64_t n_local, int d, int64_t 
     };
     const size_t len = (size_t)k * (d + 1);
     const bool exchange = allreduce && h->nranks > 1;
-    const bool graphable = !h->profile && !h->no_graph && iters >= 3 && st != nullptr &&
-                           (!exchange || (h->peer_ready && len <= h->peer_cap));
+    const bool graphable = !h->profile && !h->no_graph && iters >= 3 && (!exchange || (h->peer_ready && len <= h->peer_cap));
     if (!graphable) {
         for (int i = 0; i < iters; ++i) {
             rc = one();
@@ -292,38 +295,56 @@ int hk_lloyd_run(hk_handle_t hh, const void* X, int64_t n_local, int d, int64_t 
         key[18] = (uint64_t)(uintptr_t)h->part;
         key[19] = (uint64_t)(uintptr_t)h->red;
     }
-    const int chunk = iters - done;
-    if (chunk <= 0) return 0;
-    if (!(h->run_graph && h->run_graph_key == key && h->run_graph_iters == chunk)) {
-        if (h->run_graph) {
-            cudaGraphExecDestroy(h->run_graph);
-            h->run_graph = nullptr;
-        }
-        cudaGraph_t g = nullptr;
-        HK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        for (int i = 0; i < chunk && rc == 0; ++i) rc = one();
-        const cudaError_t ce = cudaStreamEndCapture(st, &g);
-        if (rc || ce != cudaSuccess) {
-            if (g) cudaGraphDestroy(g);
-            cudaGetLastError();
-            if (rc) return rc;
-            set_error("hk_lloyd_run: stream capture failed: %s", cudaGetErrorString(ce));
-            return 1000 + (int)ce;
-        }
-        const cudaError_t ie = cudaGraphInstantiate(&h->run_graph, g, 0);
-        cudaGraphDestroy(g);
-        if (ie != cudaSuccess) {
-            h->run_graph = nullptr;
-            set_error("hk_lloyd_run: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
-            return 1000 + (int)ie;
+    if (!(h->run_graph && h->run_graph_key == key)) {
+        // (re)capture: one graph of RUN_CHUNK steps and one of a single step, replayed as often as `iters` needs, so a
+        // different iteration count never recaptures.  Capture happens on a stream of the library's own (the caller's may
+        // be the legacy default stream, which cannot be captured); the graphs are launched into the caller's stream.
+        if (h->run_graph) cudaGraphExecDestroy(h->run_graph);
+        if (h->run_graph1) cudaGraphExecDestroy(h->run_graph1);
+        h->run_graph = h->run_graph1 = nullptr;
+        if (!h->cap_stream) HK_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+        cudaStream_t cs = h->cap_stream;
+        for (int which = 0; which < 2; ++which) {
+            const int nsteps = which == 0 ? RUN_CHUNK : 1;
+            cudaGraph_t g = nullptr;
+            HK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+            for (int i = 0; i < nsteps && rc == 0; ++i)
+                rc = step_impl(h, X, n_local, d, ldx, dtype, C, C_prev, k, nullptr, HK_LABEL_NONE, use_tol, tol_cmp,
+                               shift2_out, state, allreduce, row_ws, row_ws_bytes, path, cs);
+            const cudaError_t ce = cudaStreamEndCapture(cs, &g);
+            if (rc || ce != cudaSuccess) {
+                if (g) cudaGraphDestroy(g);
+                cudaGetLastError();
+                if (rc) return rc;
+                set_error("hk_lloyd_run: stream capture failed: %s", cudaGetErrorString(ce));
+                return 1000 + (int)ce;
+            }
+            cudaGraphExec_t* dst = which == 0 ? &h->run_graph : &h->run_graph1;
+            const cudaError_t ie = cudaGraphInstantiate(dst, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) {
+                *dst = nullptr;
+                set_error("hk_lloyd_run: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+                return 1000 + (int)ie;
+            }
+            HK_CUDA(cudaGraphUpload(*dst, st));  // pay the upload now, not at the first replay
         }
         h->run_graph_key = key;
-        h->run_graph_iters = chunk;
         h->graph_builds++;
     }
-    HK_CUDA(cudaGraphLaunch(h->run_graph, st));
-    h->launches += 2 * (int64_t)chunk;
-    h->graph_launches++;
+    int left = iters - done;
+    while (left >= RUN_CHUNK) {
+        HK_CUDA(cudaGraphLaunch(h->run_graph, st));
+        h->launches += 2 * (int64_t)RUN_CHUNK;
+        h->graph_launches++;
+        left -= RUN_CHUNK;
+    }
+    while (left > 0) {
+        HK_CUDA(cudaGraphLaunch(h->run_graph1, st));
+        h->launches += 2;
+        h->graph_launches++;
+        --left;
+    }
     return 0;
 }
 

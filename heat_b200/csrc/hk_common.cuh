@@ -64,8 +64,8 @@ struct Handle {
     // ticket + executed-exchange counter of the finish kernel (device, 2 x u32)
     unsigned int* fin_sync = nullptr;
     // CUDA graph of the last hk_lloyd_run call shape
-    cudaGraphExec_t run_graph = nullptr;
-    int run_graph_iters = 0;
+    cudaGraphExec_t run_graph = nullptr, run_graph1 = nullptr;
+    cudaStream_t cap_stream = nullptr;
     bool no_graph = false;
     int64_t graph_builds = 0, graph_launches = 0;
     std::vector<uint64_t> run_graph_key;
