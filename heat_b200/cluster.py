@@ -46,8 +46,9 @@ class KMeans(BaseEstimator):
     """K-Means clustering (Lloyd's algorithm) — drop-in for ``heat.cluster.KMeans``.
 
     Parameters are those of the reference (heat/cluster/kmeans.py:55-62).  ``init`` may be a DNDarray of
-    shape (n_clusters, n_features) (the parity entry point, _kcluster.py:136-143) or ``"random"``.
-    The k-means|| / batchparallel initialisers are not part of the accelerated path.
+    shape (n_clusters, n_features) (the parity entry point, _kcluster.py:136-143), ``"random"`` or ``"kmeans++"`` /
+    ``"probability_based"`` (k-means||, _kcluster.py:146-245, with the N-sized work on the device).
+    ``"batchparallel"`` is a different algorithm and not part of this path.
     """
 
     def __init__(self, n_clusters: int = 8, init: Union[str, DNDarray] = "random", max_iter: int = 300,
@@ -122,10 +123,118 @@ class KMeans(BaseEstimator):
             g.manual_seed(0 if self.random_state is None else int(self.random_state))
             idx = torch.randint(0, max(x.shape[0] - 1, 1), (self.n_clusters,), generator=g)
             self._cluster_centers = _gather_rows(x, idx)
+        elif self.init == "probability_based":
+            self._cluster_centers = self._probability_based_init(x, oversampling, iter_multiplier)
         else:
             raise NotImplementedError(
-                f'init="{self.init}" is outside the accelerated path (SURVEY.md §8f N2); pass a DNDarray of '
-                'initial centroids or init="random"')
+                'init="batchparallel" runs a different algorithm (per-rank k-means + hierarchical merge, '
+                'heat/cluster/batchparallelclustering.py) and is not part of this path; use "kmeans++", "random" or a '
+                "DNDarray of initial centroids")
+
+    # -- k-means|| initialisation (reference: _kcluster.py:146-245, 283-350) ------------------------------------
+    def _probability_based_init(self, x: DNDarray, oversampling: float, iter_multiplier: float) -> DNDarray:
+        """``init="kmeans++"`` / ``"probability_based"``: the reference's k-means|| scheme with the device doing the
+        N-sized work.  Same structure as the reference: one uniformly drawn row; ``int(iter_multiplier * log(cost))``
+        rounds in which every row joins the candidate set with probability ``oversampling * d / sum(d)`` (d = distance
+        to the nearest candidate so far; the reference samples on distances, not squared distances); candidates are
+        weighted by the number of rows closest to them and reclustered to ``n_clusters`` centroids by weighted
+        k-means++ seeding plus Lloyd iterations on the (small) candidate set.  Distances to the rows come from
+        ``hk_cdist`` on the NEW candidates of a round only (a running minimum per row is kept), the weights from
+        ``hk_assign``.  Random numbers come from torch generators seeded with ``random_state`` (Heat's own counter-based
+        generator is not reproduced, so the sampled rows differ from the reference's for the same seed)."""
+        import math
+        import warnings
+
+        xl, cdtype = _device_operands(x)
+        dev = xl.device
+        eng = _engine.get_engine(dev)
+        comm = x.comm
+        distributed = x.split is not None and comm.is_distributed()
+        if distributed:
+            eng.init_comm(comm)
+        n_loc, d = xl.shape
+        seed = 0 if self.random_state is None else int(self.random_state)
+        g_all = torch.Generator().manual_seed(seed)  # identical stream on every rank: global decisions
+        g_loc = torch.Generator(device=dev).manual_seed(seed * 7919 + 104729 * (comm.rank if distributed else 0) + 1)
+
+        def allsum(v: torch.Tensor) -> torch.Tensor:
+            if distributed:
+                comm.Allreduce(IN_PLACE, v)
+            return v
+
+        def fold_min(dmin: torch.Tensor, new: torch.Tensor) -> None:
+            # dmin[i] = min(dmin[i], min_j |x_i - new_j|): hk_cdist on row blocks that keep the temporary below 1 GiB
+            m = new.shape[0]
+            if m == 0 or n_loc == 0:
+                return
+            rows = max(1024, min(n_loc, (1 << 28) // max(m, 1)))
+            buf = torch.empty((min(rows, n_loc), m), dtype=cdtype, device=dev)
+            for r0 in range(0, n_loc, rows):
+                r1 = min(n_loc, r0 + rows)
+                out = buf[: r1 - r0]
+                eng.cdist(xl[r0:r1], new, out, quadratic_expansion=True)
+                torch.minimum(dmin[r0:r1], out.min(dim=1).values, out=dmin[r0:r1])
+
+        idx0 = torch.randint(0, max(x.shape[0] - 1, 1), (1,), generator=g_all)
+        first = _gather_rows(x, idx0).larray.to(cdtype).contiguous()  # (1, d), replicated
+        dmin0 = torch.full((n_loc,), float("inf"), dtype=cdtype, device=dev)
+        fold_min(dmin0, first)
+        cost0 = float(allsum(dmin0.sum(dtype=torch.float64).reshape(1))[0])
+        num_iters = max(1, int(iter_multiplier * math.log(cost0))) if cost0 > 0 else 1
+
+        def sample(ovs: float) -> torch.Tensor:
+            cents, dmin = first, dmin0.clone()
+            for _ in range(num_iters):
+                total = float(allsum(dmin.sum(dtype=torch.float64).reshape(1))[0])
+                prob = dmin * (ovs / max(total, 1e-12))
+                pick = torch.rand(n_loc, generator=g_loc, device=dev, dtype=cdtype) <= prob
+                local = xl[pick].reshape(-1, d)
+                new = comm.Allgatherv_rows(local) if distributed else local
+                if new.shape[0]:
+                    new = new.contiguous()
+                    cents = torch.cat([cents, new], dim=0)
+                    fold_min(dmin, new)
+            return cents
+
+        cents = sample(float(oversampling))
+        if cents.shape[0] <= self.n_clusters:
+            warnings.warn(f"Oversampling={oversampling} is too low for data set."
+                          "Increasing it by factor 10 automatically. And restarting centroid initialization.", UserWarning)
+            oversampling = 10 * oversampling
+            cents = sample(float(oversampling))
+        if cents.shape[0] <= self.n_clusters:
+            raise ValueError(f"The parameter oversampling={oversampling} and/or iter_multiplier={iter_multiplier} "
+                             "are chosen too small for the initialization of cluster centers.")
+        # weights = number of rows closest to each candidate
+        m = cents.shape[0]
+        lab = torch.empty(n_loc, dtype=torch.int32, device=dev)
+        eng.assign(xl, cents.contiguous(), lab)
+        weights = allsum(torch.bincount(lab.long(), minlength=m).to(torch.float64))
+        # recluster the candidates (m x d, small): weighted k-means++ seeding + Lloyd, identically on every rank
+        # (reference: batchparallelclustering.py:23-88 run on rank 0 and broadcast)
+        xc, w = cents.double().cpu(), weights.cpu()
+        k = self.n_clusters
+        idxs = torch.zeros(k, dtype=torch.long)
+        idxs[0] = torch.randint(0, m, (1,), generator=g_all)
+        for i in range(1, k):
+            dist = torch.cdist(xc, xc[idxs[:i]]).min(dim=1).values
+            p = w * dist
+            if float(p.sum()) <= 0:  # fewer distinct candidates than clusters
+                p = torch.ones(m, dtype=torch.float64)
+            idxs[i] = torch.multinomial(p, 1, generator=g_all)
+        centers = xc[idxs].clone()
+        tol = 0.0 if self.tol is None else float(self.tol)
+        for _ in range(int(self.max_iter)):
+            labels = torch.cdist(xc, centers).argmin(dim=1)
+            old = centers.clone()
+            for i in range(k):
+                sel = labels == i
+                if bool(sel.any()):  # an empty cluster keeps its centre
+                    centers[i] = xc[sel].mean(dim=0)
+            if torch.allclose(centers, old, atol=tol):
+                break
+        out = centers.to(device=dev, dtype=xl.dtype if x.larray.dtype in _FLOATS else cdtype)
+        return DNDarray(out, (k, d), out.dtype, None, dev, comm, True)
 
     # -- the hot loop -------------------------------------------------------------------------------------
     def fit(self, x: DNDarray, oversampling: float = 2, iter_multiplier: float = 1):

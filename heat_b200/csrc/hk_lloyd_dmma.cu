@@ -104,6 +104,15 @@ __global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
     }
     __syncthreads();
 
+    // per-warp results live in registers across the role code (declared here so that every thread of the block meets
+    // the same block-wide barriers after it)
+    double acc0[NB][2], acc1[NB][2];
+    int cnt[NB];
+#pragma unroll
+    for (int mb = 0; mb < NB; ++mb) {
+        acc0[mb][0] = acc0[mb][1] = acc1[mb][0] = acc1[mb][1] = 0.0;
+        cnt[mb] = 0;
+    }
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
@@ -125,6 +134,7 @@ __global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
                 }
             }
         }
+        __syncwarp();  // lanes 1-31 must not run ahead to the block-wide barriers below while lane 0 still produces
     } else {
         // ================= compute warps =================
         const int we = warp - 1;
@@ -165,13 +175,6 @@ __global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
         const bool cfinite = __all_sync(0xffffffffu, cfin);
         // accumulators of onehot^T . X: accN[mb] = cluster 8 mb + g, D columns 2 t + {0, 1} of block nbf = N, i.e.
         // features 4 t + N and 4 t + 2 + N
-        double acc0[NB][2], acc1[NB][2];
-        int cnt[NB];
-#pragma unroll
-        for (int mb = 0; mb < NB; ++mb) {
-            acc0[mb][0] = acc0[mb][1] = acc1[mb][0] = acc1[mb][1] = 0.0;
-            cnt[mb] = 0;
-        }
         double fv_acc = 0.0;
         const bool want_fv = p.fv_part != nullptr;
         const int label_kind = p.label_kind;
@@ -339,10 +342,18 @@ __global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
                 ph ^= 1;
             }
         }
-        if (SUMS) {
-            // every warp's sums[cluster][feature] and counts go through shared memory (the row tiles are dead by then) and
-            // are added per CTA in a fixed order: one slot per CTA for the cross-CTA reduction
-            __syncthreads();  // all compute warps and the producer are past their last tile
+        if (want_fv) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) fv_acc += __shfl_xor_sync(0xffffffffu, fv_acc, o);
+            if (lane == 0) fvred[we] = fv_acc;
+        }
+    }
+    __syncthreads();  // all compute warps and the producer are past their last tile: the row tiles are dead
+    if (SUMS) {
+        // every compute warp's sums[cluster][feature] and counts go through shared memory and are added per CTA in a
+        // fixed order: one slot per CTA for the cross-CTA reduction
+        if (warp >= 1) {
+            const int we = warp - 1, g = lane >> 2, t = lane & 3;
             double* wsl = reinterpret_cast<double*>(smem) + (size_t)we * (size_t)(k * (D + 1));
 #pragma unroll
             for (int mb = 0; mb < NB; ++mb) {
@@ -359,15 +370,7 @@ __global__ void __launch_bounds__((1 + C_WARPS) * 32, 1)
                 }
             }
         }
-        if (want_fv) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) fv_acc += __shfl_xor_sync(0xffffffffu, fv_acc, o);
-            if (lane == 0) fvred[we] = fv_acc;
-        }
-    }
-    if (SUMS && warp == 0) __syncthreads();  // the producer's half of the barrier the compute warps take before writing
-    __syncthreads();
-    if (SUMS) {
+        __syncthreads();
         const int per = k * (D + 1);
         const double* all = reinterpret_cast<const double*>(smem);
         for (int i = tid; i < per; i += blockDim.x) {
@@ -436,6 +439,7 @@ int launch_dmma_inst(Handle* h, const CUtensorMap& map, const DmmaParams& p, siz
 
 }  // namespace
 
+
 bool dmma_supported(const Handle* h, const LloydArgs& a) {
     (void)h;
     if (a.dtype != HK_F64 || a.d != D) return false;
@@ -448,7 +452,13 @@ bool dmma_supported(const Handle* h, const LloydArgs& a) {
 
 int launch_lloyd_dmma(Handle* h, const LloydArgs& a) {
     const bool sums = a.partials != nullptr;
-    const int S = 12;  // 12 x 16 KB row tiles in flight per SM
+    // Stages in flight per SM: a MULTIPLE of the number of tile residues, so that every stage is always consumed by the
+    // same four warps.  A warp waits on a stage's "full" barrier with a one-bit phase parity; if consecutive uses of a
+    // stage belonged to different warps, a warp could reach its wait while the PREVIOUS use's TMA load is still in flight
+    // (loads complete out of order), see the parity of the phase before and walk on without data.  Observed as a hang
+    // once in a few hundred million tiles with 12 stages and 7 residues.
+    const int S = 2 * ER;  // 14 x 16 KB row tiles
+    static_assert((2 * ER) % ER == 0 && 2 * ER <= 16, "stage count must be a multiple of the residue count");
     const size_t smem = (size_t)S * STAGE_BYTES + 32 * 8 + C_WARPS * 8 + 1024;
     CUtensorMap map;
     int rc = make_tensor_map_2d(&map, a.X, 8, (uint64_t)a.n, (uint64_t)a.d, (uint64_t)a.ldx, (uint32_t)a.d, TM, 128);

@@ -194,6 +194,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS : 0)) 
                 }
             }
         }
+        __syncwarp();  // lanes 1-31 must not run ahead to the block-wide barriers below while lane 0 still produces
     } else if (warp >= E_FIRST && warp < E_FIRST + E_WARPS) {
         // ================= distance warps =================
         const int we = warp - E_FIRST;
@@ -439,7 +440,9 @@ struct RowPlan {
 
 RowPlan plan_row(const Handle* h, int k, bool sums) {
     RowPlan pl{0, 0, false};
-    for (int S = 12; S >= 4; --S) {
+    // a multiple of the residue counts (4 distance-warp groups, 2 accumulator groups): every stage is then always
+    // consumed by the same warps, which keeps their one-bit phase parities unambiguous
+    for (int S = 12; S >= 4; S -= ER) {
         RowLayout L = row_layout(k, S, sums);
         if (L.total <= (size_t)h->smem_optin) {
             pl.S = S;

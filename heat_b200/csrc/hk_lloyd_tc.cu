@@ -512,10 +512,8 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 16 + s, 4 + (SUMS ? 4 : 0));
             mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 32 + s, 4);
         }
-        for (int b = 0; b < NBUF; ++b) {
-            mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 48 + b, 1);
-            mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 64 + b, 4);
-        }
+        for (int b = 0; b < 16; ++b) mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 48 + b, 1);  // tfull ring
+        for (int b = 0; b < NBUF; ++b) mbar_init(reinterpret_cast<uint64_t*>(smem + p.o_bars) + 64 + b, 4);
         mbar_fence_init();
         tma_prefetch_desc(&xmap);
         *cmax_s = 0.f;
@@ -664,7 +662,8 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         const uint64_t bext_d = umma_desc_k_sw128(sbase + p.o_Bext);
         int s = mpar % S, b = mpar % NBUF;
         uint32_t ph = (uint32_t)((mpar / S) & 1), bph = (uint32_t)((mpar / NBUF) & 1);
-        for (int tile = blockIdx.x + mpar * gridDim.x; tile < ntiles; tile += HK_TC_MI * gridDim.x) {
+        int il = mpar;  // local tile counter of this CTA
+        for (int tile = blockIdx.x + mpar * gridDim.x; tile < ntiles; tile += HK_TC_MI * gridDim.x, il += HK_TC_MI) {
             TC_T(t0 = clock64();)
             mbar_wait_a(b_tempty + b * 8, bph ^ 1);
             TC_T(t1 = clock64();)
@@ -687,8 +686,10 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                         umma_tf32(dcol, ad, bd, idesc, 1u);  // D += x . (-2 c_j)
                     }
                 }
+                // "accumulator ready" goes to a ring of 16 barriers indexed by the local tile number, not to one barrier per
+                // TMEM buffer: see the wait in the epilogue
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                 b_tfull + b * 8)
+                                 b_tfull + (uint32_t)(il & 15) * 8)
                              : "memory");
             }
             __syncwarp();
@@ -732,7 +733,6 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         int s = r % S;
         uint32_t ph = (uint32_t)((r / S) & 1);
         int b = r % NBUF;
-        uint32_t bph = (uint32_t)((r / NBUF) & 1);
         int i = r;  // local tile counter of this CTA
         for (int tile = blockIdx.x + r * gridDim.x; tile < ntiles; tile += ER * gridDim.x, i += ER) {
             TC_T(t0 = clock64();)
@@ -741,9 +741,24 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             const bool active = grow < n32;
 
             float xn, xs;  // |x|^2 and |x| of this row, or upper bounds for every row of the tile
-            // x tile landed.  Observed here even when only the cached bound is read, so that the labels published
-            // below order the accumulator warps after the TMA writes without a wait of their own.
-            warp_wait(b_full + s * 8, ph, lane);
+            // One-bit phase parities and shared barriers: consecutive uses of a stage belong to DIFFERENT epilogue warps
+            // (3 residues over S stages), so a warp can reach a wait while the PREVIOUS use is still incomplete (TMA loads
+            // land out of order), see the parity of the phase before and walk on.  Hence
+            //  * this warp waits on the stage's "full" barrier only when it reads the tile itself (first pass over a
+            //    matrix / no row workspace), and then first on what the producer waits for before it issues THIS tile - the
+            //    stage released by all consumers of the previous use - after which the parity is unambiguous;
+            //  * "accumulator ready" is a ring of 16 barriers indexed by the tile number: the previous use of the same
+            //    barrier lies 16 tiles back, and a tile that far back has been consumed completely before the producer
+            //    could issue the tile this warp finished last (S <= 12 stages), so there the parity cannot alias.
+            // With a cached bound the tile is not touched here: the labels published below are ordered after the TMA
+            // writes through the MMA (it consumed the tile before it signalled "accumulator ready").
+            if (xn_mode != XN_READ) {
+                if (lane == 0) {
+                    mbar_wait_a(b_empty + s * 8, ph ^ 1);
+                    mbar_wait_a(b_full + s * 8, ph);
+                }
+                __syncwarp();
+            }
             if (xn_mode == XN_READ) {
                 xs = __ldg(p.bounds + tile);  // the cache holds an upper bound of max |x| over the tile
                 xn = xs * xs;
@@ -760,7 +775,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             }
             const float E2 = 2.002f * (beta2 * xs * cpmax + gam * (xn + cmax2));
 
-            warp_wait(b_tfull + b * 8, bph, lane);  // accumulator ready: s_j = |c_j|^2 - 2 x.c'_j (TF32)
+            warp_wait(b_tfull + (uint32_t)(i & 15) * 8, (uint32_t)((i >> 4) & 1), lane);  // s_j = |c_j|^2 - 2 x.c'_j (TF32)
             TC_T(t1 = clock64();
                  if (p.tl && blockIdx.x == 0 && q == 0 && lane == 0 && i < 512) p.tl[i * 8 + 2] = clock64();)
             tc_fence_after();
@@ -865,7 +880,8 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
             TC_T(t2 = clock64();)
             if (!SUMS && want_fv && active && !cold) {
                 // functional value of a decided row: exact distance to its centroid
-                mbar_wait_a(b_full + s * 8, ph);  // this thread is about to read the x tile itself
+                mbar_wait_a(b_empty + s * 8, ph ^ 1);  // (see above) then the tile itself
+                mbar_wait_a(b_full + s * 8, ph);
                 const float sq = sqrtf(exact_pair_inl(xt, row, p.C, lab, d, cn[lab]));
                 fv_acc += (double)(sq * sq);
             }
@@ -905,10 +921,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 ph ^= 1;
             }
             b += ER;
-            while (b >= NBUF) {
-                b -= NBUF;
-                bph ^= 1;
-            }
+            while (b >= NBUF) b -= NBUF;
             TC_T(tw0 += t1 - t0; tw1 += t2 - t1; tw2 += clock64() - t2;)
         }
         if (want_fv) {
@@ -1167,8 +1180,11 @@ TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
     if ((size_t)8 * (k + 1) * d * 4 > 80 * 1024) pl.NA = 4;
     if (sums && (size_t)pl.NA * (k + 1) * d * 4 > 100 * 1024) return pl;
     // TMEM: nbuf distance buffers of nk columns each (at most 8, 512 columns in all)
+    // (an EVEN number: the two MMA warps alternate over the buffers and wait on their "empty" barriers with one-bit
+    // parities, so consecutive uses of a buffer must belong to the same warp - see the note at the epilogue's wait)
     int nb = 512 / pl.nk;
     pl.nbuf = nb > 8 ? 8 : nb;
+    if (pl.nbuf > 2) pl.nbuf &= ~1;
     uint32_t cols = 32;
     while (cols < (uint32_t)(pl.nbuf * pl.nk)) cols <<= 1;
     pl.tmem_cols = cols;
@@ -1176,7 +1192,7 @@ TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
 #ifndef HK_TC_SMAX
 #define HK_TC_SMAX 12
 #endif
-    for (int S = HK_TC_SMAX; S >= 4; --S) {
+    for (int S = HK_TC_SMAX & ~1; S >= 4; S -= 2) {  // even: the MMA / accumulator warps alternate over the stages
         TcLayout L = tc_layout(d, k, pl.nk, S, pl.NA, sums);
         if (L.total <= budget) {
             pl.S = S;

@@ -168,7 +168,33 @@ __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
-#ifdef HK_MBAR_SPIN
+#ifdef HK_WATCHDOG
+    // debugging aid: a wait that lasts longer than ~2 s reports who is stuck on what and kills the kernel
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.b32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(0x989680u)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000ll) {
+            printf("hk watchdog: block %d warp %d lane %d stuck on mbarrier smem+0x%x parity %u\n", (int)blockIdx.x,
+                   (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31), bar, parity);
+            __trap();
+        }
+    }
+#elif defined(HK_MBAR_CLOOP)
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.b32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(0x989680u)
+            : "memory");
+    } while (!ok);
+#elif defined(HK_MBAR_SPIN)
     asm volatile(
         "{\n"
         ".reg .pred p;\n"

@@ -23,6 +23,8 @@ CASES = {
     "overlap_f64_d16_k8": dict(n=20000, d=16, k=8, dtype="f64", max_iter=40, tol=1e-6, offset=0.5),
     "empty_cluster_f32": dict(n=5000, d=8, k=5, dtype="f32", max_iter=10, tol=1e-4, kind="empty"),
     "mixed_f64data_f32init": dict(n=8000, d=16, k=8, dtype="f64", init_dtype="f32", max_iter=50, tol=1e-4),
+    # float32 data + float64 centroids: the reference promotes both operands of cdist to float64 (distance.py:392-395)
+    "mixed_f32data_f64init": dict(n=8000, d=16, k=8, dtype="f32", init_dtype="f64", max_iter=50, tol=1e-4),
     "replicated_f32": dict(n=6000, d=8, k=6, dtype="f32", max_iter=50, tol=1e-4, split=None),
     "odd_d5_k3_f32": dict(n=7001, d=5, k=3, dtype="f32", max_iter=50, tol=1e-4),
     "wide_d128_k32_f32": dict(n=6000, d=128, k=32, dtype="f32", max_iter=30, tol=1e-4),

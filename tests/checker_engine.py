@@ -66,12 +66,15 @@ class CheckerEngine:
         c_prev.copy_(c)
         self.lloyd_finalize(part, c.clone(), c, use_tol, tol_cmp, shift2, state)
 
+    def cdist(self, x, y, out, quadratic_expansion, sqrt=True):
+        out.copy_(orc.cdist(x, y, quadratic_expansion))
+
     def assign(self, x, c, labels, fv=None, path="auto", row_ws=None):
         if x.shape[0] == 0:
             if fv is not None:
                 fv.zero_()
             return
         lab, mins = orc.assign_to_cluster(x, c, eval_functional_value=True)
-        labels.copy_(lab.to(labels.dtype))
+        labels.copy_(lab.to(labels.dtype).view(labels.shape))
         if fv is not None:
             fv[0] = float((mins.double() ** 2).sum())

@@ -1,0 +1,85 @@
+"""The Heat binding on CUDA: ``heat_b200.integration.install()`` patches the UNMODIFIED reference (installed in
+``baseline/_ref``, imported under ``oracle/mpi4py_shim``) and real ``ht.cluster.KMeans(init=DNDarray).fit/predict`` and
+``ht.spatial.cdist`` on CUDA DNDarrays run through libhkmeans.so; results are compared with the reference's own CPU
+outputs (tests/golden).  Reference entry points: heat/cluster/kmeans.py:105-148, heat/cluster/_kcluster.py:352-415,
+heat/spatial/distance.py:32-44."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+SHIM = os.path.join(ROOT, "oracle", "mpi4py_shim")
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ht():
+    if not os.path.isdir(os.path.join(REF, "heat")):
+        pytest.skip("baseline/_ref (pip install --target of the reference) is not present")
+    for q in (REF, SHIM):
+        if q not in sys.path:
+            sys.path.insert(0, q)
+    import heat
+
+    import heat_b200.integration as hki
+
+    assert hki.install() is True
+    yield heat
+    hki.uninstall()
+
+
+@pytest.mark.parametrize("name", ["blobs_f32_d32_k64", "blobs_f64_d16_k8", "config1_spherical", "empty_cluster_f32",
+                                  "overlap_f32_d4_k16", "replicated_f32"])
+def test_heat_kmeans_runs_on_the_native_path(ht, name):
+    from cases import CASES, make_case
+    from helpers import assert_fit_matches, load_golden
+    from heat_b200 import engine
+    from oracle import kmeans_oracle as orc
+
+    spec = CASES[name]
+    x, init = make_case(name)
+    gold = load_golden(name)
+    dev = torch.device("cuda", 0)
+    eng = engine.get_engine(dev)
+    l0 = eng.launch_count()
+    hx = ht.array(x, split=spec.get("split", 0), device="gpu")
+    hc = ht.array(init, device="gpu")
+    assert hx.larray.is_cuda
+    km = ht.cluster.KMeans(n_clusters=init.shape[0], init=hc, max_iter=spec["max_iter"], tol=spec["tol"])
+    km.fit(hx)
+    assert eng.launch_count() > l0, "the patched KMeans.fit did not launch a kernel of libhkmeans.so"
+    assert isinstance(km.cluster_centers_, ht.DNDarray) and km.cluster_centers_.larray.is_cuda
+    assert km.cluster_centers_.split is None and km.labels_.split == spec.get("split", 0)
+    assert km.labels_.dtype == ht.int64 and tuple(km.labels_.shape) == (x.shape[0], 1)
+    n_ref = int(gold["n_iter"])
+    res = orc.fit([x], init, max_iter=max(n_ref - 1, 0), tol=None) if n_ref > 1 else None
+    pre = res.cluster_centers if res is not None else init
+    assert_fit_matches(name, x, init, gold, km.cluster_centers_.larray, km.labels_.larray, km.n_iter_,
+                       float(km.inertia_.larray), pre_centers=pre.to(x.dtype))
+    pred = km.predict(hx)
+    par = orc.compare_labels(x, torch.from_numpy(gold["centers"]).to(x.dtype),
+                             torch.from_numpy(gold["predict_labels"].astype(np.int64)), pred.larray.cpu())
+    assert par.hard == 0, par
+    rtol = 1e-4 if x.dtype == torch.float32 else 1e-10
+    np.testing.assert_allclose(float(km.functional_value_.larray), float(gold["functional_value"]), rtol=rtol)
+
+
+def test_heat_cdist_runs_on_the_native_path(ht):
+    from helpers import load_golden
+    from heat_b200 import engine
+
+    g = load_golden("cdist")
+    eng = engine.get_engine(torch.device("cuda", 0))
+    for dt, atol in (("f32", 1e-5), ("f64", 1e-8)):
+        X, Y = torch.from_numpy(g[f"X_{dt}"]), torch.from_numpy(g[f"Y_{dt}"])
+        l0 = eng.launch_count()
+        d = ht.spatial.cdist(ht.array(X, split=0, device="gpu"), ht.array(Y, device="gpu"), quadratic_expansion=True)
+        assert eng.launch_count() > l0
+        assert d.split == 0 and d.larray.is_cuda
+        ref = torch.from_numpy(g[f"D_{dt}_quad"])
+        assert torch.allclose(d.larray.cpu(), ref, atol=atol, rtol=0)

@@ -340,3 +340,130 @@ def test_full_size_properties_config3():
     ref = orc.assign_to_cluster(xs, c.cpu()).view(-1)
     par = orc.compare_labels(xs, c.cpu(), ref, lab[idx.to(DEV)].cpu().long())
     assert par.hard == 0, par
+
+
+def test_lloyd_run_replays_graphs_and_equals_single_steps():
+    """hk_lloyd_run (first step eager, the rest replayed from cached CUDA graphs) gives bit-identical centroids to the same
+    number of hk_lloyd_step calls, counts every executed iteration, and respects the sticky convergence flag."""
+    from heat_b200.synthetic import blobs_shard, initial_centroids
+
+    n, d, k = 300_000, 32, 64
+    x, _ = blobs_shard(n, d, k, device=DEV, offset=1.0)
+    c0 = initial_centroids(k, d, 1.0).to(DEV)
+    eng = engine.get_engine(DEV)
+    res = []
+    for mode in ("steps", "run", "run_nograph"):
+        c, cp = c0.clone(), torch.empty_like(c0)
+        sh = torch.zeros((), device=DEV)
+        st = torch.zeros(4, dtype=torch.int32, device=DEV)
+        ws = eng.row_workspace(n)
+        g0 = eng.graph_launch_count()
+        if mode == "steps":
+            for _ in range(11):
+                eng.lloyd_step(x, c, cp, False, 0.0, sh, st, False, row_ws=ws)
+        else:
+            eng.graph(mode == "run")
+            eng.lloyd_run(x, c, cp, False, 0.0, sh, st, False, 11, row_ws=ws)
+            eng.graph(True)
+        torch.cuda.synchronize()
+        assert st.cpu().tolist()[:2] == [0, 11]
+        if mode == "run":
+            assert eng.graph_launch_count() - g0 == 3  # 10 replayed steps = 1 x 8 + 2 x 1
+        res.append((c.clone(), cp.clone(), float(sh)))
+    for other in res[1:]:
+        assert torch.equal(res[0][0], other[0]) and torch.equal(res[0][1], other[1]) and res[0][2] == other[2]
+    # with a tolerance: iterations enqueued after convergence are no-ops and n_iter stays exact
+    c, cp = c0.clone(), torch.empty_like(c0)
+    sh = torch.zeros((), device=DEV)
+    st = torch.zeros(4, dtype=torch.int32, device=DEV)
+    eng.lloyd_run(x, c, cp, True, 1e-4, sh, st, False, 60, row_ws=eng.row_workspace(n))
+    flag, it = st.cpu().tolist()[:2]
+    ref = orc.fit([x.cpu()], c0.cpu(), max_iter=60, tol=1e-4)
+    assert flag == 1 and it == ref.n_iter
+    assert orc.centers_rel_err(ref.cluster_centers, c.cpu()) <= 1e-5
+
+
+def test_row_workspace_is_owned_by_the_caller():
+    """The |x| bound cache lives in a caller-owned buffer tied to the matrix content: filled by the first pass (flag word
+    set), read afterwards; a zeroed buffer after the rows changed, or no buffer at all, give the same results bit for
+    bit.  The library itself keeps no per-matrix state (two matrices at the same address cannot confuse it)."""
+    eng = engine.get_engine(DEV)
+    n, d, k = 50_000, 32, 64
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(n, d, generator=g).to(DEV)
+    c = torch.randn(k, d, generator=g).to(DEV)
+    ws = eng.row_workspace(n)
+    assert ws.numel() == (n + 127) // 128 * 4 + 16 and int(ws.view(torch.int32)[-4]) == 0
+    outs = []
+    for row_ws in (ws, ws, None):
+        part = torch.empty(k * (d + 1), dtype=torch.float64, device=DEV)
+        lab = torch.empty(n, dtype=torch.int32, device=DEV)
+        eng.lloyd_accumulate(x, c, part, labels=lab, path="tc", row_ws=row_ws)
+        outs.append((part.clone(), lab.clone()))
+    assert int(ws.view(torch.int32)[(n + 127) // 128]) == 1  # filled
+    for o in outs[1:]:
+        assert torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1])
+    # the rows change in place (same address, same shape): the caller zeroes its workspace, results follow the new rows
+    x.mul_(100.0)
+    ws.zero_()
+    part = torch.empty(k * (d + 1), dtype=torch.float64, device=DEV)
+    lab = torch.empty(n, dtype=torch.int32, device=DEV)
+    eng.lloyd_accumulate(x, c, part, labels=lab, path="tc", row_ws=ws)
+    ref = orc.assign_to_cluster(x.cpu(), c.cpu()).view(-1)
+    assert orc.compare_labels(x.cpu(), c.cpu(), ref, lab.cpu().long()).hard == 0
+    with pytest.raises(_lib.HKError, match="row workspace"):
+        eng.lloyd_accumulate(x, c, part, path="tc", row_ws=ws[:64])
+
+
+def test_kmeanspp_init_on_device():
+    """init="kmeans++" (k-means||, _kcluster.py:146-245) with hk_cdist / hk_assign doing the N-sized work: on
+    well-separated blobs the fit finds every true centre; string inits keep the reference's error contract."""
+    from heat_b200.synthetic import blobs_shard, true_centres
+
+    n, d, k = 200_000, 32, 64
+    x, _ = blobs_shard(n, d, k, device=DEV, offset=4.0, seed=33)
+    km = hb.cluster.KMeans(n_clusters=k, init="kmeans++", max_iter=30, tol=1e-4, random_state=1)
+    km.fit(hb.array(x, split=0))
+    dist = torch.cdist(true_centres(k, d, 4.0, 33).double(), km.cluster_centers_.larray.cpu().double())
+    # k-means|| + Lloyd may leave a few centres merged/split on 64 clusters; most are found exactly
+    assert int((dist.min(dim=1).values < 0.2).sum()) >= k - 6
+    assert km.cluster_centers_.shape == (k, d) and km.n_iter_ >= 1
+    with pytest.raises(ValueError):
+        hb.cluster.KMeans(n_clusters=k, init="kmeans++").fit(hb.array(x, split=0), oversampling=1)
+
+
+@pytest.mark.parametrize("k,d", [(96, 32), (160, 32), (128, 32), (96, 64), (32, 32), (64, 64)])
+def test_tc_many_tiles_per_cta(k, d):
+    """The fused tensor-core kernel over tens of tiles per CTA for every TMEM plan (2, 4 and 8 accumulator buffers, 8-12
+    stages): the barrier hand-offs between the roles are only exercised when the pipeline wraps many times.  Labels
+    against the oracle, sums against an fp64 index_add over the kernel's own labels, twice (run-to-run bit equality)."""
+    n = 600_000
+    g = torch.Generator().manual_seed(k * 7 + d)
+    cen = 1.5 * torch.randn(k, d, generator=g)
+    x = cen[torch.randint(0, k, (n,), generator=g)] + torch.randn(n, d, generator=g)
+    c = cen + 0.3 * torch.randn(k, d, generator=g)
+    eng = engine.get_engine(DEV)
+    xd, cd = x.to(DEV), c.to(DEV)
+    outs = []
+    for rep in range(2):
+        part = torch.empty(k * (d + 1), dtype=torch.float64, device=DEV)
+        lab = torch.empty(n, dtype=torch.int32, device=DEV)
+        eng.lloyd_accumulate(xd, cd, part, labels=lab, path="tc", row_ws=eng.row_workspace(n) if rep else None)
+        outs.append((part.clone(), lab.clone()))
+    assert eng.last_variant().startswith("tc<"), eng.last_variant()
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])
+    got = outs[0][1].cpu().long()
+    hard = rr = 0
+    for r0 in range(0, n, 200_000):
+        xs = x[r0 : r0 + 200_000]
+        par = orc.compare_labels(xs, c, orc.assign_to_cluster(xs, c).view(-1), got[r0 : r0 + 200_000])
+        hard += par.hard
+        rr += par.ref_rounding
+    assert hard == 0 and rr <= n // 5000, (k, d, hard, rr)
+    p = outs[0][0].cpu().view(k, d + 1)
+    exp = torch.zeros(k, d + 1, dtype=torch.float64)
+    exp[:, :d].index_add_(0, got, x.double())
+    exp[:, d] = torch.bincount(got, minlength=k).double()
+    assert torch.equal(p[:, d], exp[:, d])
+    scale = x.double().abs().max() * exp[:, d].clamp(min=1).view(-1, 1)
+    assert float(((p[:, :d] - exp[:, :d]).abs() / scale).max()) < 2e-6

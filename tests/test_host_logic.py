@@ -54,6 +54,36 @@ def test_chunk_matches_reference_rule():
     assert lib.hk_chunk(10, 0, 0, None, None) != 0
 
 
+def test_row_workspace_size_and_null_handle_calls():
+    """hk_row_ws_bytes is host arithmetic (one float per 128-row tile + flag words); calls on a null handle fail with a
+    status and a message instead of crashing."""
+    lib = _lib.load()
+    assert lib.hk_row_ws_bytes(0) == 16
+    assert lib.hk_row_ws_bytes(128) == 20 and lib.hk_row_ws_bytes(129) == 24
+    assert lib.hk_row_ws_bytes(100_000_000) == (781250 + 4) * 4
+    assert lib.hk_row_ws_bytes(-5) == 0
+    out = (ctypes.c_int64 * 6)()
+    assert lib.hk_stats_read(None, out) != 0 and b"hk_stats_read" in lib.hk_last_error()
+    assert lib.hk_comm_mode(None) == 0 and lib.hk_graph_launch_count(None) == 0
+    assert lib.hk_comm_peer_export(None, 16, None) != 0
+    assert lib.hk_lloyd_run(None, None, 0, 1, 1, 0, None, None, 1, 0, 0.0, None, None, 0, None, 0, 0, 1, None) != 0
+
+
+def test_in_place_sentinel_and_allgather_bytes():
+    from heat_b200.communication import IN_PLACE, get_comm
+
+    comm = get_comm()
+    t = torch.arange(4.0)
+    comm.Allreduce(IN_PLACE, t)  # np == 1: no-op, the buffer is not copied onto itself
+    assert t.tolist() == [0.0, 1.0, 2.0, 3.0]
+    comm.Allreduce("IN_PLACE", t)  # the string spelling of older call sites still means in place
+    src = torch.ones(4)
+    comm.Allreduce(src, t)
+    assert t.tolist() == [1.0] * 4
+    assert comm.allgather_bytes(b"abc") == [b"abc"]
+    assert repr(IN_PLACE) == "IN_PLACE"
+
+
 def test_estimator_protocol_and_params():
     # reference: tests/cluster/test_kmeans.py:18-34
     km = hb.cluster.KMeans()
