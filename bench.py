@@ -561,7 +561,40 @@ def run_ours(args, wl):
                 if "sec_per_iter" in rg:
                     rg["iter_per_s_extrapolated"] = 1.0 / (rg["sec_per_iter"] * n / rg["rows"])
                 line["reference_gpu"] = rg
+    if world == 1 and args.workload == "config3" and args.data == "blobs" and not args.no_extras and not args.rows:
+        line["other_workloads"] = run_extras(args)
     print(json.dumps(line), flush=True)
+
+
+def run_extras(args):
+    """The other BASELINE.json configurations (5: fp64 small k, 2: cdist, 4: large k) and the headline configuration
+    on inputs that are NOT well-separated blobs, each measured by a short run of this same script in a child process
+    (N=1 only) and folded into the headline line, so that the driver's single default run sees them all."""
+    out = {}
+    jobs = [("config5", "blobs"), ("config2", "blobs"), ("config4", "blobs"), ("config3", "randn"), ("config3", "uncentred")]
+    for wl, data in jobs:
+        key = wl if data == "blobs" else f"{wl}:{data}"
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", wl, "--data", data, "--steps", "8", "--warmup", "3",
+               "--no-e2e", "--no-cpu", "--no-extras", "--ref-gpu-rows", "0", "--path", args.path]
+        try:
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+            js = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+            if not js:
+                out[key] = {"error": (res.stderr or res.stdout)[-200:]}
+                continue
+            j = json.loads(js[-1])
+            r = j["roofline"]
+            ent = {"metric": j["metric"], "value": j["value"], "unit": j["unit"], "ms_per_step": j["ms_per_step"],
+                   "kernel": r["kernel"], "kernel_ms_avg": r["kernel_ms_avg"], "bound": r["bound"], "roofline_frac": r["frac"],
+                   "steps": j["steps"], "workload": j["config"]["workload"]}
+            if j.get("parity"):
+                ent["parity_ok"] = j["parity"]["ok"]
+            if j.get("filter"):
+                ent["undecided_frac"] = j["filter"]["undecided_frac"]
+            out[key] = ent
+        except Exception as ex:  # reported, never hidden
+            out[key] = {"error": str(ex)[:200]}
+    return out
 
 
 def main():
@@ -577,6 +610,8 @@ def main():
     ap.add_argument("--no-row-ws", action="store_true", help="run without the per-matrix |x| bound workspace")
     ap.add_argument("--ref-gpu-rows", type=int, default=4_000_000,
                     help="rows for the second bar: the unmodified reference on this GPU through torch CUDA (0 = skip)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the short runs of the other configurations that the default N=1 run folds into its line")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--rows", type=int, default=None, help="override the global row count (experiments only)")

@@ -584,11 +584,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     const float cmax = *cmax_s;
     const bool force_exact = *force_exact_s != 0;
     // centre only when it helps (it always does unless the centroids straddle the origin already)
-#ifdef HK_NO_MU
-    const bool use_mu = false;
-#else
     const bool use_mu = !force_exact && (*cpmax_s < cmax);
-#endif
     const float cpmax = use_mu ? *cpmax_s : cmax;
     // operand B = -2 * (c - mu): K-blocked, 128B-swizzled, rows >= k zero
     for (int e = tid; e < nk * (d >> 2); e += blockDim.x) {
@@ -713,13 +709,8 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
         const int row = q * 32 + lane;
         const uint32_t tlane = __shfl_sync(0xffffffffu, tmem_base, 0) + ((uint32_t)(q * 32) << 16);
         const float beta2 = 2.f * 1.05f * 0.001953125f;
-#ifdef HK_OLD_E
-        const float gam = (float)(d + 3) * 1.1920929e-7f;
-        const float cmax2 = cmax * cmax;
-#else
         const float gam = (float)(2 * d + 6) * 1.1920929e-7f;
         const float cmax2 = cmax * cmax + cpmax * cpmax;
-#endif
         const uint32_t a_qalloc = sbase + p.o_misc + 272;  // ring control: allocated slots | consumed slots | warps done
         const uint32_t a_ring = sbase + p.o_ring;
         const uint32_t a_ecnt = sbase + p.o_cnt + (uint32_t)we * (uint32_t)(k * 4);
@@ -1189,10 +1180,7 @@ TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
     while (cols < (uint32_t)(pl.nbuf * pl.nk)) cols <<= 1;
     pl.tmem_cols = cols;
     const size_t budget = (size_t)h->smem_optin;
-#ifndef HK_TC_SMAX
-#define HK_TC_SMAX 12
-#endif
-    for (int S = HK_TC_SMAX & ~1; S >= 4; S -= 2) {  // even: the MMA / accumulator warps alternate over the stages
+    for (int S = 12; S >= 4; S -= 2) {  // even: the MMA / accumulator warps alternate over the stages
         TcLayout L = tc_layout(d, k, pl.nk, S, pl.NA, sums);
         if (L.total <= budget) {
             pl.S = S;

@@ -169,7 +169,8 @@ __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
 #ifdef HK_WATCHDOG
-    // debugging aid: a wait that lasts longer than ~2 s reports who is stuck on what and kills the kernel
+    // debugging aid (-DHK_WATCHDOG): a wait that lasts longer than ~2 s reports who is stuck on what and kills the kernel
+    // instead of hanging the GPU
     const long long t0 = clock64();
     for (;;) {
         uint32_t ok;
@@ -185,15 +186,6 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
             __trap();
         }
     }
-#elif defined(HK_MBAR_CLOOP)
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.b32 %0, 1, 0, p;\n}\n"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity), "r"(0x989680u)
-            : "memory");
-    } while (!ok);
 #elif defined(HK_MBAR_SPIN)
     asm volatile(
         "{\n"
