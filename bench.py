@@ -421,9 +421,13 @@ def run_ours(args, wl):
                     "exact_pairs_per_undecided_row": (st["exact_pairs"] / st["undecided_rows"]) if st["undecided_rows"] else 0.0,
                     "all_centroid_rows": st["all_centroid_rows"], "passes": st["passes"],
                     "what": "rows of the timed passes the TF32 filter could not decide (re-evaluated with the exact formula)"}
-    # second region: K eager iterations with per-kernel events
+    # second region: K eager iterations with per-kernel events.  A pause first: at ~1 kW this kernel runs into the board's
+    # power cap within ~0.1 s of sustained load (sw_power_cap, clocks drop ~10 %); both regions are K-step bursts from an
+    # idle GPU, which is also how MEASURED_PEAKS.json's copy bandwidth (best of 10 short copies) was taken.
     if row_ws is not None:
         row_ws.zero_()
+    barrier()
+    time.sleep(1.0)
     barrier()
     eng.profile(True)
     eng.profile_read()

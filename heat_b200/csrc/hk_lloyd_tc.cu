@@ -92,6 +92,7 @@ struct TcParams {
                                 // the all-centroid formula, warps that entered the cold path, rows seen, passes
     // shared-memory layout (byte offsets from the 1024-aligned base), computed on the host
     uint32_t o_stages, o_B, o_Aext, o_Bext, o_cn, o_acc, o_lab, o_cnt, o_snap, o_bars, o_misc, o_ring;
+    int ring_n, maxp;         // undecided-row ring entries (power of two) / pair-scratch entries
     unsigned long long* dbg;  // optional [grid][32 warps][8] cycle counters (HK_TC_DEBUG=1)
     unsigned long long* tl;   // optional timeline of CTA 0: [512 local tiles][8 events] clock64 stamps
 };
@@ -102,7 +103,7 @@ struct TcLayout {
 
 __host__ inline size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-__host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sums) {
+__host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sums, int ring_n = 128, int maxp = 96) {
     TcLayout L;
     size_t o = 0;
     L.stages = o;
@@ -127,8 +128,8 @@ __host__ inline TcLayout tc_layout(int d, int k, int nk, int S, int NA, bool sum
     o += 8 * 96;  // mbarriers
     L.misc = o;  // tmem slot, maxima, flags, fv partials, cold-path counters, ring control words, mu[d]
     o += 1024;
-    L.ring = o;  // undecided-row ring (128 x 16 B) + pair scratch of the refine warp (96 x 16 B)
-    o += (size_t)128 * 16 + (size_t)96 * 16;
+    L.ring = o;  // undecided-row ring (ring_n x 16 B) + pair scratch of the refine warp (maxp x 16 B)
+    o += (size_t)ring_n * 16 + (size_t)maxp * 16;
     L.total = o + 1024;  // slack for manual 1024-byte alignment of the base
     return L;
 }
@@ -212,7 +213,7 @@ enum { XN_COMPUTE = 0, XN_WRITE = 1, XN_READ = 2 };
 //
 // ring entry: word0 = tag (low 16 bits of slot index + 1) | stage << 16 | chunk_lo << 20 | chunk_hi << 23 | full << 26,
 //             word1 = global row, word2/3 = candidate masks of columns [32 chunk_lo, +32) / [32 chunk_hi, +32)
-constexpr int RING = 128;
+constexpr int RING_MAX = 128;  // ring entries (a power of two; 32 when shared memory is short, see plan_tc)
 constexpr int R_WARPS = 1;  // refine warps (warp 2).  Measured and dropped: a second refine warp (25 warps leave 72
                             // registers per thread: decided-only data -7 %), and the producer / MMA / epilogue warps
                             // lending a hand between two tiles (their pipelines stall: unstructured data +35 %)
@@ -242,6 +243,7 @@ struct RefineCtx {
     bool sums, want_fv;
     uint32_t a_ring, a_qalloc, a_stages, a_lab, b_lfull, a_ecnt0;
     const float* cn;
+    int ring_n, maxp;  // ring entries (power of two) and pair-scratch entries of this launch
 };
 struct RefineStats {
     unsigned n_und = 0, n_pairs = 0, n_full = 0, n_batches = 0;
@@ -260,7 +262,7 @@ struct RefineStats {
 // (Force-inlined on purpose: as a noinline function this code - never executed on decided-only data - made the whole
 // kernel 25 % slower; letting the epilogue warps help between two tiles cost the decided-only case 13 %.  Both A/B
 // measured, see profiles/README.md.)
-constexpr int MAXP = 96;
+constexpr int MAXP_MAX = 96;  // pair scratch entries (32 when shared memory is short)
 __device__ __forceinline__ int refine_batch(const RefineCtx& c, int lane, uint32_t a_scr, RefineStats& rs) {
     constexpr unsigned FULLM = 0xffffffffu;
     const int k = c.k, d = c.d;
@@ -280,7 +282,7 @@ __device__ __forceinline__ int refine_batch(const RefineCtx& c, int lane, uint32
     uint32_t head = lane == 0 ? lds_u32_volatile(a_qhead) : 0u;
     head = __shfl_sync(FULLM, head, 0);
     const uint32_t idx = head + (uint32_t)lane;
-    const uint32_t ea = c.a_ring + (idx & (RING - 1)) * 16;
+    const uint32_t ea = c.a_ring + (idx & (uint32_t)(c.ring_n - 1)) * 16;
     // one 16-byte load per entry (the pusher publishes tag and payload with one 16-byte store)
     uint32_t w0, grow;
     unsigned mlo, mhi;
@@ -307,7 +309,7 @@ __device__ __forceinline__ int refine_batch(const RefineCtx& c, int lane, uint32
     }
     // rows whose candidates fit the scratch (a prefix: incl is non-decreasing); a first row that does not fit alone
     // goes through the all-centroid loop
-    int n = __popc(__ballot_sync(FULLM, lane < n_ready && incl <= MAXP));
+    int n = __popc(__ballot_sync(FULLM, lane < n_ready && incl <= c.maxp));
     if (n == 0) {
         n = 1;
         if (lane == 0) {
@@ -524,7 +526,7 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     }
     if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
     for (int f = tid; f < d; f += blockDim.x) mu_s[f] = 0.f;
-    for (int e = tid; e < RING * 4; e += blockDim.x) reinterpret_cast<uint32_t*>(smem + p.o_ring)[e] = 0u;  // no tag matches
+    for (int e = tid; e < p.ring_n * 4; e += blockDim.x) reinterpret_cast<uint32_t*>(smem + p.o_ring)[e] = 0u;  // no tag matches
     if (tid < 4) reinterpret_cast<uint32_t*>(smem + p.o_misc + 272)[tid] = 0u;  // q_alloc, q_head, q_done, q_lock
     // seed operand A_ext[r] = (1,1,1,0,...)
     for (int e = tid; e < 8 * 8; e += blockDim.x) {
@@ -854,11 +856,11 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
                 slot0 = __shfl_sync(0xffffffffu, slot0, 0);
                 if (cold) {
                     const uint32_t idx = slot0 + (uint32_t)__popc(pm & lanemask_lt());
-                    while ((int32_t)(idx - lds_u32_volatile(a_qalloc + 4)) >= RING) __nanosleep(32);  // ring full
+                    while ((int32_t)(idx - lds_u32_volatile(a_qalloc + 4)) >= p.ring_n) __nanosleep(32);  // ring full
                     // one 16-byte store publishes the entry (tag and payload land together)
                     const uint32_t w0 = ((idx + 1u) & 0xffffu) | ((uint32_t)s << 16) | ((uint32_t)(clo >> 5) << 20) |
                                         ((uint32_t)(chi >> 5) << 23) | (full ? (1u << 26) : 0u);
-                    asm volatile("st.volatile.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_ring + (idx & (RING - 1)) * 16),
+                    asm volatile("st.volatile.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_ring + (idx & (uint32_t)(p.ring_n - 1)) * 16),
                                  "r"(w0), "r"((uint32_t)grow), "r"(full ? 0u : mlo), "r"(full ? 0u : mhi)
                                  : "memory");
                     lab = k;  // no label yet: the refine warp stores the final one (and counts the row)
@@ -928,8 +930,8 @@ __global__ void __launch_bounds__((MISC_WARPS + E_WARPS + (SUMS ? A_WARPS_MAX : 
     } else if (warp == 2) {
         // ================= refine warp 0 =================
         const RefineCtx rc{k, d, p.C, p.labels, p.label_kind, SUMS, p.fv_part != nullptr, sbase + p.o_ring,
-                           sbase + p.o_misc + 272, a_stages, a_lab, b_lfull, sbase + p.o_cnt, cn};
-        refine_role(rc, lane, sbase + p.o_ring + RING * 16, stat_s, fvred + E_WARPS);
+                           sbase + p.o_misc + 272, a_stages, a_lab, b_lfull, sbase + p.o_cnt, cn, p.ring_n, p.maxp};
+        refine_role(rc, lane, sbase + p.o_ring + (uint32_t)p.ring_n * 16, stat_s, fvred + E_WARPS);
     } else if (SUMS && warp >= A_FIRST && warp < A_FIRST + p.NA) {
         // ================= accumulator warps =================
         const int a = warp - A_FIRST;
@@ -1155,7 +1157,7 @@ __global__ void reduce_scalar_tc_kernel(const double* __restrict__ v, int n, dou
 }
 
 struct TcPlan {
-    int S, nk, NA, nbuf, fql2;
+    int S, nk, NA, nbuf, fql2, ring_n, maxp;
     uint32_t tmem_cols;
     size_t smem;
     bool ok;
@@ -1180,13 +1182,18 @@ TcPlan plan_tc(const Handle* h, int d, int k, bool sums) {
     while (cols < (uint32_t)(pl.nbuf * pl.nk)) cols <<= 1;
     pl.tmem_cols = cols;
     const size_t budget = (size_t)h->smem_optin;
-    for (int S = 12; S >= 4; S -= 2) {  // even: the MMA / accumulator warps alternate over the stages
-        TcLayout L = tc_layout(d, k, pl.nk, S, pl.NA, sums);
-        if (L.total <= budget) {
-            pl.S = S;
-            pl.smem = L.total;
-            pl.ok = true;
-            return pl;
+    // full-size refine ring first; shapes that are short of shared memory get a 32-entry ring rather than fewer than 4 stages
+    for (int small = 0; small < 2; ++small) {
+        pl.ring_n = small ? 32 : RING_MAX;
+        pl.maxp = small ? 32 : MAXP_MAX;
+        for (int S = 12; S >= 4; S -= 2) {  // even: the MMA / accumulator warps alternate over the stages
+            TcLayout L = tc_layout(d, k, pl.nk, S, pl.NA, sums, pl.ring_n, pl.maxp);
+            if (L.total <= budget) {
+                pl.S = S;
+                pl.smem = L.total;
+                pl.ok = true;
+                return pl;
+            }
         }
     }
     return pl;
@@ -1242,7 +1249,9 @@ int launch_lloyd_tc(Handle* h, const LloydArgs& a) {
     p.state = a.state;
     p.tmem_cols = pl.tmem_cols;
     {
-        const TcLayout L = tc_layout(a.d, a.k, pl.nk, pl.S, pl.NA, sums);
+        const TcLayout L = tc_layout(a.d, a.k, pl.nk, pl.S, pl.NA, sums, pl.ring_n, pl.maxp);
+        p.ring_n = pl.ring_n;
+        p.maxp = pl.maxp;
         p.o_stages = (uint32_t)L.stages;
         p.o_B = (uint32_t)L.B;
         p.o_Aext = (uint32_t)L.Aext;

@@ -432,7 +432,7 @@ def test_kmeanspp_init_on_device():
         hb.cluster.KMeans(n_clusters=k, init="kmeans++").fit(hb.array(x, split=0), oversampling=1)
 
 
-@pytest.mark.parametrize("k,d", [(96, 32), (160, 32), (128, 32), (96, 64), (32, 32), (64, 64)])
+@pytest.mark.parametrize("k,d", [(96, 32), (160, 32), (128, 32), (32, 64), (32, 32), (48, 64)])
 def test_tc_many_tiles_per_cta(k, d):
     """The fused tensor-core kernel over tens of tiles per CTA for every TMEM plan (2, 4 and 8 accumulator buffers, 8-12
     stages): the barrier hand-offs between the roles are only exercised when the pipeline wraps many times.  Labels
