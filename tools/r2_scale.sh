@@ -3,7 +3,7 @@
 N=${1:-8}
 mkdir -p gpurun_out
 if [ "$N" = "1" ]; then
-  timeout 600 python bench.py --gpus 1 --steps 20 --warmup 3 --no-e2e --no-cpu > gpurun_out/r2_scale_n$N.log 2>&1
+  timeout 600 python bench.py --gpus 1 --steps 20 --warmup 3 --no-e2e --no-cpu --no-extras > gpurun_out/r2_scale_n$N.log 2>&1
 else
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 --no-e2e > gpurun_out/r2_scale_n$N.log 2>&1
 fi
