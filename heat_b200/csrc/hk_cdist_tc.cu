@@ -8,8 +8,9 @@
 //   warp 0      : TMA producer — A tiles (raw X and xl, 128 rows x f) once per row tile, B slots (raw Y / yl,
 //                 128 rows x 32 features = 16 KB) through a ring
 //   warp 1      : tcgen05.mma issuer (M=128, N=128, K=8), 4 accumulator buffers of 128 columns in TMEM
-//   warps 4-11  : epilogue (thread == output row == TMEM lane): tcgen05.ld 32 columns -> distances -> swizzled
-//                 staging tile in shared memory -> TMA store (cp.async.bulk.tensor, clipped at the matrix edge)
+//   warps 4-11  : epilogue (thread == output row == TMEM lane): tcgen05.ld 32 columns (the next slice's load in
+//                 flight) -> distances -> this warp's swizzled 32 x 32 staging tile (double-buffered) -> this warp's
+//                 own TMA store (cp.async.bulk.tensor, clipped at the matrix edge); no block-level barrier
 // Replaces cdist -> _dist -> _euclidian_fast on the local blocks (heat/spatial/distance.py:32-64, 409-414).
 #include <math.h>
 
@@ -33,6 +34,7 @@ struct CdParams {
     const float* yn;
     int sqrt_flag;
     int nslot;  // B ring slots in use (2..NSLOT)
+    int nstg;   // output staging buffers per epilogue warp (1 or 2)
     // ARGMIN variant (large-k Lloyd pass): no distance matrix is written; per row the first-index argmin over all n
     // columns goes to labels[], rows whose runner-up is within window * (|x|^2 + *cmax2) are appended to queue[]
     int32_t* labels;
@@ -81,8 +83,21 @@ __global__ void split_lo_kernel(const float* __restrict__ A, int64_t rows, int f
 // the epilogue is issue-bound, and the result stays within the parity tolerance of the exact path
 __device__ __forceinline__ float sqrt_fast(float v) {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
+}
+
+// tcgen05.wait::ld with the loaded registers as operands: their consumers cannot be scheduled above the wait, so the
+// next slice's tcgen05.ld may stay in flight while this one is processed
+__device__ __forceinline__ void tmem_wait_ld32(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]),
+                   "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),
+                   "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
 }
 
 template <bool ARGMIN>
@@ -98,7 +113,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const int nkb = p.nkb;
     const uint32_t a_A = sbase + p.o_A;        // [2 parts][nkb][128 rows x 128 B]
     const uint32_t a_B = sbase + p.o_B;        // [NSLOT][128 rows x 128 B]
-    const uint32_t a_stage = sbase + p.o_stage;  // [2][128 rows x 128 B] output staging, 128B swizzle
+    const uint32_t a_stage = sbase + p.o_stage;  // [8 warps][nstg][32 rows x 128 B] output staging, 128B swizzle
     // barriers: a_full | a_empty | b_full[NSLOT] | b_empty[NSLOT] | t_full[NBUF] | t_empty[NBUF]
     const uint32_t b_afull = sbase + p.o_bars;
     const uint32_t b_aempty = b_afull + 8;
@@ -274,9 +289,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         const int grp = we >> 2;  // two groups of four warps alternate over the column chunks
         const int row = q * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-        const uint32_t stage = a_stage + (uint32_t)grp * kb_bytes;
-        const uint32_t srow = stage + (uint32_t)row * 128;
-        const int bar_id = 1 + grp;
+        const uint32_t wstage = a_stage + (uint32_t)(we * p.nstg) * 4096u;  // this warp's nstg staging buffers of 4 KB
+        int sb = 0;
         int lc = 0;  // chunk counter of this CTA (all row tiles)
         for (int rt = blockIdx.x; rt < p.num_row_tiles; rt += gridDim.x) {
             const int64_t grow = (int64_t)rt * TM + row;
@@ -292,6 +306,70 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 const uint32_t tph = (uint32_t)((lc / NBUF) & 1);
                 warp_wait(b_tfull + buf * 8, tph, lane);
                 tc_fence_after();
+                if constexpr (!ARGMIN) {
+                    // Per warp: 32 rows x 32 columns (4 KB) per slice through this warp's own staging buffers and its
+                    // own TMA stores; the next slice's tcgen05.ld is in flight while this one is converted.
+                    uint32_t a[2][32];
+                    tmem_ld32(tlane + (uint32_t)(buf * TN), a[0]);
+#pragma unroll
+                    for (int sl = 0; sl < TN / 32; ++sl) {
+                        uint32_t(&v)[32] = a[sl & 1];
+                        tmem_wait_ld32(v);
+                        if (sl + 1 < TN / 32) {
+                            tmem_ld32(tlane + (uint32_t)(buf * TN + (sl + 1) * 32), a[(sl + 1) & 1]);
+                        } else {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_a(b_tempty + buf * 8);  // accumulator drained by this warp
+                        }
+                        const int col0 = c * TN + sl * 32;
+                        // the TMA store that last read this staging buffer must have finished reading it
+                        if (lane == 0) {
+                            if (p.nstg == 2)
+                                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            else
+                                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        }
+                        __syncwarp();
+                        const uint32_t sbuf = wstage + (uint32_t)sb * 4096u;
+                        const uint32_t srow = sbuf + (uint32_t)lane * 128u;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (col0 + j < p.n) yv = __ldg(reinterpret_cast<const float4*>(p.yn + col0 + j));
+                            float4 o;
+                            o.x = fmaf(-2.f, __uint_as_float(v[j + 0]), xn + yv.x);
+                            o.y = fmaf(-2.f, __uint_as_float(v[j + 1]), xn + yv.y);
+                            o.z = fmaf(-2.f, __uint_as_float(v[j + 2]), xn + yv.z);
+                            o.w = fmaf(-2.f, __uint_as_float(v[j + 3]), xn + yv.w);
+                            o.x = o.x < 0.f ? 0.f : o.x;
+                            o.y = o.y < 0.f ? 0.f : o.y;
+                            o.z = o.z < 0.f ? 0.f : o.z;
+                            o.w = o.w < 0.f ? 0.f : o.w;
+                            if (p.sqrt_flag) {
+                                o.x = sqrt_fast(o.x);
+                                o.y = sqrt_fast(o.y);
+                                o.z = sqrt_fast(o.z);
+                                o.w = sqrt_fast(o.w);
+                            }
+                            // staging tile: 32 rows x 128 B, 16-byte chunk index XOR (row & 7) (matches the store map)
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(
+                                             srow + (uint32_t)((((j >> 2) ^ (lane & 7))) << 4)),
+                                         "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                                         : "memory");
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                             &out_map),
+                                         "r"(sbuf), "r"(col0), "r"(rt * TM + q * 32)
+                                         : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        sb = (sb + 1 == p.nstg) ? 0 : sb + 1;
+                    }
+                } else {
 #pragma unroll 1
                 for (int sl = 0; sl < TN / 32; ++sl) {
                     uint32_t a[32];
@@ -303,68 +381,31 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                         if (lane == 0) mbar_arrive_a(b_tempty + buf * 8);  // accumulator drained by this warp
                     }
                     const int col0 = c * TN + sl * 32;
-                    if (ARGMIN) {
-                        // d^2 of 32 columns in place, then chunk minimum + mask of the columns within thr of it
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 yv = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);  // columns >= n never win
-                            if (col0 + j < p.n) yv = __ldg(reinterpret_cast<const float4*>(p.yn + col0 + j));
-                            float o0 = fmaf(-2.f, __uint_as_float(a[j + 0]), xn + yv.x);
-                            float o1 = fmaf(-2.f, __uint_as_float(a[j + 1]), xn + yv.y);
-                            float o2 = fmaf(-2.f, __uint_as_float(a[j + 2]), xn + yv.z);
-                            float o3 = fmaf(-2.f, __uint_as_float(a[j + 3]), xn + yv.w);
-                            a[j + 0] = __float_as_uint(o0 < 0.f ? 0.f : o0);
-                            a[j + 1] = __float_as_uint(o1 < 0.f ? 0.f : o1);
-                            a[j + 2] = __float_as_uint(o2 < 0.f ? 0.f : o2);
-                            a[j + 3] = __float_as_uint(o3 < 0.f ? 0.f : o3);
-                        }
-                        const float mc = min32(a);
-                        const unsigned mk = below_mask32(a, mc + thr);
-                        if (mc < m_best) {
-                            m_second = m_best;
-                            m_best = mc;
-                            mk_best = mk;
-                            c_best = col0;
-                        } else {
-                            m_second = fminf(m_second, mc);
-                        }
-                        continue;
-                    }
-                    // the previous TMA store of this staging buffer must have finished reading it
-                    if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    named_bar_sync(bar_id, 128);
+                    // d^2 of 32 columns in place, then chunk minimum + mask of the columns within thr of it
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 yv = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);  // columns >= n never win
                         if (col0 + j < p.n) yv = __ldg(reinterpret_cast<const float4*>(p.yn + col0 + j));
-                        float4 o;
-                        o.x = fmaf(-2.f, __uint_as_float(a[j + 0]), xn + yv.x);
-                        o.y = fmaf(-2.f, __uint_as_float(a[j + 1]), xn + yv.y);
-                        o.z = fmaf(-2.f, __uint_as_float(a[j + 2]), xn + yv.z);
-                        o.w = fmaf(-2.f, __uint_as_float(a[j + 3]), xn + yv.w);
-                        o.x = o.x < 0.f ? 0.f : o.x;
-                        o.y = o.y < 0.f ? 0.f : o.y;
-                        o.z = o.z < 0.f ? 0.f : o.z;
-                        o.w = o.w < 0.f ? 0.f : o.w;
-                        if (p.sqrt_flag) {
-                            o.x = sqrt_fast(o.x);
-                            o.y = sqrt_fast(o.y);
-                            o.z = sqrt_fast(o.z);
-                            o.w = sqrt_fast(o.w);
-                        }
-                        // staging tile: 128 rows x 128 B, 16-byte chunk index XOR (row & 7) (matches the store map)
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)((((j >> 2) ^ (row & 7))) << 4)),
-                                     "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
-                                     : "memory");
+                        float o0 = fmaf(-2.f, __uint_as_float(a[j + 0]), xn + yv.x);
+                        float o1 = fmaf(-2.f, __uint_as_float(a[j + 1]), xn + yv.y);
+                        float o2 = fmaf(-2.f, __uint_as_float(a[j + 2]), xn + yv.z);
+                        float o3 = fmaf(-2.f, __uint_as_float(a[j + 3]), xn + yv.w);
+                        a[j + 0] = __float_as_uint(o0 < 0.f ? 0.f : o0);
+                        a[j + 1] = __float_as_uint(o1 < 0.f ? 0.f : o1);
+                        a[j + 2] = __float_as_uint(o2 < 0.f ? 0.f : o2);
+                        a[j + 3] = __float_as_uint(o3 < 0.f ? 0.f : o3);
                     }
-                    fence_proxy_async();
-                    named_bar_sync(bar_id, 128);
-                    if (q == 0 && lane == 0) {
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&out_map),
-                                     "r"(stage), "r"(col0), "r"(rt * TM)
-                                     : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    const float mc = min32(a);
+                    const unsigned mk = below_mask32(a, mc + thr);
+                    if (mc < m_best) {
+                        m_second = m_best;
+                        m_best = mc;
+                        mk_best = mk;
+                        c_best = col0;
+                    } else {
+                        m_second = fminf(m_second, mc);
                     }
+                }
                 }
             }
             if (ARGMIN) {
@@ -398,7 +439,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 }
             }
         }
-        if (!ARGMIN && q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (!ARGMIN && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     tc_fence_before();
@@ -412,7 +453,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 struct CdLayout {
     size_t A, B, stage, bars, total;
 };
-CdLayout cd_layout(int nkb, int nslot) {
+CdLayout cd_layout(int nkb, int nslot, int nstg) {
     CdLayout L;
     size_t o = 0;
     L.A = o;
@@ -420,7 +461,7 @@ CdLayout cd_layout(int nkb, int nslot) {
     L.B = o;
     o += (size_t)nslot * TM * 128;
     L.stage = o;
-    o += (size_t)2 * TM * 128;
+    o += (size_t)nstg * EPI_WARPS * 4096;  // per epilogue warp: nstg buffers of 32 rows x 128 B
     L.bars = o;
     o += 512;
     L.total = o + 1024;
@@ -428,11 +469,13 @@ CdLayout cd_layout(int nkb, int nslot) {
 }
 
 // largest B ring (2..NSLOT slots) that fits next to the A tiles
-int cd_nslot(const Handle* h, int nkb) {
+int cd_nslot(const Handle* h, int nkb, int nstg) {
     for (int ns = NSLOT; ns >= 2; --ns)
-        if (cd_layout(nkb, ns).total <= (size_t)h->smem_optin) return ns;
+        if (cd_layout(nkb, ns, nstg).total <= (size_t)h->smem_optin) return ns;
     return 0;
 }
+// double-buffered output staging when the B ring keeps at least 4 slots next to it
+int cd_nstg(const Handle* h, int nkb) { return cd_nslot(h, nkb, 2) >= 4 ? 2 : 1; }
 
 }  // namespace
 
@@ -445,7 +488,7 @@ bool cdist_tc_supported(const Handle* h, const void* X, int64_t m, int f, int64_
         return false;
     if (m >= ((int64_t)1 << 31) - TM || n >= ((int64_t)1 << 31) - TN) return false;
     if (m < 1024 || n < 128) return false;  // small problems: the exact-FMA kernel is as good and bit-closer
-    return cd_nslot(h, f / 32) >= 2;
+    return cd_nslot(h, f / 32, 1) >= 2;
 }
 
 namespace {
@@ -489,15 +532,17 @@ int launch_cdist_tc_impl(Handle* h, const void* X, int64_t m, int f, int64_t ldx
     rc = make_tensor_map_2d(&yl_map, yl, 4, (uint64_t)n, (uint64_t)f, (uint64_t)f, 32, TN, 128);
     if (rc) return rc;
     if (am == nullptr)
-        rc = make_tensor_map_2d(&out_map, out, 4, (uint64_t)m, (uint64_t)n, (uint64_t)ldo, 32, TM, 128);
+        rc = make_tensor_map_2d(&out_map, out, 4, (uint64_t)m, (uint64_t)n, (uint64_t)ldo, 32, 32, 128);
     else
         out_map = xl_map;  // unused by the ARGMIN kernel
     if (rc) return rc;
 
-    const int nslot = cd_nslot(h, nkb);
-    const CdLayout L = cd_layout(nkb, nslot);
+    const int nstg = am != nullptr ? 1 : cd_nstg(h, nkb);  // the ARGMIN variant stores nothing (2 KB exchange area)
+    const int nslot = cd_nslot(h, nkb, nstg);
+    const CdLayout L = cd_layout(nkb, nslot, nstg);
     CdParams p{};
     p.nslot = nslot;
+    p.nstg = nstg;
     p.m = m;
     p.n = n;
     p.f = f;
