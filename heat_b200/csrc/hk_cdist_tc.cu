@@ -87,6 +87,27 @@ __device__ __forceinline__ float sqrt_fast(float v) {
     return r;
 }
 
+// packed fp32 pairs (add/fma.rn.f32x2: one issue slot for two results, each rounded like the scalar instruction)
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+// (|x|^2 + |y|^2) - 2 * dot for two adjacent columns
+__device__ __forceinline__ void dist2_pair(float& o0, float& o1, uint32_t d0, uint32_t d1, uint64_t xn2, float y0, float y1) {
+    uint64_t dv, s, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(dv) : "r"(d0), "r"(d1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(s) : "l"(xn2), "l"(pack2(y0, y1)));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(dv), "l"(pack2(-2.f, -2.f)), "l"(s));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(r));
+}
+// max(v, 0) that keeps NaN (v < 0 ? 0 : v) in one instruction
+__device__ __forceinline__ float clamp0_nan(float v) {
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 // tcgen05.wait::ld with the loaded registers as operands: their consumers cannot be scheduled above the wait, so the
 // next slice's tcgen05.ld may stay in flight while this one is processed
 __device__ __forceinline__ void tmem_wait_ld32(uint32_t (&v)[32]) {
@@ -307,6 +328,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 warp_wait(b_tfull + buf * 8, tph, lane);
                 tc_fence_after();
                 if constexpr (!ARGMIN) {
+                    const uint64_t xn2 = pack2(xn, xn);
                     // Per warp: 32 rows x 32 columns (4 KB) per slice through this warp's own staging buffers and its
                     // own TMA stores; the next slice's tcgen05.ld is in flight while this one is converted.
                     uint32_t a[2][32];
@@ -338,14 +360,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                             float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (col0 + j < p.n) yv = __ldg(reinterpret_cast<const float4*>(p.yn + col0 + j));
                             float4 o;
-                            o.x = fmaf(-2.f, __uint_as_float(v[j + 0]), xn + yv.x);
-                            o.y = fmaf(-2.f, __uint_as_float(v[j + 1]), xn + yv.y);
-                            o.z = fmaf(-2.f, __uint_as_float(v[j + 2]), xn + yv.z);
-                            o.w = fmaf(-2.f, __uint_as_float(v[j + 3]), xn + yv.w);
-                            o.x = o.x < 0.f ? 0.f : o.x;
-                            o.y = o.y < 0.f ? 0.f : o.y;
-                            o.z = o.z < 0.f ? 0.f : o.z;
-                            o.w = o.w < 0.f ? 0.f : o.w;
+                            dist2_pair(o.x, o.y, v[j + 0], v[j + 1], xn2, yv.x, yv.y);
+                            dist2_pair(o.z, o.w, v[j + 2], v[j + 3], xn2, yv.z, yv.w);
+                            o.x = clamp0_nan(o.x);
+                            o.y = clamp0_nan(o.y);
+                            o.z = clamp0_nan(o.z);
+                            o.w = clamp0_nan(o.w);
                             if (p.sqrt_flag) {
                                 o.x = sqrt_fast(o.x);
                                 o.y = sqrt_fast(o.y);
