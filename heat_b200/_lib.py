@@ -11,6 +11,7 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_void_
 
 HK_F32, HK_F64 = 0, 1
 HK_LABEL_NONE, HK_LABEL_U8, HK_LABEL_I32, HK_LABEL_I64 = 0, 1, 2, 3
+HK_METRIC_EUCLIDEAN, HK_METRIC_GAUSSIAN, HK_METRIC_MANHATTAN = 0, 1, 2
 HK_PATH_AUTO, HK_PATH_SIMT, HK_PATH_TC, HK_PATH_GENERIC, HK_PATH_ROW128 = 0, 1, 2, 3, 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -53,6 +54,33 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int,
          c_int, c_int, c_void_p],
+    ),
+    "hk_pairwise": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int,
+         c_int, c_int, c_double, c_void_p],
+    ),
+    "hk_assign_l1": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p],
+    ),
+    "hk_row_keep": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    "hk_select_passes": (c_int, [c_int]),
+    "hk_select_hist": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+         c_void_p],
+    ),
+    "hk_select_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "hk_select_value": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hk_nearest_rows_l1": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p],
+    ),
+    "hk_topk_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "hk_knn_vote": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p],
     ),
     "hk_comm_unique_id": (c_int, [c_void_p]),
     "hk_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),

@@ -381,3 +381,159 @@ def _gather_rows(x: DNDarray, idx: torch.Tensor) -> DNDarray:
         if x.comm.is_distributed():
             x.comm.Allreduce(IN_PLACE, out)
     return DNDarray(out, (k, d), out.dtype, None, out.device, x.comm, True)
+
+
+class _L1Cluster(KMeans):
+    """Shared part of KMedians / KMedoids: Manhattan metric (p = 1), assignment by ``hk_assign_l1``, medians of every
+    cluster by distributed radix selection (``hk_select_*``), the reference's fit loops with their per-iteration
+    convergence test on the host (heat/cluster/kmedians.py:105-147, kmedoids.py:112-156)."""
+
+    _INIT_ALIAS = ""
+
+    def __init__(self, n_clusters: int = 8, init: Union[str, DNDarray] = "random", max_iter: int = 300,
+                 tol: Optional[float] = 1e-4, random_state: Optional[int] = None):
+        if isinstance(init, str) and init == self._INIT_ALIAS:
+            init = "probability_based"
+        super().__init__(n_clusters=n_clusters, init=init, max_iter=max_iter, tol=tol, random_state=random_state)
+        self._p = 1
+
+    def _operands(self, x: DNDarray):
+        xl, cdtype = _device_operands(x)
+        eng = _engine.get_engine(xl.device)
+        c = self._cluster_centers.larray.to(xl.device)
+        if c.dtype == torch.float64 and cdtype == torch.float32:  # promotion of distance.py:392-395
+            xl, cdtype = xl.to(torch.float64), torch.float64
+        return xl, cdtype, eng, c.to(cdtype).contiguous()
+
+    def _assign_to_cluster(self, x: DNDarray, eval_functional_value: bool = False) -> DNDarray:
+        """Reference: heat/cluster/_kcluster.py:352-370 with metric = manhattan(expand=True), p = 1."""
+        xl, cdtype, eng, c = self._operands(x)
+        dev = xl.device
+        labels = torch.empty((xl.shape[0], 1), dtype=torch.int64, device=dev)
+        fv = torch.zeros(1, dtype=torch.float64, device=dev) if eval_functional_value else None
+        eng.assign_l1(xl, c, labels, fv)
+        if eval_functional_value:
+            if x.split is not None and x.comm.is_distributed():
+                x.comm.Allreduce(IN_PLACE, fv)
+            self._functional_value = DNDarray(fv[0].to(cdtype), (), cdtype, None, dev, x.comm, True)
+        return DNDarray(labels, (x.shape[0], 1), torch.int64, x.split, dev, x.comm, x.balanced)
+
+    def _cluster_medians(self, x: DNDarray, labels: DNDarray):
+        """(medians [k, d] on the device, kept-row counts [k] on the host) over all ranks."""
+        xl, cdtype, eng, _ = self._operands(x)
+        distributed = x.split is not None and x.comm.is_distributed()
+        allsum = (lambda t: x.comm.Allreduce(IN_PLACE, t)) if distributed else None
+        med, counts = eng.cluster_medians(xl, labels.larray, self.n_clusters, allsum)
+        return med, counts.cpu()
+
+    def _random_row(self, x: DNDarray) -> torch.Tensor:
+        """Failsafe of the reference for a cluster without points: a uniformly drawn data row
+        (kmedians.py:82-95; torch's generator instead of Heat's, so the row differs for the same seed)."""
+        if not hasattr(self, "_failsafe_rng"):
+            self._failsafe_rng = torch.Generator().manual_seed(0 if self.random_state is None else int(self.random_state))
+        idx = torch.randint(0, x.shape[0], (1,), generator=self._failsafe_rng)
+        return _gather_rows(x, idx).larray[0]
+
+    def _check_fit_input(self, x):
+        if not isinstance(x, DNDarray):
+            raise ValueError(f"input needs to be a ht.DNDarray, but was {type(x)}")
+
+
+class KMedians(_L1Cluster):
+    """K-Medians clustering — drop-in for ``heat.cluster.KMedians`` (heat/cluster/kmedians.py:11-147): Manhattan
+    metric, centroids = per-feature medians of the assigned rows."""
+
+    _INIT_ALIAS = "kmedians++"
+
+    def _update_centroids(self, x: DNDarray, matching_centroids: DNDarray) -> torch.Tensor:
+        """Reference: heat/cluster/kmedians.py:60-103."""
+        med, counts = self._cluster_medians(x, matching_centroids)
+        new = self._cluster_centers.larray.clone()
+        new.copy_(med.to(new.dtype))
+        for j in (counts == 0).nonzero().view(-1).tolist():
+            new[j] = self._random_row(x).to(new.dtype)
+        return new
+
+    def fit(self, x: DNDarray, oversampling: float = 2, iter_multiplier: float = 1):
+        """Reference: heat/cluster/kmedians.py:105-147."""
+        self._check_fit_input(x)
+        self._initialize_cluster_centers(x, oversampling, iter_multiplier)
+        self._n_iter = 0
+        dev = _device_operands(x)[0].device
+        c = self._cluster_centers.larray.to(dev)
+        self._cluster_centers = DNDarray(c, tuple(c.shape), c.dtype, None, dev, x.comm, True)
+        matching = None
+        for _ in range(int(self.max_iter)):
+            self._n_iter += 1
+            matching = self._assign_to_cluster(x)
+            new = self._update_centroids(x, matching)
+            inertia = ((self._cluster_centers.larray - new) ** 2).sum()
+            self._inertia = DNDarray(inertia, (), inertia.dtype, None, dev, x.comm, True)
+            self._cluster_centers = DNDarray(new, tuple(new.shape), new.dtype, None, dev, x.comm, True)
+            if self.tol is not None and float(inertia) <= float(np.float32(self.tol)):
+                break
+        if matching is None:
+            raise ValueError("max_iter must be at least 1")
+        self._labels = matching
+        return self
+
+
+class KMedoids(_L1Cluster):
+    """K-Medoids clustering — drop-in for ``heat.cluster.KMedoids`` (heat/cluster/kmedoids.py:11-156): Manhattan
+    metric, every centroid is the data row closest to the median of its cluster."""
+
+    _INIT_ALIAS = "kmedoids++"
+
+    def __init__(self, n_clusters: int = 8, init: Union[str, DNDarray] = "random", max_iter: int = 300,
+                 random_state: Optional[int] = None):
+        super().__init__(n_clusters=n_clusters, init=init, max_iter=max_iter, tol=0.0, random_state=random_state)
+
+    def _update_centroids(self, x: DNDarray, matching_centroids: DNDarray) -> torch.Tensor:
+        """Reference: heat/cluster/kmedoids.py:57-110."""
+        med, counts = self._cluster_medians(x, matching_centroids)
+        xl, cdtype, eng, _ = self._operands(x)
+        comm = x.comm
+        distributed = x.split is not None and comm.is_distributed()
+        row_base = 0
+        if distributed:
+            row_base = sum(comm.row_counts(xl.shape[0])[: comm.rank])
+        bd, bi = eng.nearest_rows_l1(xl, med.to(cdtype).contiguous(), row_base)
+        if distributed:
+            # (distance, global index) of every rank; the smallest distance wins, the lowest index on ties
+            cand = comm.allgather_bytes(torch.stack([bd, bi.double()]).cpu().numpy().tobytes())
+            both = torch.stack([torch.frombuffer(bytearray(b), dtype=torch.float64).view(2, -1) for b in cand])  # [p,2,k]
+            dist, gidx = both[:, 0], both[:, 1]
+            order = torch.argsort(dist + 0.0, dim=0, stable=True)  # ranks hold ascending index ranges
+            best = order[0]
+            idx = gidx.gather(0, best.view(1, -1)).view(-1).long()
+        else:
+            idx = bi.cpu()
+        new = self._cluster_centers.larray.clone()
+        ok = counts > 0
+        if bool(ok.any()):
+            rows = _gather_rows(x, idx[ok]).larray.to(new.dtype)
+            new[ok.to(new.device)] = rows
+        for j in (~ok).nonzero().view(-1).tolist():
+            new[j] = self._random_row(x).to(new.dtype)
+        return new
+
+    def fit(self, x: DNDarray, oversampling: float = 2, iter_multiplier: float = 1):
+        """Reference: heat/cluster/kmedoids.py:112-156."""
+        self._check_fit_input(x)
+        self._initialize_cluster_centers(x, oversampling, iter_multiplier)
+        self._n_iter = 0
+        dev = _device_operands(x)[0].device
+        c = self._cluster_centers.larray.to(dev)
+        self._cluster_centers = DNDarray(c, tuple(c.shape), c.dtype, None, dev, x.comm, True)
+        matching = None
+        for _ in range(int(self.max_iter)):
+            self._n_iter += 1
+            matching = self._assign_to_cluster(x)
+            new = self._update_centroids(x, matching)
+            if torch.equal(self._cluster_centers.larray, new):
+                break
+            self._cluster_centers = DNDarray(new, tuple(new.shape), new.dtype, None, dev, x.comm, True)
+        if matching is None:
+            raise ValueError("max_iter must be at least 1")
+        self._labels = matching
+        return self

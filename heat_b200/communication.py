@@ -110,6 +110,43 @@ class ProcessGroupCommunication(Communication):
         self._dist.all_gather(parts, mine, group=self.group)
         return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
 
+    def row_counts(self, n_local: int) -> list:
+        """Rows held by every rank, in rank order (``counts_displs_shape``, communication.py:256-281, but from the
+        actual local shapes so unbalanced arrays work)."""
+        if self.size == 1:
+            return [int(n_local)]
+        out = [None] * self.size
+        self._dist.all_gather_object(out, int(n_local), group=self.group)
+        return [int(c) for c in out]
+
+    def ring_post(self, stationary: torch.Tensor, step: int, counts: list):
+        """Start step ``step`` of the ring of ``_dist`` (distance.py:262-282, 431-462): this rank's block goes to rank
+        ``(rank + step) % size`` while the block of rank ``(rank - step) % size`` arrives.  Returns ``(moving,
+        requests, sender)``; the transfer runs beside whatever is launched until ``ring_wait``."""
+        dist = self._dist
+        receiver = (self.rank + step) % self.size
+        sender = (self.rank - step) % self.size
+        moving = torch.empty((counts[sender],) + tuple(stationary.shape[1:]), dtype=stationary.dtype,
+                             device=stationary.device)
+        ops = []
+        # zero-row blocks are not sent: both sides know the counts
+        if stationary.shape[0] > 0:
+            ops.append(dist.P2POp(dist.isend, stationary, self._global_rank(receiver), group=self.group))
+        if moving.shape[0] > 0:
+            ops.append(dist.P2POp(dist.irecv, moving, self._global_rank(sender), group=self.group))
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        return moving, reqs, sender
+
+    @staticmethod
+    def ring_wait(reqs) -> None:
+        for r in reqs:
+            r.wait()
+
+    def _global_rank(self, group_rank: int) -> int:
+        if self.group is None:
+            return group_rank
+        return self._dist.get_global_rank(self.group, group_rank)
+
     def allgather_bytes(self, payload: bytes) -> list:
         """Every rank's ``payload`` in rank order (small host-side objects: IPC handles, row counts)."""
         if self.size == 1:

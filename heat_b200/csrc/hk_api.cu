@@ -381,6 +381,124 @@ int hk_cdist(hk_handle_t hh, const void* X, int64_t m, int f, int64_t ldx, const
                         reinterpret_cast<cudaStream_t>(stream));
 }
 
+int hk_pairwise(hk_handle_t hh, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n,
+                int64_t ldy, void* out, int64_t ldo, int dtype, int metric, int expand, double sigma,
+                void* stream) {
+    HK_ARG(hh != nullptr, "hk_pairwise: null handle");
+    HK_ARG(dtype == HK_F32 || dtype == HK_F64, "hk_pairwise: bad dtype");
+    HK_ARG(metric == HK_METRIC_EUCLIDEAN || metric == HK_METRIC_GAUSSIAN || metric == HK_METRIC_MANHATTAN,
+           "hk_pairwise: bad metric");
+    HK_ARG(m >= 0 && n >= 0 && f >= 1, "hk_pairwise: bad shape");
+    HK_ARG(ldx >= f && ldy >= f && ldo >= n, "hk_pairwise: bad leading dimension");
+    HK_ARG(metric != HK_METRIC_GAUSSIAN || (sigma == sigma && sigma != 0.0), "hk_pairwise: bad sigma");
+    if (m == 0 || n == 0) return 0;
+    HK_ARG(X && Y && out, "hk_pairwise: null pointer");
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    HK_CUDA(cudaSetDevice(h->device));
+    const int body = metric == HK_METRIC_MANHATTAN ? 2 : (expand ? 1 : 0);
+    const int post = metric == HK_METRIC_EUCLIDEAN ? 1 : (metric == HK_METRIC_GAUSSIAN ? 2 : 0);
+    return launch_cdist(h, X, m, f, ldx, Y, n, ldy, out, ldo, dtype, body, post,
+                        reinterpret_cast<cudaStream_t>(stream), 2.0 * sigma * sigma);
+}
+
+// ---- other consumers of the assignment pattern --------------------------------------------------
+#define HK_HANDLE(name)                                   \
+    HK_ARG(hh != nullptr, name ": null handle");          \
+    Handle* h = reinterpret_cast<Handle*>(hh);            \
+    HK_CUDA(cudaSetDevice(h->device));                    \
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream)
+
+int hk_assign_l1(hk_handle_t hh, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, const void* C, int k,
+                 void* labels, int label_kind, double* min_d_sum, void* stream) {
+    HK_ARG(dtype == HK_F32 || dtype == HK_F64, "hk_assign_l1: bad dtype");
+    HK_ARG(n_local >= 0 && d >= 1 && k >= 1 && ldx >= d, "hk_assign_l1: bad shape");
+    HK_ARG(label_kind >= HK_LABEL_NONE && label_kind <= HK_LABEL_I64, "hk_assign_l1: bad label kind");
+    HK_ARG(label_kind != HK_LABEL_U8 || k <= 256, "hk_assign_l1: uint8 labels need k <= 256");
+    HK_HANDLE("hk_assign_l1");
+    if (n_local == 0) {
+        if (min_d_sum != nullptr) HK_CUDA(cudaMemsetAsync(min_d_sum, 0, sizeof(double), st));
+        return 0;
+    }
+    HK_ARG(X && C, "hk_assign_l1: null pointer");
+    HK_ARG(label_kind == HK_LABEL_NONE || labels != nullptr, "hk_assign_l1: null labels");
+    return launch_assign_l1(h, X, n_local, d, ldx, dtype, C, k, labels, label_kind, min_d_sum, st);
+}
+
+int hk_row_keep(hk_handle_t hh, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, void* keep_u8,
+                void* stream) {
+    HK_ARG(dtype == HK_F32 || dtype == HK_F64, "hk_row_keep: bad dtype");
+    HK_ARG(n_local >= 0 && d >= 1 && ldx >= d, "hk_row_keep: bad shape");
+    HK_HANDLE("hk_row_keep");
+    if (n_local == 0) return 0;
+    HK_ARG(X && keep_u8, "hk_row_keep: null pointer");
+    return launch_row_keep(h, X, n_local, d, ldx, dtype, reinterpret_cast<uint8_t*>(keep_u8), st);
+}
+
+int hk_select_passes(int dtype) { return dtype == HK_F64 ? 8 : 4; }
+
+int hk_select_hist(hk_handle_t hh, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, const void* labels_i64,
+                   const void* keep_u8, int k, const void* prefix_u64, int pass, void* hist_i64, void* stream) {
+    HK_ARG(dtype == HK_F32 || dtype == HK_F64, "hk_select_hist: bad dtype");
+    HK_ARG(n_local >= 0 && d >= 1 && k >= 1 && ldx >= d, "hk_select_hist: bad shape");
+    HK_ARG(pass >= 0 && pass < hk_select_passes(dtype), "hk_select_hist: bad pass");
+    HK_HANDLE("hk_select_hist");
+    if (n_local == 0) return 0;
+    HK_ARG(X && labels_i64 && keep_u8 && prefix_u64 && hist_i64, "hk_select_hist: null pointer");
+    return launch_select_hist(h, X, n_local, d, ldx, dtype, reinterpret_cast<const int64_t*>(labels_i64),
+                              reinterpret_cast<const uint8_t*>(keep_u8), k, reinterpret_cast<const uint64_t*>(prefix_u64),
+                              pass, reinterpret_cast<unsigned long long*>(hist_i64), st);
+}
+
+int hk_select_step(hk_handle_t hh, const void* hist_i64, void* remaining_i64, void* prefix_u64, int k, int d,
+                   void* stream) {
+    HK_ARG(k >= 1 && d >= 1, "hk_select_step: bad shape");
+    HK_HANDLE("hk_select_step");
+    HK_ARG(hist_i64 && remaining_i64 && prefix_u64, "hk_select_step: null pointer");
+    return launch_select_step(h, reinterpret_cast<const unsigned long long*>(hist_i64),
+                              reinterpret_cast<int64_t*>(remaining_i64), reinterpret_cast<uint64_t*>(prefix_u64), 2 * k * d,
+                              st);
+}
+
+int hk_select_value(hk_handle_t hh, const void* prefix_u64, const double* frac, int k, int d, int dtype, void* medians,
+                    void* stream) {
+    HK_ARG(dtype == HK_F32 || dtype == HK_F64, "hk_select_value: bad dtype");
+    HK_ARG(k >= 1 && d >= 1, "hk_select_value: bad shape");
+    HK_HANDLE("hk_select_value");
+    HK_ARG(prefix_u64 && frac && medians, "hk_select_value: null pointer");
+    return launch_select_value(h, reinterpret_cast<const uint64_t*>(prefix_u64), frac, k, d, dtype, medians, st);
+}
+
+int hk_nearest_rows_l1(hk_handle_t hh, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, const void* P,
+                       int k, int64_t row_base, double* best_dist, void* best_index_i64, void* stream) {
+    HK_ARG(dtype == HK_F32 || dtype == HK_F64, "hk_nearest_rows_l1: bad dtype");
+    HK_ARG(n_local >= 1 && d >= 1 && k >= 1 && ldx >= d, "hk_nearest_rows_l1: bad shape");
+    HK_HANDLE("hk_nearest_rows_l1");
+    HK_ARG(X && P && best_dist && best_index_i64, "hk_nearest_rows_l1: null pointer");
+    return launch_nearest_rows_l1(h, X, n_local, d, ldx, dtype, P, k, row_base, best_dist,
+                                  reinterpret_cast<int64_t*>(best_index_i64), st);
+}
+
+int hk_topk_rows(hk_handle_t hh, const void* D, int64_t m, int64_t n, int64_t ldd, int dtype, int kk, void* values,
+                 void* indices_i64, void* stream) {
+    HK_ARG(dtype == HK_F32 || dtype == HK_F64, "hk_topk_rows: bad dtype");
+    HK_ARG(m >= 0 && n >= 1 && ldd >= n && kk >= 1 && kk <= n, "hk_topk_rows: bad shape");
+    HK_HANDLE("hk_topk_rows");
+    if (m == 0) return 0;
+    HK_ARG(D && values && indices_i64, "hk_topk_rows: null pointer");
+    return launch_topk_rows(h, D, m, n, ldd, dtype, kk, values, reinterpret_cast<int64_t*>(indices_i64), st);
+}
+
+int hk_knn_vote(hk_handle_t hh, const void* indices_i64, int64_t m, int kk, const void* Y, int64_t n, int n_classes,
+                int64_t ldy, int dtype, void* classes_i64, void* stream) {
+    HK_ARG(dtype == HK_F32 || dtype == HK_F64, "hk_knn_vote: bad dtype");
+    HK_ARG(m >= 0 && n >= 1 && kk >= 1 && n_classes >= 1 && ldy >= n_classes, "hk_knn_vote: bad shape");
+    HK_HANDLE("hk_knn_vote");
+    if (m == 0) return 0;
+    HK_ARG(indices_i64 && Y && classes_i64, "hk_knn_vote: null pointer");
+    return launch_knn_vote(h, reinterpret_cast<const int64_t*>(indices_i64), m, kk, Y, n, n_classes, ldy, dtype,
+                           reinterpret_cast<int64_t*>(classes_i64), st);
+}
+
 int hk_comm_unique_id(void* id128) {
     HK_ARG(id128 != nullptr, "hk_comm_unique_id: null");
     return comm_unique_id(id128);

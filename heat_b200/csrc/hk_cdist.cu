@@ -22,12 +22,14 @@ __global__ void row_norms_kernel(const T* __restrict__ A, int64_t rows, int f, i
     out[r] = s;
 }
 
-template <typename T, bool QUAD>
+// BODY: 0 = sum (x-y)^2, 1 = x.y for the quadratic expansion, 2 = sum |x-y| (heat/spatial/distance.py:120-133)
+// post: 0 = as accumulated, 1 = sqrt, 2 = exp(-v / gden) with gden = 2 sigma^2 (distance.py:67-101)
+template <typename T, int BODY>
 __global__ void __launch_bounds__(256) cdist_simt_kernel(const T* __restrict__ X, int64_t m, int f,
                                                          int64_t ldx, const T* __restrict__ Y, int64_t n,
                                                          int64_t ldy, T* __restrict__ out, int64_t ldo,
                                                          const T* __restrict__ xn, const T* __restrict__ yn,
-                                                         int sqrt_flag) {
+                                                         int post, T gden) {
     __shared__ T xs[BK][BM + 4];
     __shared__ T ys[BK][BN + 4];
     const int tid = threadIdx.x;
@@ -61,8 +63,10 @@ __global__ void __launch_bounds__(256) cdist_simt_kernel(const T* __restrict__ X
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    if (QUAD) {
+                    if (BODY == 1) {
                         acc[a][b] = fma(xv[a], yv[b], acc[a][b]);
+                    } else if (BODY == 2) {
+                        acc[a][b] += fabs(xv[a] - yv[b]);
                     } else {
                         const T df = xv[a] - yv[b];
                         acc[a][b] = fma(df, df, acc[a][b]);
@@ -80,11 +84,14 @@ __global__ void __launch_bounds__(256) cdist_simt_kernel(const T* __restrict__ X
             const int64_t gj = j0 + tx * 4 + b;
             if (gj >= n) continue;
             T v = acc[a][b];
-            if (QUAD) {
+            if (BODY == 1) {
                 v = (xn[gi] + yn[gj]) - T(2) * v;
                 v = v < T(0) ? T(0) : v;  // clamp(0, inf); NaN propagates
             }
-            if (sqrt_flag) v = sqrt(v);
+            if (post == 1)
+                v = sqrt(v);
+            else if (post == 2)
+                v = exp(-v / gden);
             out[gi * ldo + gj] = v;
         }
     }
@@ -92,7 +99,8 @@ __global__ void __launch_bounds__(256) cdist_simt_kernel(const T* __restrict__ X
 
 template <typename T>
 int run_cdist(Handle* h, const T* X, int64_t m, int f, int64_t ldx, const T* Y, int64_t n, int64_t ldy,
-              T* out, int64_t ldo, int quad, int sqrt_flag, cudaStream_t st) {
+              T* out, int64_t ldo, int body, int post, double gden, cudaStream_t st) {
+    const int quad = body == 1;
     T* xn = nullptr;
     T* yn = nullptr;
     if (quad) {
@@ -114,12 +122,14 @@ int run_cdist(Handle* h, const T* X, int64_t m, int f, int64_t ldx, const T* Y, 
         dim3 grid(gx, gy);
         prof_begin(h, st);
         if (quad)
-            cdist_simt_kernel<T, true><<<grid, 256, 0, st>>>(X + r0 * ldx, m - r0, f, ldx, Y, n, ldy,
-                                                             out + r0 * ldo, ldo, xn + r0, yn, sqrt_flag);
+            cdist_simt_kernel<T, 1><<<grid, 256, 0, st>>>(X + r0 * ldx, m - r0, f, ldx, Y, n, ldy, out + r0 * ldo, ldo,
+                                                          xn + r0, yn, post, (T)gden);
+        else if (body == 2)
+            cdist_simt_kernel<T, 2><<<grid, 256, 0, st>>>(X + r0 * ldx, m - r0, f, ldx, Y, n, ldy, out + r0 * ldo, ldo,
+                                                          nullptr, nullptr, post, (T)gden);
         else
-            cdist_simt_kernel<T, false><<<grid, 256, 0, st>>>(X + r0 * ldx, m - r0, f, ldx, Y, n, ldy,
-                                                              out + r0 * ldo, ldo, nullptr, nullptr,
-                                                              sqrt_flag);
+            cdist_simt_kernel<T, 0><<<grid, 256, 0, st>>>(X + r0 * ldx, m - r0, f, ldx, Y, n, ldy, out + r0 * ldo, ldo,
+                                                          nullptr, nullptr, post, (T)gden);
         prof_end(h, st);
         HK_CUDA(cudaGetLastError());
         h->launches++;
@@ -130,23 +140,25 @@ int run_cdist(Handle* h, const T* X, int64_t m, int f, int64_t ldx, const T* Y, 
 }  // namespace
 
 int launch_cdist_tc(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n,
-                    int64_t ldy, void* out, int64_t ldo, int sqrt_flag, cudaStream_t stream);
+                    int64_t ldy, void* out, int64_t ldo, int post, float gscale, cudaStream_t stream);
 bool cdist_tc_supported(const Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y,
                         int64_t n, int64_t ldy, const void* out, int64_t ldo);
 
 int launch_cdist(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n,
-                 int64_t ldy, void* out, int64_t ldo, int dtype, int quad, int sqrt_flag,
-                 cudaStream_t stream) {
-    if (dtype == HK_F32 && quad && cdist_tc_supported(h, X, m, f, ldx, Y, n, ldy, out, ldo)) {
+                 int64_t ldy, void* out, int64_t ldo, int dtype, int body, int post, cudaStream_t stream,
+                 double gden) {
+    if (dtype == HK_F32 && body == 1 && cdist_tc_supported(h, X, m, f, ldx, Y, n, ldy, out, ldo)) {
         h->variant = "cdist_tc<f32>";
-        return launch_cdist_tc(h, X, m, f, ldx, Y, n, ldy, out, ldo, sqrt_flag, stream);
+        // exp(-v / gden) = 2^(v * gscale)
+        const float gscale = (float)(-1.4426950408889634 / gden);
+        return launch_cdist_tc(h, X, m, f, ldx, Y, n, ldy, out, ldo, post, gscale, stream);
     }
     h->variant = dtype == HK_F64 ? "cdist_simt<f64>" : "cdist_simt<f32>";
     if (dtype == HK_F64)
         return run_cdist<double>(h, (const double*)X, m, f, ldx, (const double*)Y, n, ldy, (double*)out, ldo,
-                                 quad, sqrt_flag, stream);
-    return run_cdist<float>(h, (const float*)X, m, f, ldx, (const float*)Y, n, ldy, (float*)out, ldo, quad,
-                            sqrt_flag, stream);
+                                 body, post, gden, stream);
+    return run_cdist<float>(h, (const float*)X, m, f, ldx, (const float*)Y, n, ldy, (float*)out, ldo, body, post,
+                            gden, stream);
 }
 
 }  // namespace hk

@@ -32,7 +32,8 @@ struct CdParams {
     int num_row_tiles, num_chunks;
     const float* xn;
     const float* yn;
-    int sqrt_flag;
+    int post;      // 0 = squared distances, 1 = sqrt, 2 = 2^(d2 * gscale) (Gaussian kernel)
+    float gscale;  // -log2(e) / (2 sigma^2)
     int nslot;  // B ring slots in use (2..NSLOT)
     int nstg;   // output staging buffers per epilogue warp (1 or 2)
     // ARGMIN variant (large-k Lloyd pass): no distance matrix is written; per row the first-index argmin over all n
@@ -119,6 +120,12 @@ __device__ __forceinline__ void tmem_wait_ld32(uint32_t (&v)[32]) {
                    "+r"(v[30]), "+r"(v[31])
                  :
                  : "memory");
+}
+
+__device__ __forceinline__ float exp2_fast(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
 }
 
 template <bool ARGMIN>
@@ -366,11 +373,16 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                             o.y = clamp0_nan(o.y);
                             o.z = clamp0_nan(o.z);
                             o.w = clamp0_nan(o.w);
-                            if (p.sqrt_flag) {
+                            if (p.post == 1) {
                                 o.x = sqrt_fast(o.x);
                                 o.y = sqrt_fast(o.y);
                                 o.z = sqrt_fast(o.z);
                                 o.w = sqrt_fast(o.w);
+                            } else if (p.post == 2) {
+                                o.x = exp2_fast(o.x * p.gscale);
+                                o.y = exp2_fast(o.y * p.gscale);
+                                o.z = exp2_fast(o.z * p.gscale);
+                                o.w = exp2_fast(o.w * p.gscale);
                             }
                             // staging tile: 32 rows x 128 B, 16-byte chunk index XOR (row & 7) (matches the store map)
                             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(
@@ -522,7 +534,7 @@ struct ArgminOut {
     const int32_t* state;
 };
 int launch_cdist_tc_impl(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n, int64_t ldy,
-                         void* out, int64_t ldo, int sqrt_flag, const ArgminOut* am, cudaStream_t st) {
+                         void* out, int64_t ldo, int post, float gscale, const ArgminOut* am, cudaStream_t st) {
     const int nkb = f / 32;
     // scratch: xl [m x f], yl [n x f], xn [m], yn [n]
     const size_t need = ((size_t)m * f + (size_t)n * f + (size_t)m + (size_t)n + 64) * sizeof(float);
@@ -571,7 +583,8 @@ int launch_cdist_tc_impl(Handle* h, const void* X, int64_t m, int f, int64_t ldx
     p.num_chunks = (int)((n + TN - 1) / TN);
     p.xn = xn;
     p.yn = yn;
-    p.sqrt_flag = sqrt_flag;
+    p.post = post;
+    p.gscale = gscale;
     p.o_A = (uint32_t)L.A;
     p.o_B = (uint32_t)L.B;
     p.o_stage = (uint32_t)L.stage;
@@ -603,8 +616,8 @@ int launch_cdist_tc_impl(Handle* h, const void* X, int64_t m, int f, int64_t ldx
 }  // namespace
 
 int launch_cdist_tc(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n, int64_t ldy,
-                    void* out, int64_t ldo, int sqrt_flag, cudaStream_t st) {
-    return launch_cdist_tc_impl(h, X, m, f, ldx, Y, n, ldy, out, ldo, sqrt_flag, nullptr, st);
+                    void* out, int64_t ldo, int post, float gscale, cudaStream_t st) {
+    return launch_cdist_tc_impl(h, X, m, f, ldx, Y, n, ldy, out, ldo, post, gscale, nullptr, st);
 }
 
 // distances are consumed in the epilogue: labels[row_base + r] = first-index argmin_j d2(x_r, y_j); rows whose runner-up
@@ -613,7 +626,7 @@ int launch_cdist_tc_argmin(Handle* h, const void* X, int64_t m, int f, int64_t l
                            int32_t* labels, int64_t row_base, int32_t* queue, int* qcount, const float* cmax2, float window,
                            const int32_t* state, cudaStream_t st) {
     ArgminOut am{labels, queue, qcount, cmax2, window, row_base, state};
-    return launch_cdist_tc_impl(h, X, m, f, ldx, Y, n, ldy, nullptr, 4, 0, &am, st);
+    return launch_cdist_tc_impl(h, X, m, f, ldx, Y, n, ldy, nullptr, 4, 0, 0.f, &am, st);
 }
 
 }  // namespace hk

@@ -165,9 +165,28 @@ int launch_finalize(Handle* h, const double* partials, const void* C_in, void* C
                     int k, int d, int dtype, int use_tol, double tol_cmp, void* shift2_out,
                     int32_t* state, cudaStream_t stream);
 
+// hk_kcluster.cu — L1 assignment, radix selection of per-cluster medians, nearest rows, top-k + vote
+int launch_assign_l1(Handle* h, const void* X, int64_t n, int d, int64_t ldx, int dtype, const void* C, int k,
+                     void* labels, int label_kind, double* fv, cudaStream_t st);
+int launch_row_keep(Handle* h, const void* X, int64_t n, int d, int64_t ldx, int dtype, uint8_t* keep, cudaStream_t st);
+int launch_select_hist(Handle* h, const void* X, int64_t n, int d, int64_t ldx, int dtype, const int64_t* labels,
+                       const uint8_t* keep, int k, const uint64_t* prefix, int pass, unsigned long long* hist,
+                       cudaStream_t st);
+int launch_select_step(Handle* h, const unsigned long long* hist, int64_t* remaining, uint64_t* prefix, int entries,
+                       cudaStream_t st);
+int launch_select_value(Handle* h, const uint64_t* prefix, const double* frac, int k, int d, int dtype, void* out,
+                        cudaStream_t st);
+int launch_nearest_rows_l1(Handle* h, const void* X, int64_t n, int d, int64_t ldx, int dtype, const void* P, int k,
+                           int64_t row_base, double* out_d, int64_t* out_i, cudaStream_t st);
+int launch_topk_rows(Handle* h, const void* D, int64_t m, int64_t n, int64_t ldd, int dtype, int kk, void* vals,
+                     int64_t* idx, cudaStream_t st);
+int launch_knn_vote(Handle* h, const int64_t* idx, int64_t m, int kk, const void* Y, int64_t n, int nc, int64_t ldy,
+                    int dtype, int64_t* classes, cudaStream_t st);
+
+// body: 0 = sum (x-y)^2, 1 = quadratic expansion, 2 = sum |x-y|; post: 0 none, 1 sqrt, 2 exp(-v / gden)
 int launch_cdist(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n,
-                 int64_t ldy, void* out, int64_t ldo, int dtype, int quad, int sqrt_flag,
-                 cudaStream_t stream);
+                 int64_t ldy, void* out, int64_t ldo, int dtype, int body, int post, cudaStream_t stream,
+                 double gden = 1.0);
 
 int comm_allreduce_f64(Handle* h, double* buf, int64_t count, cudaStream_t stream);
 

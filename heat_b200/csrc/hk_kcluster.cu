@@ -1,0 +1,488 @@
+// Other consumers of the "stream the rows of X against a small replicated codebook" pattern:
+//   * L1 assignment             <- KMedians / KMedoids._assign_to_cluster with metric = manhattan(expand=True)
+//                                  (heat/cluster/kmedians.py:43-50, kmedoids.py:45-52, _kcluster.py:352-370)
+//   * per-cluster, per-feature medians by distributed radix selection (counts only travel between ranks)
+//                               <- KMedians._update_centroids: ht.median of the rows of every cluster
+//                                  (heat/cluster/kmedians.py:60-103, heat/core/statistics.py:1684-1728)
+//   * nearest row to each of k points (first index) <- KMedoids._update_centroids (heat/cluster/kmedoids.py:94-110)
+//   * k smallest entries per row + class vote       <- KNeighborsClassifier.predict
+//                                  (heat/classification/kneighborsclassifier.py:124-135)
+// Plain SIMT kernels: these paths are bound by streaming X once per pass (k small) and are not the headline.
+#include <math.h>
+
+#include "hk_common.cuh"
+
+namespace hk {
+namespace {
+
+constexpr int NT = 256;
+
+// order-preserving integer image of a float (ascending; -0 < +0, NaN with the sign bit clear above +inf)
+template <typename T>
+struct Key;
+template <>
+struct Key<float> {
+    static constexpr int BITS = 32;
+    static __device__ __forceinline__ uint64_t enc(float v) {
+        const uint32_t u = __float_as_uint(v);
+        return (uint64_t)(u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u));
+    }
+    static __device__ __forceinline__ float dec(uint64_t k64) {
+        const uint32_t k = (uint32_t)k64;
+        return __uint_as_float((k >> 31) ? (k ^ 0x80000000u) : ~k);
+    }
+};
+template <>
+struct Key<double> {
+    static constexpr int BITS = 64;
+    static __device__ __forceinline__ uint64_t enc(double v) {
+        const uint64_t u = (uint64_t)__double_as_longlong(v);
+        return u ^ ((u >> 63) ? 0xFFFFFFFFFFFFFFFFull : 0x8000000000000000ull);
+    }
+    static __device__ __forceinline__ double dec(uint64_t k) {
+        return __longlong_as_double((long long)((k >> 63) ? (k ^ 0x8000000000000000ull) : ~k));
+    }
+};
+
+__device__ __forceinline__ void store_label(void* labels, int kind, int64_t i, int j) {
+    if (kind == HK_LABEL_I64)
+        reinterpret_cast<int64_t*>(labels)[i] = j;
+    else if (kind == HK_LABEL_I32)
+        reinterpret_cast<int32_t*>(labels)[i] = j;
+    else if (kind == HK_LABEL_U8)
+        reinterpret_cast<uint8_t*>(labels)[i] = (uint8_t)j;
+}
+
+// torch.min / argmin order on (value, index): NaN counts as the smallest value, the first occurrence wins
+template <typename T>
+__device__ __forceinline__ bool better(T a, int64_t ia, T b, int64_t ib) {
+    const bool an = a != a, bn = b != b;
+    if (an != bn) return an;
+    if (!an && a != b) return a < b;
+    return ia < ib;
+}
+
+// labels[i] = first-index argmin_j sum_f |x_if - c_jf|; fv_part[block] = sum over the block's rows of that minimum
+template <typename T, bool CSMEM>
+__global__ void __launch_bounds__(NT) assign_l1_kernel(const T* __restrict__ X, int64_t n, int d, int64_t ldx,
+                                                       const T* __restrict__ C, int k, void* labels, int label_kind,
+                                                       double* __restrict__ fv_part) {
+    extern __shared__ unsigned char sm_raw[];
+    T* cs = reinterpret_cast<T*>(sm_raw);
+    __shared__ double red[NT / 32];
+    const int tid = threadIdx.x;
+    if (CSMEM) {
+        for (int i = tid; i < k * d; i += NT) cs[i] = C[i];
+        __syncthreads();
+    }
+    double fv = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * NT + tid; i < n; i += (int64_t)gridDim.x * NT) {
+        const T* x = X + i * ldx;
+        T best = T(0);
+        int bj = 0;
+        for (int j = 0; j < k; ++j) {
+            const T* c = CSMEM ? cs + (size_t)j * d : C + (size_t)j * d;
+            T s = T(0);
+            for (int f = 0; f < d; ++f) s += fabs(x[f] - c[f]);
+            if (j == 0 || s < best || (s != s && best == best)) {
+                best = s;
+                bj = j;
+            }
+        }
+        store_label(labels, label_kind, i, bj);
+        fv += (double)best;
+    }
+    if (fv_part != nullptr) {
+        for (int o = 16; o > 0; o >>= 1) fv += __shfl_xor_sync(0xffffffffu, fv, o);
+        if ((tid & 31) == 0) red[tid >> 5] = fv;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < NT / 32; ++w) s += red[w];
+            fv_part[blockIdx.x] = s;
+        }
+    }
+}
+
+__global__ void sum_blocks_kernel(const double* __restrict__ part, int nb, double* __restrict__ out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double s = 0.0;
+        for (int b = 0; b < nb; ++b) s += part[b];  // fixed order: repeatable
+        out[0] = s;
+    }
+}
+
+// keep[i] = 0 for rows that are entirely zero (the reference drops them before the median, kmedians.py:76-79)
+template <typename T>
+__global__ void __launch_bounds__(NT) row_keep_kernel(const T* __restrict__ X, int64_t n, int d, int64_t ldx,
+                                                      uint8_t* __restrict__ keep) {
+    const int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x;
+    if (i >= n) return;
+    const T* x = X + i * ldx;
+    bool any = false;
+    for (int f = 0; f < d; ++f) any |= (x[f] != T(0));
+    keep[i] = any ? 1 : 0;
+}
+
+// One digit (8 bits) of the radix selection: for both order statistics w (lower / upper middle) of every (cluster,
+// feature), count the kept values of that cluster whose leading digits equal prefix[w][j][f] by their next digit.
+template <typename T>
+__global__ void __launch_bounds__(NT) select_hist_kernel(const T* __restrict__ X, int64_t n, int d, int64_t ldx,
+                                                         const int64_t* __restrict__ labels,
+                                                         const uint8_t* __restrict__ keep, int k,
+                                                         const uint64_t* __restrict__ prefix, int pass,
+                                                         unsigned long long* __restrict__ hist) {
+    const int shift = Key<T>::BITS - 8 * (pass + 1);
+    const int64_t total = n * (int64_t)d;
+    for (int64_t e = (int64_t)blockIdx.x * NT + threadIdx.x; e < total; e += (int64_t)gridDim.x * NT) {
+        const int64_t i = e / d;
+        const int f = (int)(e - i * d);
+        if (!keep[i]) continue;
+        const int64_t j = labels[i];
+        if (j < 0 || j >= k) continue;
+        const uint64_t key = Key<T>::enc(X[i * ldx + f]);
+        const uint64_t lead = pass == 0 ? 0 : (key >> (shift + 8));
+        const unsigned digit = (unsigned)((key >> shift) & 255u);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const size_t base = ((size_t)w * k + (size_t)j) * d + f;
+            if (pass == 0 || lead == prefix[base]) atomicAdd(&hist[base * 256 + digit], 1ULL);
+        }
+    }
+}
+
+// choose the digit that holds the wanted rank, descend into it
+__global__ void select_step_kernel(const unsigned long long* __restrict__ hist, int64_t* __restrict__ remaining,
+                                   uint64_t* __restrict__ prefix, int entries) {
+    const int base = blockIdx.x * blockDim.x + threadIdx.x;
+    if (base >= entries) return;
+    int64_t rem = remaining[base];
+    unsigned digit = 255;
+    for (unsigned b = 0; b < 256; ++b) {
+        const int64_t c = (int64_t)hist[(size_t)base * 256 + b];
+        if (rem < c) {
+            digit = b;
+            break;
+        }
+        rem -= c;
+    }
+    remaining[base] = rem;
+    prefix[base] = (prefix[base] << 8) | digit;
+}
+
+// median = lo + (hi - lo) * frac (heat/core/statistics.py:1708-1728); frac[j] = 0.5 for an even count, else 0
+template <typename T>
+__global__ void select_value_kernel(const uint64_t* __restrict__ prefix, const double* __restrict__ frac, int k, int d,
+                                    T* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= k * d) return;
+    const int j = e / d;
+    const T lo = Key<T>::dec(prefix[e]);
+    const T hi = Key<T>::dec(prefix[(size_t)k * d + e]);
+    out[e] = lo + (hi - lo) * (T)frac[j];
+}
+
+// per block and point j: the row (first index) with the smallest L1 distance to P[j]
+template <typename T>
+__global__ void __launch_bounds__(NT) nearest_rows_l1_kernel(const T* __restrict__ X, int64_t n, int d, int64_t ldx,
+                                                             const T* __restrict__ P, int k, int64_t row_base,
+                                                             double* __restrict__ part_d, int64_t* __restrict__ part_i) {
+    __shared__ double sd[NT / 32];
+    __shared__ int64_t si[NT / 32];
+    const int tid = threadIdx.x;
+    for (int j = 0; j < k; ++j) {
+        const T* p = P + (size_t)j * d;
+        double bd = INFINITY;
+        int64_t bi = INT64_MAX;
+        for (int64_t i = (int64_t)blockIdx.x * NT + tid; i < n; i += (int64_t)gridDim.x * NT) {
+            const T* x = X + i * ldx;
+            T s = T(0);
+            for (int f = 0; f < d; ++f) s += fabs(x[f] - p[f]);
+            if (better<double>((double)s, row_base + i, bd, bi)) {
+                bd = (double)s;
+                bi = row_base + i;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (better<double>(od, oi, bd, bi)) {
+                bd = od;
+                bi = oi;
+            }
+        }
+        if ((tid & 31) == 0) {
+            sd[tid >> 5] = bd;
+            si[tid >> 5] = bi;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < NT / 32; ++w)
+                if (better<double>(sd[w], si[w], bd, bi)) {
+                    bd = sd[w];
+                    bi = si[w];
+                }
+            part_d[(size_t)blockIdx.x * k + j] = bd;
+            part_i[(size_t)blockIdx.x * k + j] = bi;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void nearest_final_kernel(const double* __restrict__ part_d, const int64_t* __restrict__ part_i, int nb, int k,
+                                     double* __restrict__ out_d, int64_t* __restrict__ out_i) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    double bd = part_d[j];
+    int64_t bi = part_i[j];
+    for (int b = 1; b < nb; ++b) {
+        const double od = part_d[(size_t)b * k + j];
+        const int64_t oi = part_i[(size_t)b * k + j];
+        if (better<double>(od, oi, bd, bi)) {
+            bd = od;
+            bi = oi;
+        }
+    }
+    out_d[j] = bd;
+    out_i[j] = bi;
+}
+
+// one warp per row: the kk smallest (value, index) pairs in ascending order; NaN entries are never selected before a
+// number (torch.topk(largest=False) ranks NaN as the largest value)
+template <typename T>
+__global__ void __launch_bounds__(NT) topk_rows_kernel(const T* __restrict__ D, int64_t m, int64_t n, int64_t ldd, int kk,
+                                                       T* __restrict__ vals, int64_t* __restrict__ idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * NT + threadIdx.x) >> 5;
+    if (row >= m) return;
+    const T* r = D + row * ldd;
+    T last_v = T(0);
+    int64_t last_i = -1;
+    for (int t = 0; t < kk; ++t) {
+        T bv = T(0);
+        int64_t bi = -1;  // -1: nothing found yet
+        for (int64_t c = lane; c < n; c += 32) {
+            const T v = r[c];
+            // candidates: strictly after (last_v, last_i) in (value, index) order; NaN sorts after every number
+            const bool vn = v != v;
+            bool after;
+            if (last_i < 0)
+                after = true;
+            else {
+                const bool ln = last_v != last_v;
+                if (vn != ln)
+                    after = vn;
+                else if (!vn && v != last_v)
+                    after = v > last_v;
+                else
+                    after = c > last_i;
+            }
+            if (!after) continue;
+            bool take;
+            if (bi < 0)
+                take = true;
+            else {
+                const bool bn = bv != bv;
+                if (vn != bn)
+                    take = bn;
+                else if (!vn && v != bv)
+                    take = v < bv;
+                else
+                    take = c < bi;
+            }
+            if (take) {
+                bv = v;
+                bi = c;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const T ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi < 0) continue;
+            bool take;
+            if (bi < 0)
+                take = true;
+            else {
+                const bool on = ov != ov, bn = bv != bv;
+                if (on != bn)
+                    take = bn;
+                else if (!on && ov != bv)
+                    take = ov < bv;
+                else
+                    take = oi < bi;
+            }
+            if (take) {
+                bv = ov;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            vals[row * kk + t] = bv;
+            idx[row * kk + t] = bi;
+        }
+        last_v = bv;
+        last_i = bi;
+    }
+}
+
+// classes[i] = first-index argmax_c sum_t Y[idx[i,t], c]   (one-hot or soft label rows, kneighborsclassifier.py:128-134)
+template <typename T>
+__global__ void __launch_bounds__(NT) knn_vote_kernel(const int64_t* __restrict__ idx, int64_t m, int kk,
+                                                      const T* __restrict__ Y, int64_t n, int nc, int64_t ldy,
+                                                      int64_t* __restrict__ classes) {
+    const int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x;
+    if (i >= m) return;
+    T best = T(0);
+    int bc = 0;
+    for (int c = 0; c < nc; ++c) {
+        T s = T(0);
+        for (int t = 0; t < kk; ++t) {
+            const int64_t r = idx[i * kk + t];
+            if (r >= 0 && r < n) s += Y[r * ldy + c];
+        }
+        if (c == 0 || s > best || (s != s && best == best)) {  // torch.max: NaN wins, first occurrence
+            best = s;
+            bc = c;
+        }
+    }
+    classes[i] = bc;
+}
+
+int blocks_for(const Handle* h, int64_t work_items) {
+    int64_t b = (work_items + NT - 1) / NT;
+    const int64_t cap = (int64_t)h->num_sms * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+template <typename T>
+int run_assign_l1(Handle* h, const T* X, int64_t n, int d, int64_t ldx, const T* C, int k, void* labels, int label_kind,
+                  double* fv, cudaStream_t st) {
+    const int grid = blocks_for(h, n);
+    double* part = nullptr;
+    if (fv != nullptr) {
+        int rc = ensure_part(h, (size_t)grid * sizeof(double) + 64);
+        if (rc) return rc;
+        part = reinterpret_cast<double*>(h->part);
+    }
+    const size_t csz = (size_t)k * d * sizeof(T);
+    prof_begin(h, st);
+    if (csz <= 96 * 1024) {
+        HK_CUDA(cudaFuncSetAttribute(assign_l1_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csz));
+        assign_l1_kernel<T, true><<<grid, NT, csz, st>>>(X, n, d, ldx, C, k, labels, label_kind, part);
+    } else {
+        assign_l1_kernel<T, false><<<grid, NT, 0, st>>>(X, n, d, ldx, C, k, labels, label_kind, part);
+    }
+    prof_end(h, st);
+    HK_CUDA(cudaGetLastError());
+    h->launches++;
+    if (fv != nullptr) {
+        sum_blocks_kernel<<<1, 32, 0, st>>>(part, grid, fv);
+        HK_CUDA(cudaGetLastError());
+        h->launches++;
+    }
+    return 0;
+}
+
+}  // namespace
+
+int launch_assign_l1(Handle* h, const void* X, int64_t n, int d, int64_t ldx, int dtype, const void* C, int k,
+                     void* labels, int label_kind, double* fv, cudaStream_t st) {
+    h->variant = dtype == HK_F64 ? "assign_l1<f64>" : "assign_l1<f32>";
+    if (dtype == HK_F64)
+        return run_assign_l1<double>(h, (const double*)X, n, d, ldx, (const double*)C, k, labels, label_kind, fv, st);
+    return run_assign_l1<float>(h, (const float*)X, n, d, ldx, (const float*)C, k, labels, label_kind, fv, st);
+}
+
+int launch_row_keep(Handle* h, const void* X, int64_t n, int d, int64_t ldx, int dtype, uint8_t* keep, cudaStream_t st) {
+    const unsigned grid = (unsigned)((n + NT - 1) / NT);
+    if (dtype == HK_F64)
+        row_keep_kernel<double><<<grid, NT, 0, st>>>((const double*)X, n, d, ldx, keep);
+    else
+        row_keep_kernel<float><<<grid, NT, 0, st>>>((const float*)X, n, d, ldx, keep);
+    HK_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int launch_select_hist(Handle* h, const void* X, int64_t n, int d, int64_t ldx, int dtype, const int64_t* labels,
+                       const uint8_t* keep, int k, const uint64_t* prefix, int pass, unsigned long long* hist,
+                       cudaStream_t st) {
+    const int grid = blocks_for(h, n * (int64_t)d);
+    if (dtype == HK_F64)
+        select_hist_kernel<double><<<grid, NT, 0, st>>>((const double*)X, n, d, ldx, labels, keep, k, prefix, pass, hist);
+    else
+        select_hist_kernel<float><<<grid, NT, 0, st>>>((const float*)X, n, d, ldx, labels, keep, k, prefix, pass, hist);
+    HK_CUDA(cudaGetLastError());
+    h->launches++;
+    h->variant = dtype == HK_F64 ? "select_hist<f64>" : "select_hist<f32>";
+    return 0;
+}
+
+int launch_select_step(Handle* h, const unsigned long long* hist, int64_t* remaining, uint64_t* prefix, int entries,
+                       cudaStream_t st) {
+    select_step_kernel<<<(entries + 127) / 128, 128, 0, st>>>(hist, remaining, prefix, entries);
+    HK_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int launch_select_value(Handle* h, const uint64_t* prefix, const double* frac, int k, int d, int dtype, void* out,
+                        cudaStream_t st) {
+    const int e = k * d;
+    if (dtype == HK_F64)
+        select_value_kernel<double><<<(e + 127) / 128, 128, 0, st>>>(prefix, frac, k, d, (double*)out);
+    else
+        select_value_kernel<float><<<(e + 127) / 128, 128, 0, st>>>(prefix, frac, k, d, (float*)out);
+    HK_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int launch_nearest_rows_l1(Handle* h, const void* X, int64_t n, int d, int64_t ldx, int dtype, const void* P, int k,
+                           int64_t row_base, double* out_d, int64_t* out_i, cudaStream_t st) {
+    const int grid = blocks_for(h, n);
+    const size_t need = (size_t)grid * k * (sizeof(double) + sizeof(int64_t)) + 64;
+    int rc = ensure_part(h, need);
+    if (rc) return rc;
+    double* pd = reinterpret_cast<double*>(h->part);
+    int64_t* pi = reinterpret_cast<int64_t*>(pd + (size_t)grid * k);
+    if (dtype == HK_F64)
+        nearest_rows_l1_kernel<double><<<grid, NT, 0, st>>>((const double*)X, n, d, ldx, (const double*)P, k, row_base, pd, pi);
+    else
+        nearest_rows_l1_kernel<float><<<grid, NT, 0, st>>>((const float*)X, n, d, ldx, (const float*)P, k, row_base, pd, pi);
+    HK_CUDA(cudaGetLastError());
+    nearest_final_kernel<<<(k + 127) / 128, 128, 0, st>>>(pd, pi, grid, k, out_d, out_i);
+    HK_CUDA(cudaGetLastError());
+    h->launches += 2;
+    h->variant = dtype == HK_F64 ? "nearest_rows_l1<f64>" : "nearest_rows_l1<f32>";
+    return 0;
+}
+
+int launch_topk_rows(Handle* h, const void* D, int64_t m, int64_t n, int64_t ldd, int dtype, int kk, void* vals,
+                     int64_t* idx, cudaStream_t st) {
+    const unsigned grid = (unsigned)((m * 32 + NT - 1) / NT);
+    if (dtype == HK_F64)
+        topk_rows_kernel<double><<<grid, NT, 0, st>>>((const double*)D, m, n, ldd, kk, (double*)vals, idx);
+    else
+        topk_rows_kernel<float><<<grid, NT, 0, st>>>((const float*)D, m, n, ldd, kk, (float*)vals, idx);
+    HK_CUDA(cudaGetLastError());
+    h->launches++;
+    h->variant = dtype == HK_F64 ? "topk_rows<f64>" : "topk_rows<f32>";
+    return 0;
+}
+
+int launch_knn_vote(Handle* h, const int64_t* idx, int64_t m, int kk, const void* Y, int64_t n, int nc, int64_t ldy,
+                    int dtype, int64_t* classes, cudaStream_t st) {
+    const unsigned grid = (unsigned)((m + NT - 1) / NT);
+    if (dtype == HK_F64)
+        knn_vote_kernel<double><<<grid, NT, 0, st>>>(idx, m, kk, (const double*)Y, n, nc, ldy, classes);
+    else
+        knn_vote_kernel<float><<<grid, NT, 0, st>>>(idx, m, kk, (const float*)Y, n, nc, ldy, classes);
+    HK_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+}  // namespace hk

@@ -20,7 +20,7 @@
 namespace hk {
 
 int launch_cdist_tc(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n, int64_t ldy,
-                    void* out, int64_t ldo, int sqrt_flag, cudaStream_t st);
+                    void* out, int64_t ldo, int post, float gscale, cudaStream_t st);
 int launch_cdist_tc_argmin(Handle* h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n, int64_t ldy,
                            int32_t* labels, int64_t row_base, int32_t* queue, int* qcount, const float* cmax2, float window,
                            const int32_t* state, cudaStream_t st);

@@ -9,10 +9,12 @@ import torch
 
 from . import _lib
 from ._lib import (HK_F32, HK_F64, HK_LABEL_I32, HK_LABEL_I64, HK_LABEL_NONE, HK_LABEL_U8, HK_PATH_AUTO,
-                   HK_PATH_GENERIC, HK_PATH_ROW128, HK_PATH_SIMT, HK_PATH_TC, check)
+                   HK_METRIC_EUCLIDEAN, HK_METRIC_GAUSSIAN, HK_METRIC_MANHATTAN, HK_PATH_GENERIC, HK_PATH_ROW128,
+                   HK_PATH_SIMT, HK_PATH_TC, check)
 
 _DT = {torch.float32: HK_F32, torch.float64: HK_F64}
 _LK = {torch.uint8: HK_LABEL_U8, torch.int32: HK_LABEL_I32, torch.int64: HK_LABEL_I64}
+METRICS = {"euclidean": HK_METRIC_EUCLIDEAN, "gaussian": HK_METRIC_GAUSSIAN, "manhattan": HK_METRIC_MANHATTAN}
 PATHS = {"auto": HK_PATH_AUTO, "simt": HK_PATH_SIMT, "tc": HK_PATH_TC, "generic": HK_PATH_GENERIC,
          "row128": HK_PATH_ROW128}
 
@@ -177,6 +179,84 @@ class CudaEngine:
                                 y.stride(0) if n > 1 else f, _ptr(out), out.stride(0) if m > 1 else n,
                                 _DT[x.dtype], int(quadratic_expansion), int(sqrt), _stream(self.device)),
               "hk_cdist")
+
+    def pairwise(self, x, y, out, metric: str = "euclidean", expand: bool = False, sigma: float = 1.0):
+        """out = metric(x, y) on local blocks; ``out`` may be a column slice of a wider matrix (row stride kept)."""
+        m, f = x.shape
+        n = y.shape[0]
+        check(self.lib.hk_pairwise(self.h, _ptr(x), m, f, x.stride(0) if m > 1 else f, _ptr(y), n,
+                                   y.stride(0) if n > 1 else f, _ptr(out), out.stride(0) if m > 1 else max(n, 1),
+                                   _DT[x.dtype], METRICS[metric], int(expand), float(sigma), _stream(self.device)),
+              "hk_pairwise")
+
+    # -- other consumers of the assignment pattern (KMedians / KMedoids / kNN) ---------------------------------
+    def assign_l1(self, x, c, labels, fv=None):
+        self._check_x(x, c)
+        n, d = x.shape
+        check(self.lib.hk_assign_l1(self.h, _ptr(x), n, d, x.stride(0) if n > 1 else d, _DT[x.dtype], _ptr(c), c.shape[0],
+                                    _ptr(labels), _LK[labels.dtype] if labels is not None else HK_LABEL_NONE, _ptr(fv),
+                                    _stream(self.device)), "hk_assign_l1")
+
+    def cluster_medians(self, x, labels, k: int, allsum=None):
+        """Medians of every (cluster, feature) over the rows of all ranks (hk_select_* protocol of include/hkmeans.h).
+        ``allsum(t)`` sums an int64 device tensor over the ranks in place (None: one process).  Returns
+        ``(medians [k, d], counts [k] int64)``; rows that are entirely zero are not counted (kmedians.py:76-79)."""
+        n, d = x.shape
+        dt, st = _DT[x.dtype], _stream(self.device)
+        ldx = x.stride(0) if n > 1 else d
+        dev = x.device
+        keep = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+        check(self.lib.hk_row_keep(self.h, _ptr(x), n, d, ldx, dt, _ptr(keep), st), "hk_row_keep")
+        lab = labels.reshape(-1)
+        if lab.dtype != torch.int64 or not lab.is_contiguous():
+            lab = lab.to(torch.int64).contiguous()
+        prefix = torch.zeros((2, k, d), dtype=torch.int64, device=dev)  # uint64 bit patterns
+        remaining = torch.zeros((2, k, d), dtype=torch.int64, device=dev)
+        hist = torch.empty((2, k, d, 256), dtype=torch.int64, device=dev)
+        counts = None
+        for p in range(self.lib.hk_select_passes(dt)):
+            hist.zero_()
+            check(self.lib.hk_select_hist(self.h, _ptr(x), n, d, ldx, dt, _ptr(lab), _ptr(keep), k, _ptr(prefix), p,
+                                          _ptr(hist), st), "hk_select_hist")
+            if allsum is not None:
+                allsum(hist)
+            if p == 0:
+                counts = hist[0, :, 0, :].sum(dim=1)  # kept rows per cluster
+                remaining[0] = ((counts - 1).clamp(min=0) // 2).view(k, 1)
+                remaining[1] = (counts // 2).view(k, 1)
+            check(self.lib.hk_select_step(self.h, _ptr(hist), _ptr(remaining), _ptr(prefix), k, d, st), "hk_select_step")
+        frac = torch.where(counts % 2 == 0, 0.5, 0.0).to(torch.float64)
+        med = torch.empty((k, d), dtype=x.dtype, device=dev)
+        check(self.lib.hk_select_value(self.h, _ptr(prefix), _ptr(frac), k, d, dt, _ptr(med), st), "hk_select_value")
+        return med, counts
+
+    def nearest_rows_l1(self, x, p, row_base: int):
+        """(distance [k] float64, global row index [k] int64) of the shard row closest in L1 to every row of ``p``."""
+        n, d = x.shape
+        k = p.shape[0]
+        bd = torch.full((k,), float("inf"), dtype=torch.float64, device=x.device)
+        bi = torch.full((k,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=x.device)
+        if n > 0:
+            check(self.lib.hk_nearest_rows_l1(self.h, _ptr(x), n, d, x.stride(0) if n > 1 else d, _DT[x.dtype], _ptr(p), k,
+                                              int(row_base), _ptr(bd), _ptr(bi), _stream(self.device)),
+                  "hk_nearest_rows_l1")
+        return bd, bi
+
+    def topk_rows(self, dmat, kk: int):
+        m, n = dmat.shape
+        vals = torch.empty((m, kk), dtype=dmat.dtype, device=dmat.device)
+        idx = torch.empty((m, kk), dtype=torch.int64, device=dmat.device)
+        check(self.lib.hk_topk_rows(self.h, _ptr(dmat), m, n, dmat.stride(0) if m > 1 else n, _DT[dmat.dtype], kk,
+                                    _ptr(vals), _ptr(idx), _stream(self.device)), "hk_topk_rows")
+        return vals, idx
+
+    def knn_vote(self, idx, y):
+        m, kk = idx.shape
+        n, nc = y.shape
+        out = torch.empty(m, dtype=torch.int64, device=idx.device)
+        check(self.lib.hk_knn_vote(self.h, _ptr(idx), m, kk, _ptr(y), n, nc, y.stride(0) if n > 1 else nc, _DT[y.dtype],
+                                   _ptr(out), _stream(self.device)), "hk_knn_vote")
+        return out
 
     # -- introspection -------------------------------------------------------------------------------------
     def launch_count(self) -> int:

@@ -10,6 +10,8 @@ everything else falls through to the reference implementation untouched:
 * ``heat.cluster.KMeans.fit``            (heat/cluster/kmeans.py:105-148)  -> fused ``hk_lloyd_step`` loop
 * ``heat.cluster.KMeans._assign_to_cluster`` (heat/cluster/_kcluster.py:352-370) -> ``hk_assign``
   (``predict`` and ``fit_predict`` go through it)
+* ``heat.spatial.distance._euclidian / _gaussian / _gaussian_fast / _manhattan / _manhattan_fast`` (distance.py:17-133) ->
+  ``hk_pairwise`` on the local blocks (``rbf``, ``manhattan``, ``cdist`` without the expansion; rings untouched).
 * ``heat.spatial.distance._euclidian_fast`` (heat/spatial/distance.py:32-44) -> ``hk_cdist`` on the local blocks, which
   accelerates ``cdist(quadratic_expansion=True)`` for every caller without touching ``_dist``'s split logic
   (the operator plug point, distance.py:209-227).
@@ -123,9 +125,32 @@ def install() -> bool:
         _engine.get_engine(x.device).cdist(xc, yc, out, quadratic_expansion=True, sqrt=True)
         return out
 
+    def _tile(name, metric, expand):
+        """A replacement for one of distance.py's tile metrics (:17-133): the same local blocks through hk_pairwise."""
+        orig = getattr(hdist, name)
+        _ORIG["tile_" + name] = orig
+
+        def tile(x: torch.Tensor, y: torch.Tensor, sigma: float = 1.0) -> torch.Tensor:
+            if not (x.is_cuda and y.is_cuda and x.dtype == y.dtype and x.dtype in (torch.float32, torch.float64)
+                    and x.dim() == 2 and y.dim() == 2):
+                return orig(x, y, sigma) if metric == "gaussian" else orig(x, y)
+            xc = x if x.stride(1) == 1 else x.contiguous()
+            yc = y if y.stride(1) == 1 else y.contiguous()
+            out = torch.empty((xc.shape[0], yc.shape[0]), dtype=x.dtype, device=x.device)
+            _engine.get_engine(x.device).pairwise(xc, yc, out, metric, expand, sigma)
+            return out
+
+        tile.__name__ = name
+        setattr(hdist, name, tile)
+
     KM.fit = fit
     KM._assign_to_cluster = _assign_to_cluster
     hdist._euclidian_fast = _euclidian_fast
+    # rbf / manhattan / cdist without the expansion: _dist (layouts, rings) stays the reference's
+    for name, metric, expand in (("_euclidian", "euclidean", False), ("_gaussian", "gaussian", False),
+                                 ("_gaussian_fast", "gaussian", True), ("_manhattan", "manhattan", False),
+                                 ("_manhattan_fast", "manhattan", True)):
+        _tile(name, metric, expand)
     return True
 
 
@@ -138,4 +163,7 @@ def uninstall() -> None:
     ht.cluster.KMeans.fit = _ORIG["fit"]
     ht.cluster.KMeans._assign_to_cluster = _ORIG["assign"]
     hdist._euclidian_fast = _ORIG["efast"]
+    for key, fn in _ORIG.items():
+        if key.startswith("tile_"):
+            setattr(hdist, key[5:], fn)
     _ORIG.clear()

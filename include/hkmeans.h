@@ -15,6 +15,9 @@
  *   hk_cdist
  *        <- cdist -> _dist -> _euclidian_fast / _euclidian (X split 0|None, Y replicated)
  *                                           heat/spatial/distance.py:32-64, 136-156, 409-414
+ *   hk_pairwise
+ *        <- rbf / manhattan (and cdist) -> _dist -> _gaussian(_fast) / _manhattan(_fast)
+ *                                           heat/spatial/distance.py:67-133, 159-207
  *   hk_comm_* / hk_allreduce_f64 (and the peer-memory exchange inside hk_lloyd_step / hk_lloyd_run)
  *        <- MPICommunication.Allreduce(MPI.IN_PLACE, t, MPI.SUM) as issued by __reduce_op
  *                                           heat/core/communication.py:1089-1110,
@@ -133,6 +136,60 @@ int hk_assign(hk_handle_t h, const void* X, int64_t n_local, int d, int64_t ldx,
 int hk_cdist(hk_handle_t h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n,
              int64_t ldy, void* out, int64_t ldo, int dtype, int quadratic_expansion,
              int sqrt_flag, void* stream);
+
+/* Other metrics of heat/spatial/distance.py on the same local blocks (what _dist calls per tile, distance.py:409-414
+ * and inside the rings :262-359, :431-473):
+ *   HK_METRIC_EUCLIDEAN  cdist      sqrt(sum (x-y)^2)                  expand = quadratic_expansion   distance.py:17-64
+ *   HK_METRIC_GAUSSIAN   rbf        exp(-|x-y|^2 / (2 sigma^2))        expand = quadratic_expansion   distance.py:67-101
+ *   HK_METRIC_MANHATTAN  manhattan  sum |x-y|                          expand ignored (same values)   distance.py:104-133 */
+#define HK_METRIC_EUCLIDEAN 0
+#define HK_METRIC_GAUSSIAN 1
+#define HK_METRIC_MANHATTAN 2
+int hk_pairwise(hk_handle_t h, const void* X, int64_t m, int f, int64_t ldx, const void* Y, int64_t n,
+                int64_t ldy, void* out, int64_t ldo, int dtype, int metric, int expand, double sigma,
+                void* stream);
+
+/* ---- other consumers of the assignment pattern (KMedians / KMedoids / KNeighborsClassifier) ----------------------- */
+
+/* labels[i] = first-index argmin_j sum_f |x_if - c_jf| (+ optional sum_i of that minimum, one double)
+ *   <- _KCluster._assign_to_cluster with metric = manhattan(x, y, expand=True), p = 1
+ *      heat/cluster/kmedians.py:43-50, heat/cluster/kmedoids.py:45-52, heat/cluster/_kcluster.py:352-370 */
+int hk_assign_l1(hk_handle_t h, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, const void* C, int k,
+                 void* labels, int label_kind, double* min_d_sum, void* stream);
+
+/* Per-cluster, per-feature medians of a row shard by radix selection; only k*d*2*256 counts travel between ranks.
+ *   <- KMedians / KMedoids._update_centroids: ht.median over the rows of every cluster, all-zero rows dropped first
+ *      heat/cluster/kmedians.py:60-103, heat/cluster/kmedoids.py:57-93, heat/core/statistics.py:1684-1728
+ * Protocol (every array on the device; w = 0 lower middle, 1 upper middle):
+ *   hk_row_keep    keep[i] = row i is not entirely zero
+ *   for pass in 0 .. hk_select_passes(dtype)-1:
+ *       zero hist[2][k][d][256] (int64); hk_select_hist adds this shard's counts; sum hist over the ranks;
+ *       (after pass 0 the caller derives the cluster sizes from hist and sets remaining[2][k][d] to the wanted ranks)
+ *       hk_select_step   picks the digit holding rank remaining[w][j][f], appends it to prefix[w][j][f] (uint64)
+ *   hk_select_value   medians[j][f] = lo + (hi - lo) * frac[j]   (frac = 0.5 for even cluster sizes, else 0) */
+int hk_row_keep(hk_handle_t h, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, void* keep_u8,
+                void* stream);
+int hk_select_passes(int dtype);
+int hk_select_hist(hk_handle_t h, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, const void* labels_i64,
+                   const void* keep_u8, int k, const void* prefix_u64, int pass, void* hist_i64, void* stream);
+int hk_select_step(hk_handle_t h, const void* hist_i64, void* remaining_i64, void* prefix_u64, int k, int d,
+                   void* stream);
+int hk_select_value(hk_handle_t h, const void* prefix_u64, const double* frac, int k, int d, int dtype, void* medians,
+                    void* stream);
+
+/* best_index[j] = global index (row_base + i) of the shard row closest in L1 to P[j], first index on ties
+ *   <- KMedoids._update_centroids: dist = manhattan(x, median); idx = dist.argmin(axis=0)
+ *      heat/cluster/kmedoids.py:94-110 */
+int hk_nearest_rows_l1(hk_handle_t h, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, const void* P,
+                       int k, int64_t row_base, double* best_dist, void* best_index_i64, void* stream);
+
+/* The kk smallest entries of every row of D (ascending, lower index first on ties) and the class vote over them
+ *   <- KNeighborsClassifier.predict: ht.topk(distances, n_neighbors, largest=False); y[indices] summed; argmax
+ *      heat/classification/kneighborsclassifier.py:124-135 */
+int hk_topk_rows(hk_handle_t h, const void* D, int64_t m, int64_t n, int64_t ldd, int dtype, int kk, void* values,
+                 void* indices_i64, void* stream);
+int hk_knn_vote(hk_handle_t h, const void* indices_i64, int64_t m, int kk, const void* Y, int64_t n, int n_classes,
+                int64_t ldy, int dtype, void* classes_i64, void* stream);
 
 /* ---- communicator (NCCL, resolved with dlopen at first use) ----------------------------- */
 int hk_comm_unique_id(void* id128);                      /* 128-byte ncclUniqueId            */

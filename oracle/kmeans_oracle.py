@@ -83,6 +83,46 @@ def euclidian(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return torch.cdist(x, y)
 
 
+def gaussian(x: torch.Tensor, y: torch.Tensor, sigma: float = 1.0) -> torch.Tensor:
+    """exp(-cdist(x, y)^2 / (2 sigma^2)) (heat/spatial/distance.py:67-84)."""
+    d2 = euclidian(x, y) ** 2
+    return torch.exp(-d2 / (2 * sigma * sigma))
+
+
+def gaussian_fast(x: torch.Tensor, y: torch.Tensor, sigma: float = 1.0) -> torch.Tensor:
+    """Same through the quadratic expansion (heat/spatial/distance.py:87-101)."""
+    d2 = quadratic_expand(x, y)
+    return torch.exp(-d2 / (2 * sigma * sigma))
+
+
+def manhattan(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """torch.cdist(p=1) (heat/spatial/distance.py:104-117)."""
+    return torch.cdist(x, y, p=1)
+
+
+def manhattan_fast(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """sum |x - y| by dimension expansion (heat/spatial/distance.py:120-133)."""
+    return torch.sum(torch.abs(x.unsqueeze(1) - y.unsqueeze(0)), dim=2)
+
+
+def pairwise(x: torch.Tensor, y: torch.Tensor, metric: str = "euclidean", expand: bool = False,
+             sigma: float = 1.0) -> torch.Tensor:
+    """One tile ``metric(X.larray, Y block)`` of ``_dist`` (heat/spatial/distance.py:262, 409-414, 441, 472) for
+    cdist / rbf / manhattan (:136-206)."""
+    if x.ndim != 2 or y.ndim != 2:
+        raise NotImplementedError("Only 2D data matrices are currently supported")
+    if x.shape[1] != y.shape[1]:
+        raise ValueError("Inputs must have same shape[1]")
+    a, b = _promote_pair(x, y)
+    if metric == "euclidean":
+        return euclidian_fast(a, b) if expand else euclidian(a, b)
+    if metric == "gaussian":
+        return gaussian_fast(a, b, sigma) if expand else gaussian(a, b, sigma)
+    if metric == "manhattan":
+        return manhattan_fast(a, b) if expand else manhattan(a, b)
+    raise ValueError(metric)
+
+
 def _promote_pair(x: torch.Tensor, y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """heat/spatial/distance.py:392-403: common type, at least float32; fp64 if either is 64-bit float."""
     if x.dtype == torch.float64 or y.dtype == torch.float64:

@@ -134,8 +134,11 @@ class Status:
     def Get_source(self):
         return self.source
 
-    def Get_count(self, *a):
-        return self.nbytes
+    def Get_count(self, datatype=None):
+        # bytes without a datatype (mpi4py's default MPI.BYTE), elements of ``datatype`` otherwise
+        if datatype is None or datatype.np_dtype is None:
+            return self.nbytes
+        return self.nbytes // np.dtype(datatype.np_dtype).itemsize
 
 
 class Request:
@@ -267,7 +270,7 @@ class Comm:
     def Isend(self, buf, dest=0, tag=0):
         """Isend(buf, dest, tag=0)"""
         if not isinstance(buf, np.ndarray):
-            raise NotImplementedError("mpi4py stand-in: Isend supports numpy buffers only")
+            buf = _as_tensor(buf).numpy()  # heat's (memory, count, Datatype) spec of a contiguous torch tensor
         self._send_np(buf, dest)
         return Request()
 
@@ -286,9 +289,11 @@ class Comm:
 
     def Recv(self, buf, source=ANY_SOURCE, tag=ANY_TAG, status=None):
         """Recv(buf, source, tag, status)"""
-        if not isinstance(buf, np.ndarray):
-            raise NotImplementedError("mpi4py stand-in: Recv supports numpy buffers only")
         msg = self._recv_np(source)
+        if not isinstance(buf, np.ndarray):
+            t = _as_tensor(buf)
+            t.copy_(torch.from_numpy(np.frombuffer(msg, dtype=t.numpy().dtype, count=t.numel()).copy()))
+            return
         np.copyto(buf.reshape(-1), np.frombuffer(msg, dtype=buf.dtype, count=buf.size))
 
     # -- pickled-object collectives -------------------------------------------

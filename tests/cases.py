@@ -62,3 +62,22 @@ def make_case(name: str):
         init = init.clone()
         init[-1] = 1000.0  # nobody is closest to this centroid -> empty cluster -> origin (Q2)
     return x, init
+
+
+#: sigma of the rbf goldens (oracle/generate_golden.py:METRIC_SIGMA)
+METRIC_SIGMA = 2.5
+
+
+def consumer_inputs():
+    """Inputs of tests/golden/consumers.npz (oracle/generate_golden.py:consumer_inputs, same generator calls)."""
+    import torch
+
+    g = torch.Generator().manual_seed(11)
+    k, d, n = 4, 5, 1500
+    cent = 1.2 * torch.randn(k, d, generator=g, dtype=torch.float64)
+    lab = torch.arange(n) % k
+    x = (cent[lab] + torch.randn(n, d, generator=g, dtype=torch.float64)).to(torch.float32)
+    x[17] = 0.0
+    init = (cent + 0.5 * torch.randn(k, d, generator=g, dtype=torch.float64)).to(torch.float32)
+    xt = (cent[torch.arange(90) % k] + 1.5 * torch.randn(90, d, generator=g, dtype=torch.float64)).to(torch.float32)
+    return {"x": x, "init": init, "y": lab.clone(), "x_test": xt}

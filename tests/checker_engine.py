@@ -69,6 +69,10 @@ class CheckerEngine:
     def cdist(self, x, y, out, quadratic_expansion, sqrt=True):
         out.copy_(orc.cdist(x, y, quadratic_expansion))
 
+    def pairwise(self, x, y, out, metric="euclidean", expand=False, sigma=1.0):
+        if x.shape[0] and y.shape[0]:
+            out.copy_(orc.pairwise(x, y, metric, expand, sigma))
+
     def assign(self, x, c, labels, fv=None, path="auto", row_ws=None):
         if x.shape[0] == 0:
             if fv is not None:
@@ -78,3 +82,76 @@ class CheckerEngine:
         labels.copy_(lab.to(labels.dtype).view(labels.shape))
         if fv is not None:
             fv[0] = float((mins.double() ** 2).sum())
+
+    # -- other consumers (KMedians / KMedoids / kNN): numpy restatement of the device protocol of include/hkmeans.h ----
+    def assign_l1(self, x, c, labels, fv=None):
+        from oracle import consumers_oracle as con
+
+        if x.shape[0] == 0:
+            if fv is not None:
+                fv.zero_()
+            return
+        lab, mins = con.assign_l1(x, c)
+        labels.copy_(lab.to(labels.dtype).view(labels.shape))
+        if fv is not None:
+            fv[0] = float(mins.double().sum())
+
+    def cluster_medians(self, x, labels, k, allsum=None):
+        n, d = x.shape
+        bits = 32 if x.dtype == torch.float32 else 64
+        raw = x.contiguous().numpy().view(np.uint32 if bits == 32 else np.uint64).astype(np.uint64)
+        top = np.uint64(1) << np.uint64(bits - 1)
+        full = np.uint64((1 << bits) - 1)
+        key = np.where(raw & top != 0, raw ^ full, raw ^ top)
+        keep = (x != 0).any(dim=1).numpy()
+        lab = labels.reshape(-1).numpy()
+        prefix = np.zeros((2, k, d), dtype=np.uint64)
+        remaining = np.zeros((2, k, d), dtype=np.int64)
+        counts = None
+        for p in range(bits // 8):
+            shift = np.uint64(bits - 8 * (p + 1))
+            hist = np.zeros((2, k, d, 256), dtype=np.int64)
+            for j in range(k):
+                kj = key[keep & (lab == j)]
+                if kj.shape[0] == 0:
+                    continue
+                digit = ((kj >> shift) & np.uint64(255)).astype(np.int64)
+                for w in range(2):
+                    for f in range(d):
+                        sel = np.ones(kj.shape[0], dtype=bool) if p == 0 else (kj[:, f] >> (shift + np.uint64(8))) == prefix[w, j, f]
+                        hist[w, j, f] = np.bincount(digit[sel, f], minlength=256)
+            ht = torch.from_numpy(hist)
+            if allsum is not None:
+                allsum(ht)
+            hist = ht.numpy()
+            if p == 0:
+                counts = hist[0, :, 0, :].sum(axis=1)
+                remaining[0] = (np.maximum(counts - 1, 0) // 2).reshape(k, 1)
+                remaining[1] = (counts // 2).reshape(k, 1)
+            cum = np.cumsum(hist, axis=3)
+            digit = (cum > remaining[..., None]).argmax(axis=3)
+            before = np.where(digit > 0, np.take_along_axis(cum, np.maximum(digit - 1, 0)[..., None], axis=3)[..., 0], 0)
+            remaining = remaining - before
+            prefix = (prefix << np.uint64(8)) | digit.astype(np.uint64)
+        dec = np.where(prefix & top != 0, prefix ^ top, prefix ^ full)
+        vals = dec.astype(np.uint32 if bits == 32 else np.uint64).view(np.float32 if bits == 32 else np.float64)
+        lo, hi = torch.from_numpy(vals[0].copy()), torch.from_numpy(vals[1].copy())
+        frac = torch.from_numpy(np.where(counts % 2 == 0, 0.5, 0.0)).to(x.dtype).view(k, 1)
+        return lo + (hi - lo) * frac, torch.from_numpy(counts.copy())
+
+    def nearest_rows_l1(self, x, p, row_base):
+        k = p.shape[0]
+        bd = torch.full((k,), float("inf"), dtype=torch.float64)
+        bi = torch.full((k,), torch.iinfo(torch.int64).max, dtype=torch.int64)
+        if x.shape[0]:
+            dist = orc.manhattan_fast(x, p)
+            m = torch.min(dist, dim=0)
+            bd, bi = m.values.double(), m.indices + row_base
+        return bd, bi
+
+    def topk_rows(self, dmat, kk):
+        v, i = torch.topk(dmat, kk, dim=1, largest=False)
+        return v, i
+
+    def knn_vote(self, idx, y):
+        return torch.argmax(y[idx.flatten()].reshape(idx.shape + (y.shape[1],)).sum(dim=1), dim=1)

@@ -148,3 +148,129 @@ def test_kmeanspp_init_host_logic_over_gloo(tmp_path):
     dist = torch.cdist(res["true"].double(), res["centers"].double())
     assert float(dist.min(dim=1).values.max()) < 0.2, dist.min(dim=1).values
     assert res["n_iter"] <= 20
+
+
+def _worker_rings(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    import heat_b200 as hb
+    from cases import METRIC_SIGMA
+    from checker_engine import CheckerEngine
+    from heat_b200 import engine
+    from helpers import load_golden
+
+    comm = hb.init_from_env("gloo")
+    engine.set_engine_factory(lambda dev: CheckerEngine(dev))
+    c = load_golden("cdist")
+    X, Y = torch.from_numpy(c["X_f32"]), torch.from_numpy(c["Y_f32"])
+    res = {}
+    hx, hy = hb.array(X, split=0), hb.array(Y, split=0)
+    res["cdist_ring"] = hb.spatial.cdist(hx, hy, quadratic_expansion=True)          # distance.py:416-473
+    res["cdist_self"] = hb.spatial.cdist(hx, quadratic_expansion=True)              # distance.py:237-361
+    res["rbf_self"] = hb.spatial.rbf(hx, sigma=METRIC_SIGMA, quadratic_expansion=True)
+    res["manhattan_ring"] = hb.spatial.manhattan(hx, hy, expand=True)
+    res["split1"] = hb.spatial.cdist(hb.array(X), hy, quadratic_expansion=True)     # X replicated, Y split: split=1
+    # unbalanced blocks, one of them empty: the counts come from the actual local shapes
+    cut = [0, 50, 50, 96][: world + 1] if world == 3 else [0, 70, 96]
+    ux = hb.array(X[cut[rank]:cut[rank + 1]].clone(), is_split=0)
+    ycut = [0, 0, 25, 40][: world + 1] if world == 3 else [0, 11, 40]
+    uy = hb.array(Y[ycut[rank]:ycut[rank + 1]].clone(), is_split=0)
+    res["unbalanced"] = hb.spatial.cdist(ux, uy, quadratic_expansion=True)
+    meta = {k: (v.split, tuple(v.shape), tuple(v.lshape)) for k, v in res.items()}
+    torch.save({"local": {k: v.larray for k, v in res.items()}, "meta": meta, "cut": cut}, out + f".{rank}")
+    import torch.distributed as dist
+
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distance_rings_over_gloo(tmp_path, world):
+    """Y.split=0 and Y=None layouts of _dist (heat/spatial/distance.py:237-361, 416-473) and the split=1 result of a
+    replicated X: every rank's block equals the rows (or columns) of the reference's one-process matrix."""
+    from cases import METRIC_SIGMA  # noqa: F401
+    from helpers import load_golden
+
+    out = str(tmp_path / "rings.pt")
+    mp.spawn(_worker_rings, args=(world, _free_port(), out), nprocs=world, join=True)
+    g = load_golden("metrics")
+    full = {"cdist_ring": g["cdist_f32_quad"], "cdist_self": g["cdist_self_f32_quad"], "rbf_self": g["rbf_self_f32_quad"],
+            "manhattan_ring": g["manhattan_f32_expand"], "unbalanced": g["cdist_f32_quad"]}
+    from heat_b200.communication import chunk_rows
+
+    for rank in range(world):
+        r = torch.load(out + f".{rank}")
+        off, rows = chunk_rows(96, world, rank)
+        for k, ref in full.items():
+            split, gshape, lshape = r["meta"][k]
+            lo, hi = (r["cut"][rank], r["cut"][rank + 1]) if k == "unbalanced" else (off, off + rows)
+            assert split == 0 and gshape == ref.shape and lshape == (hi - lo, ref.shape[1]), (k, r["meta"][k])
+            np.testing.assert_allclose(r["local"][k].numpy(), ref[lo:hi], atol=1e-5, rtol=0, err_msg=k)
+        split, gshape, lshape = r["meta"]["split1"]
+        yo, yr = chunk_rows(40, world, rank)
+        assert split == 1 and gshape == (96, 40) and lshape == (96, yr)
+        np.testing.assert_allclose(r["local"]["split1"].numpy(), g["cdist_f32_quad"][:, yo:yo + yr], atol=1e-5, rtol=0)
+
+
+def _worker_consumers(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    import heat_b200 as hb
+    from cases import consumer_inputs
+    from checker_engine import CheckerEngine
+    from heat_b200 import engine
+
+    hb.init_from_env("gloo")
+    engine.set_engine_factory(lambda dev: CheckerEngine(dev))
+    inp = consumer_inputs()
+    hx = hb.array(inp["x"], split=0)
+    km = hb.cluster.KMedians(n_clusters=4, init=hb.array(inp["init"]), max_iter=30, tol=1e-4).fit(hx)
+    pred = km.predict(hx)
+    kd = hb.cluster.KMedoids(n_clusters=4, init=hb.array(inp["init"]), max_iter=30).fit(hx)
+    knn = hb.classification.KNeighborsClassifier(n_neighbors=5)
+    knn.fit(hx, hb.array(inp["y"], split=0))
+    cls = knn.predict(hb.array(inp["x_test"], split=0))
+    res = {"kmedians_centers": km.cluster_centers_.larray, "kmedians_labels": km.labels_.resplit(None).larray,
+           "kmedians_n_iter": km.n_iter_, "kmedians_inertia": float(km.inertia_), "kmedians_predict": pred.resplit(None).larray,
+           "kmedians_fv": float(km.functional_value_), "kmedoids_centers": kd.cluster_centers_.larray,
+           "kmedoids_labels": kd.labels_.resplit(None).larray, "kmedoids_n_iter": kd.n_iter_,
+           "knn_classes": cls.resplit(None).larray, "knn_split": cls.split}
+    if rank == 0:
+        torch.save(res, out)
+    import torch.distributed as dist
+
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _check_consumers(res, nm="f32"):
+    from helpers import load_golden
+
+    g = load_golden("consumers")
+    assert res["kmedians_n_iter"] == int(g[f"kmedians_{nm}_n_iter"])
+    assert np.array_equal(res["kmedians_labels"].cpu().numpy(), g[f"kmedians_{nm}_labels"])
+    np.testing.assert_allclose(res["kmedians_centers"].cpu().numpy(), g[f"kmedians_{nm}_centers"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(res["kmedians_inertia"], float(g[f"kmedians_{nm}_inertia"]), atol=1e-10)
+    assert np.array_equal(res["kmedians_predict"].cpu().numpy(), g[f"kmedians_{nm}_predict"])
+    np.testing.assert_allclose(res["kmedians_fv"], float(g[f"kmedians_{nm}_fv"]), rtol=1e-5)
+    assert res["kmedoids_n_iter"] == int(g[f"kmedoids_{nm}_n_iter"])
+    assert np.array_equal(res["kmedoids_labels"].cpu().numpy(), g[f"kmedoids_{nm}_labels"])
+    assert np.array_equal(res["kmedoids_centers"].cpu().numpy(), g[f"kmedoids_{nm}_centers"])
+    assert np.array_equal(res["knn_classes"].cpu().numpy(), g[f"knn_{nm}_classes"])
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_kmedians_kmedoids_knn_host_logic_over_gloo(tmp_path, world):
+    """split=0 shards: the radix-selection protocol (counts summed over the ranks), the cross-rank medoid choice, the
+    distance ring under kNN — results equal to the reference's one-process goldens (tests/golden/consumers.npz)."""
+    out = str(tmp_path / "consumers.pt")
+    mp.spawn(_worker_consumers, args=(world, _free_port(), out), nprocs=world, join=True)
+    res = torch.load(out)
+    assert res["knn_split"] == 0
+    _check_consumers(res)

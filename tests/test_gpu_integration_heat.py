@@ -83,3 +83,26 @@ def test_heat_cdist_runs_on_the_native_path(ht):
         assert d.split == 0 and d.larray.is_cuda
         ref = torch.from_numpy(g[f"D_{dt}_quad"])
         assert torch.allclose(d.larray.cpu(), ref, atol=atol, rtol=0)
+
+
+def test_heat_rbf_and_manhattan_run_on_the_native_path(ht):
+    from cases import METRIC_SIGMA
+    from helpers import load_golden
+    from heat_b200 import engine
+
+    g, c = load_golden("metrics"), load_golden("cdist")
+    eng = engine.get_engine(torch.device("cuda", 0))
+    for dt, atol in (("f32", 1e-5), ("f64", 1e-8)):
+        X, Y = torch.from_numpy(c[f"X_{dt}"]), torch.from_numpy(c[f"Y_{dt}"])
+        hx, hy = ht.array(X, split=0, device="gpu"), ht.array(Y, device="gpu")
+        for fn, name in ((lambda: ht.spatial.rbf(hx, hy, sigma=METRIC_SIGMA, quadratic_expansion=True), f"rbf_{dt}_quad"),
+                         (lambda: ht.spatial.rbf(hx, hy, sigma=METRIC_SIGMA), f"rbf_{dt}_direct"),
+                         (lambda: ht.spatial.manhattan(hx, hy, expand=True), f"manhattan_{dt}_expand"),
+                         (lambda: ht.spatial.manhattan(hx, hy), f"manhattan_{dt}_direct"),
+                         (lambda: ht.spatial.cdist(hx), f"cdist_self_{dt}_direct"),
+                         (lambda: ht.spatial.rbf(hx, sigma=METRIC_SIGMA, quadratic_expansion=True), f"rbf_self_{dt}_quad")):
+            l0 = eng.launch_count()
+            d = fn()
+            assert eng.launch_count() > l0, name
+            assert d.split == 0 and d.larray.is_cuda
+            assert torch.allclose(d.larray.cpu(), torch.from_numpy(g[name]), atol=atol, rtol=0), name

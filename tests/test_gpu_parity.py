@@ -310,6 +310,164 @@ def test_cdist_large_vs_oracle(m, n, f):
     assert float((got - want).abs().max()) <= 1e-5 * float(want.max()), float((got - want).abs().max())
 
 
+@pytest.mark.parametrize("dt", ["f32", "f64"])
+def test_rbf_manhattan_and_self_distances_match_reference(dt):
+    """rbf / manhattan / cdist(X) through hk_pairwise against the unmodified reference's outputs
+    (tests/golden/metrics.npz; heat/spatial/distance.py:67-133, 159-258) at its own tolerances
+    (tests/spatial/test_distances.py:42-188: atol 1e-5 fp32, 1e-8 fp64)."""
+    from cases import METRIC_SIGMA
+
+    g, c = load_golden("metrics"), load_golden("cdist")
+    X, Y = torch.from_numpy(c[f"X_{dt}"]).to(DEV), torch.from_numpy(c[f"Y_{dt}"]).to(DEV)
+    hx, hy = hb.array(X, split=0), hb.array(Y)
+    atol = 1e-5 if dt == "f32" else 1e-8
+    eng = engine.get_engine(DEV)
+    l0 = eng.launch_count()
+
+    def close(d, name, shape):
+        assert d.split == 0 and d.shape == shape and d.dtype == X.dtype and d.larray.is_cuda
+        ref = torch.from_numpy(g[name])
+        assert torch.allclose(d.larray.cpu(), ref, atol=atol, rtol=0), (name, float((d.larray.cpu() - ref).abs().max()))
+
+    for q, tag in ((False, "direct"), (True, "quad")):
+        close(hb.spatial.rbf(hx, hy, sigma=METRIC_SIGMA, quadratic_expansion=q), f"rbf_{dt}_{tag}", (96, 40))
+        close(hb.spatial.cdist(hx, quadratic_expansion=q), f"cdist_self_{dt}_{tag}", (96, 96))
+        close(hb.spatial.rbf(hx, sigma=METRIC_SIGMA, quadratic_expansion=q), f"rbf_self_{dt}_{tag}", (96, 96))
+        close(hb.spatial.manhattan(hx, hy, expand=q), f"manhattan_{dt}_{'expand' if q else 'direct'}", (96, 40))
+    close(hb.spatial.manhattan(hx, expand=True), f"manhattan_self_{dt}", (96, 96))
+    assert eng.launch_count() > l0
+    # the reference's known answers (tests/spatial/test_distances.py:42-75, 120-150): ones vs zeros in 4-D
+    o, z = hb.array(torch.ones(4, 4, device=DEV, dtype=X.dtype), split=0), hb.array(torch.zeros(6, 4, device=DEV, dtype=X.dtype))
+    assert torch.allclose(hb.spatial.rbf(o, z, sigma=1.0, quadratic_expansion=True).larray.cpu().double(),
+                          torch.full((4, 6), float(np.exp(-2.0)), dtype=torch.float64), atol=atol)
+    assert torch.equal(hb.spatial.manhattan(o, z, expand=True).larray.cpu(), torch.full((4, 6), 4.0, dtype=X.dtype))
+
+
+@pytest.mark.parametrize("m,n,f,sigma", [(3000, 512, 64, 8.0), (2100, 4096, 32, 5.0), (1500, 256, 128, 12.0)])
+def test_rbf_large_on_the_tensor_core_kernel_vs_oracle(m, n, f, sigma):
+    """Gaussian epilogue of the tcgen05 kernel (2^(d2 * -log2e / 2 sigma^2) on the 3xTF32 squared distance):
+    |delta| <= exp(-t) * delta(d2) / (2 sigma^2) + 2^-21, far inside the reference's atol 1e-5 on values in (0, 1]."""
+    g = torch.Generator().manual_seed(5)
+    X, Y = torch.randn(m, f, generator=g), torch.randn(n, f, generator=g)
+    got = hb.spatial.rbf(hb.array(X.to(DEV), split=0), hb.array(Y.to(DEV)), sigma=sigma, quadratic_expansion=True)
+    assert engine.get_engine(DEV).last_variant().startswith("cdist_tc"), engine.get_engine(DEV).last_variant()
+    want = orc.pairwise(X.double(), Y.double(), "gaussian", True, sigma)
+    err = float((got.larray.cpu().double() - want).abs().max())
+    assert err <= 2e-6, err
+    assert float(want.max()) > 0.05  # the comparison is not one of zeros
+
+
+def test_pairwise_writes_column_blocks_in_place():
+    """What the rings do with every block (heat_b200/spatial.py:_ring): the tile lands in a column range of the wider
+    local result, row stride kept, neighbouring columns untouched — aligned range (tensor-core kernel) and odd one."""
+    g = torch.Generator().manual_seed(6)
+    X, Y = torch.randn(2048, 64, generator=g), torch.randn(384, 64, generator=g)
+    eng = engine.get_engine(DEV)
+    want = orc.pairwise(X, Y, "euclidean", True)
+    for c0 in (128, 131):
+        out = torch.full((2048, 1024), -7.0, device=DEV)
+        eng.pairwise(X.to(DEV), Y.to(DEV), out[:, c0:c0 + 384], "euclidean", True)
+        assert eng.last_variant().startswith("cdist_tc" if c0 % 4 == 0 else "cdist_simt"), eng.last_variant()
+        o = out.cpu()
+        assert torch.allclose(o[:, c0:c0 + 384], want, atol=2e-5, rtol=0)
+        assert bool((o[:, :c0] == -7.0).all()) and bool((o[:, c0 + 384:] == -7.0).all())
+    # manhattan, large, both dtypes: sequential accumulation vs torch's, f * eps relative
+    for dt, rtol in ((torch.float32, 2e-6), (torch.float64, 1e-13)):
+        A, B = X[:700].to(dt), Y.to(dt)
+        out = torch.empty(700, 384, dtype=dt, device=DEV)
+        eng.pairwise(A.to(DEV), B.to(DEV), out, "manhattan", True)
+        assert torch.allclose(out.cpu(), orc.pairwise(A.double(), B.double(), "manhattan", True).to(dt), rtol=rtol * 64, atol=0)
+
+
+@pytest.mark.parametrize("nm", ["f32", "f64"])
+def test_kmedians_kmedoids_knn_match_reference(nm):
+    """KMedians / KMedoids / KNeighborsClassifier on the device against the unmodified reference's outputs
+    (tests/golden/consumers.npz; heat/cluster/kmedians.py, kmedoids.py, heat/classification/kneighborsclassifier.py)."""
+    from cases import consumer_inputs
+    from test_gloo_multirank import _check_consumers
+
+    dt = torch.float32 if nm == "f32" else torch.float64
+    inp = consumer_inputs()
+    eng = engine.get_engine(DEV)
+    l0 = eng.launch_count()
+    hx = hb.array(inp["x"].to(dt).to(DEV), split=0)
+    init = hb.array(inp["init"].to(dt).to(DEV))
+    km = hb.cluster.KMedians(n_clusters=4, init=init, max_iter=30, tol=1e-4).fit(hx)
+    assert eng.last_variant().startswith(("assign_l1", "select_hist")), eng.last_variant()
+    pred = km.predict(hx)
+    kd = hb.cluster.KMedoids(n_clusters=4, init=init, max_iter=30).fit(hx)
+    knn = hb.classification.KNeighborsClassifier(n_neighbors=5)
+    knn.fit(hx, hb.array(inp["y"].to(DEV), split=0))
+    cls = knn.predict(hb.array(inp["x_test"].to(dt).to(DEV), split=0))
+    assert eng.launch_count() > l0 + 20
+    assert km.cluster_centers_.larray.is_cuda and km.labels_.shape == (1500, 1) and km.labels_.dtype == torch.int64
+    _check_consumers({"kmedians_centers": km.cluster_centers_.larray, "kmedians_labels": km.labels_.larray,
+                      "kmedians_n_iter": km.n_iter_, "kmedians_inertia": float(km.inertia_),
+                      "kmedians_predict": pred.larray, "kmedians_fv": float(km.functional_value_),
+                      "kmedoids_centers": kd.cluster_centers_.larray, "kmedoids_labels": kd.labels_.larray,
+                      "kmedoids_n_iter": kd.n_iter_, "knn_classes": cls.larray}, nm)
+
+
+def test_l1_assignment_medians_topk_semantics():
+    """Device kernels of the N4 consumers against their CPU restatement on inputs with ties, NaN and all-zero rows."""
+    from oracle import consumers_oracle as con
+
+    eng = engine.get_engine(DEV)
+    g = torch.Generator().manual_seed(12)
+    for dt in (torch.float32, torch.float64):
+        # assignment: ties -> first index, NaN distance counts as the minimum (torch.min), narrow label types
+        c = torch.tensor([[0.0, 0.0, 0.0], [2.0, 0.0, 0.0], [2.0, 0.0, 0.0], [0.0, 5.0, 1.0]], dtype=dt)
+        x = torch.tensor([[1.0, 0.0, 0.0], [2.0, 0.1, 0.0], [float("nan"), 0.0, 0.0], [0.0, 4.0, 1.0],
+                          [float("inf"), 0.0, 0.0]], dtype=dt)
+        ref, mins = con.assign_l1(x, c)
+        for ldt in (torch.int64, torch.int32, torch.uint8):
+            lab = torch.empty(x.shape[0], dtype=ldt, device=DEV)
+            eng.assign_l1(x.to(DEV), c.to(DEV), lab)
+            assert lab.cpu().long().tolist() == ref.view(-1).tolist(), (dt, ldt)
+        xr = torch.randn(70001, 9, generator=g, dtype=torch.float64).to(dt)
+        cr = torch.randn(13, 9, generator=g, dtype=torch.float64).to(dt)
+        ref, mins = con.assign_l1(xr, cr)
+        lab = torch.empty(xr.shape[0], dtype=torch.int64, device=DEV)
+        fv = torch.zeros(1, dtype=torch.float64, device=DEV)
+        eng.assign_l1(xr.to(DEV), cr.to(DEV), lab, fv)
+        bad = (lab.cpu() != ref.view(-1)).nonzero().view(-1)
+        d_all = orc.manhattan_fast(xr[bad].double(), cr.double())
+        gap = d_all.gather(1, lab.cpu()[bad].view(-1, 1)).view(-1) - d_all.min(dim=1).values
+        assert bad.numel() <= 3 and bool((gap <= 1e-5 * d_all.min(dim=1).values).all())  # summation-order near-ties only
+        np.testing.assert_allclose(float(fv), float(mins.double().sum()), rtol=1e-6)
+        # medians: exact selection, zero rows dropped, even and odd cluster sizes, an empty cluster
+        xm = torch.randn(200003, 7, generator=g, dtype=torch.float64).to(dt)
+        xm[::1000] = 0.0
+        xm[5::97, 3] = xm[6, 3]  # many equal values in one feature
+        lm = torch.randint(0, 5, (xm.shape[0],), generator=g)
+        lm[lm == 3] = 2  # cluster 3 stays empty
+        med, counts = eng.cluster_medians(xm.to(DEV), lm.to(DEV), 5)
+        rmed, rcounts = con.cluster_medians(xm, lm, 5)
+        assert counts.cpu().tolist() == rcounts.tolist() and int(counts[3]) == 0
+        ok = rcounts > 0
+        np.testing.assert_allclose(med.cpu()[ok].numpy(), rmed[ok].numpy(), rtol=1e-6 if dt == torch.float32 else 1e-14, atol=0)
+        # nearest rows (first index on ties) to k points
+        pts = torch.cat([xm[1234:1235], xm[77:78] + 0.25, torch.zeros(1, 7, dtype=dt)])
+        bd, bi = eng.nearest_rows_l1(xm.to(DEV), pts.to(DEV), 1000)
+        dist = orc.manhattan_fast(xm, pts)
+        want = torch.min(dist, dim=0)
+        assert (bi.cpu() - 1000).tolist() == want.indices.tolist() and int(bi[2]) == 1000  # row 0 is the first zero row
+        np.testing.assert_allclose(bd.cpu().numpy(), want.values.double().numpy(), rtol=1e-6)
+        # top-k per row: ascending, lower index first on ties, NaN never before a number; class vote
+        D = torch.randn(301, 157, generator=g, dtype=torch.float64).to(dt)
+        D[:, 5] = D[:, 9]
+        D[3, :10] = float("nan")
+        D[7] = 1.0
+        vals, idx = eng.topk_rows(D.to(DEV), 6)
+        order = torch.argsort(torch.where(D != D, torch.full_like(D, float("inf")), D), dim=1, stable=True)[:, :6]
+        assert torch.equal(idx.cpu(), order)
+        assert torch.equal(vals.cpu(), D.gather(1, order))
+        Y = torch.rand(157, 4, generator=g, dtype=torch.float64).to(dt)
+        cls = eng.knn_vote(idx, Y.to(DEV))
+        votes = Y[order.flatten()].reshape(301, 6, 4).sum(dim=1)
+        assert (cls.cpu() != votes.argmax(dim=1)).sum() <= 1  # summation order of near-equal votes
+
+
 def test_full_size_properties_config3():
     """BASELINE config 3 shard sizes through size-independent properties: counts sum to N, the k x d sums
     add up to the column sums of X (checksum of checksums), labels in range, repeatable bit-for-bit."""

@@ -1,5 +1,7 @@
 """The oracle (oracle/kmeans_oracle.py) pinned against outputs of the unmodified reference
 (tests/golden/, written by oracle/generate_golden.py) and the reference's own known-answer tests."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -82,6 +84,64 @@ def test_cdist_golden_and_known_answers():
     assert torch.allclose(orc.cdist(A, B, True), torch.cdist(A, B), atol=1e-5)
     with pytest.raises(NotImplementedError):
         orc.cdist(torch.zeros(2, 2, 2), torch.zeros(2, 2))
+
+
+def test_metric_goldens_rbf_manhattan_and_self_distances():
+    """rbf / manhattan / cdist(X) restated by the oracle are bit-identical to the unmodified reference
+    (tests/golden/metrics.npz from oracle/generate_golden.py --metrics; heat/spatial/distance.py:67-133, 237-258), and the
+    reference's own rings at np=3 reproduce the rows of its one-process result (metrics_rings.json)."""
+    import json
+
+    from cases import METRIC_SIGMA
+
+    g = load_golden("metrics")
+    c = load_golden("cdist")
+    for nm in ("f32", "f64"):
+        X, Y = torch.from_numpy(c[f"X_{nm}"]), torch.from_numpy(c[f"Y_{nm}"])
+        for q, tag in ((False, "direct"), (True, "quad")):
+            assert torch.equal(orc.pairwise(X, Y, "gaussian", q, METRIC_SIGMA), torch.from_numpy(g[f"rbf_{nm}_{tag}"]))
+            assert torch.equal(orc.pairwise(X, Y, "euclidean", q), torch.from_numpy(g[f"cdist_{nm}_{tag}"]))
+            assert torch.equal(orc.pairwise(X, X, "euclidean", q), torch.from_numpy(g[f"cdist_self_{nm}_{tag}"]))
+            assert torch.equal(orc.pairwise(X, X, "gaussian", q, METRIC_SIGMA),
+                               torch.from_numpy(g[f"rbf_self_{nm}_{tag}"]))
+        assert torch.equal(orc.pairwise(X, Y, "manhattan", False), torch.from_numpy(g[f"manhattan_{nm}_direct"]))
+        assert torch.equal(orc.pairwise(X, Y, "manhattan", True), torch.from_numpy(g[f"manhattan_{nm}_expand"]))
+        assert torch.equal(orc.pairwise(X, X, "manhattan", True), torch.from_numpy(g[f"manhattan_self_{nm}"]))
+    # known answers of the reference's tests (tests/spatial/test_distances.py:42-75): ones vs zeros in 4-D
+    assert torch.allclose(orc.pairwise(torch.ones(4, 4), torch.zeros(6, 4), "gaussian", True, 1.0),
+                          torch.full((4, 6), float(np.exp(-2.0))))
+    assert torch.equal(orc.pairwise(torch.ones(4, 4), torch.zeros(6, 4), "manhattan", True), torch.full((4, 6), 4.0))
+    with open(os.path.join(os.path.dirname(__file__), "golden", "metrics_rings.json")) as f:
+        rings = json.load(f)
+    assert rings["np"] == 3 and max(rings["max_abs_diff_vs_np1"].values()) < 1e-5
+
+
+def test_consumer_goldens_kmedians_kmedoids_knn():
+    """The restated KMedians / KMedoids / kNN (oracle/consumers_oracle.py) against the unmodified reference
+    (tests/golden/consumers.npz): labels, iteration counts and kNN classes identical, centroids to rounding."""
+    from cases import consumer_inputs
+    from oracle import consumers_oracle as con
+
+    g = load_golden("consumers")
+    inp = consumer_inputs()
+    for key in ("x", "init", "x_test"):
+        assert np.array_equal(inp[key].numpy(), g[key]), key
+    for dt, nm, tol in ((torch.float32, "f32", 1e-6), (torch.float64, "f64", 1e-13)):
+        x, init = inp["x"].to(dt), inp["init"].to(dt)
+        c, lab, n_iter, inertia = con.kmedians_fit(x, init, 30, 1e-4)
+        assert n_iter == int(g[f"kmedians_{nm}_n_iter"])
+        assert np.array_equal(lab.numpy(), g[f"kmedians_{nm}_labels"])
+        np.testing.assert_allclose(c.numpy(), g[f"kmedians_{nm}_centers"], rtol=tol, atol=tol)
+        np.testing.assert_allclose(float(inertia), float(g[f"kmedians_{nm}_inertia"]), atol=1e-10)
+        pl, mins = con.assign_l1(x, c)
+        assert np.array_equal(pl.numpy(), g[f"kmedians_{nm}_predict"])
+        np.testing.assert_allclose(float(mins.double().sum()), float(g[f"kmedians_{nm}_fv"]), rtol=1e-5)
+        c, lab, n_iter = con.kmedoids_fit(x, init, 30)
+        assert n_iter == int(g[f"kmedoids_{nm}_n_iter"])
+        assert np.array_equal(lab.numpy(), g[f"kmedoids_{nm}_labels"])
+        assert np.array_equal(c.numpy(), g[f"kmedoids_{nm}_centers"])  # medoids are data rows: exact
+        cls = con.knn_predict(x, inp["y"], inp["x_test"].to(dt), 5)
+        assert np.array_equal(cls.numpy(), g[f"knn_{nm}_classes"])
 
 
 def test_argmin_first_index_and_quirks():
