@@ -105,4 +105,11 @@ def test_heat_rbf_and_manhattan_run_on_the_native_path(ht):
             d = fn()
             assert eng.launch_count() > l0, name
             assert d.split == 0 and d.larray.is_cuda
-            assert torch.allclose(d.larray.cpu(), torch.from_numpy(g[name]), atol=atol, rtol=0), name
+            got, ref = d.larray.cpu(), torch.from_numpy(g[name])
+            if name.startswith("cdist_self"):
+                # self distances: the diagonal is sqrt(rounding of |x|^2 + |x|^2 - 2 x.x) on both sides (torch.cdist also expands above 25 rows),
+                # not 0 — compare squared distances at the rounding of |x|^2 + |y|^2
+                got, ref, tol = got * got, ref * ref, (1e-4 if dt == "f32" else 1e-12)
+            else:
+                tol = atol
+            assert torch.allclose(got, ref, atol=tol, rtol=0), (name, float((got - ref).abs().max()))
