@@ -104,6 +104,130 @@ __global__ void __launch_bounds__(NT) assign_l1_kernel(const T* __restrict__ X, 
     }
 }
 
+// Tiled variant of the two L1 passes: a block stages 256 rows (coalesced loads; rows padded to d+1 words so that
+// thread == row reads them without bank conflicts) and the k points in shared memory.
+//   MODE 0: labels + per-block sum of the row minima (assignment)
+//   MODE 1: per point the closest row, first index on ties -> one candidate per block and point
+template <typename T, int MODE>
+__global__ void __launch_bounds__(NT) l1_tiled_kernel(const T* __restrict__ X, int64_t n, int d, int64_t ldx,
+                                                      const T* __restrict__ C, int k, void* labels, int label_kind,
+                                                      double* __restrict__ fv_part, int64_t row_base,
+                                                      double* __restrict__ part_d, int64_t* __restrict__ part_i) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int pd = d + 1;
+    T* cs = reinterpret_cast<T*>(sm_raw);  // [k][d]
+    T* xs = cs + (size_t)k * d;            // [NT][d + 1]
+    size_t off = ((size_t)k * d + (size_t)NT * pd) * sizeof(T);
+    off = (off + 15) & ~(size_t)15;
+    double* wd = reinterpret_cast<double*>(sm_raw + off);  // MODE 1: [warps][k] running best of every warp
+    int64_t* wi = reinterpret_cast<int64_t*>(wd + (size_t)(NT / 32) * k);
+    __shared__ double red[NT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < k * d; i += NT) cs[i] = C[i];
+    if (MODE == 1)
+        for (int i = tid; i < (NT / 32) * k; i += NT) {
+            wd[i] = INFINITY;
+            wi[i] = INT64_MAX;
+        }
+    __syncthreads();
+    const int64_t ntiles = (n + NT - 1) / NT;
+    const int step_r = NT / d, step_f = NT - step_r * d;
+    double fv = 0.0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t r0 = t * NT;
+        const int rows = (int)((n - r0) < NT ? (n - r0) : NT);
+        {
+            int r = tid / d, f = tid - r * d;
+            for (int e = tid; e < rows * d; e += NT) {
+                xs[r * pd + f] = X[(r0 + r) * ldx + f];
+                r += step_r;
+                f += step_f;
+                if (f >= d) {
+                    f -= d;
+                    ++r;
+                }
+            }
+        }
+        __syncthreads();
+        const bool act = tid < rows;
+        const T* xr = xs + (size_t)tid * pd;
+        if (MODE == 0) {
+            if (act) {
+                T best = T(0);
+                int bj = 0;
+                for (int j = 0; j < k; ++j) {
+                    const T* c = cs + (size_t)j * d;
+                    T s = T(0);
+                    for (int f = 0; f < d; ++f) s += fabs(xr[f] - c[f]);
+                    if (j == 0 || s < best || (s != s && best == best)) {
+                        best = s;
+                        bj = j;
+                    }
+                }
+                store_label(labels, label_kind, r0 + tid, bj);
+                fv += (double)best;
+            }
+        } else {
+            for (int j = 0; j < k; ++j) {
+                double bd = INFINITY;
+                int64_t bi = INT64_MAX;
+                if (act) {
+                    const T* c = cs + (size_t)j * d;
+                    T s = T(0);
+                    for (int f = 0; f < d; ++f) s += fabs(xr[f] - c[f]);
+                    bd = (double)s;
+                    bi = row_base + r0 + tid;
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                    const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (better<double>(od, oi, bd, bi)) {
+                        bd = od;
+                        bi = oi;
+                    }
+                }
+                if (lane == 0 && better<double>(bd, bi, wd[warp * k + j], wi[warp * k + j])) {
+                    wd[warp * k + j] = bd;
+                    wi[warp * k + j] = bi;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (MODE == 0) {
+        if (fv_part != nullptr) {
+            for (int o = 16; o > 0; o >>= 1) fv += __shfl_xor_sync(0xffffffffu, fv, o);
+            if (lane == 0) red[warp] = fv;
+            __syncthreads();
+            if (tid == 0) {
+                double s = 0.0;
+                for (int w = 0; w < NT / 32; ++w) s += red[w];
+                fv_part[blockIdx.x] = s;
+            }
+        }
+    } else {
+        for (int j = tid; j < k; j += NT) {
+            double bd = wd[j];
+            int64_t bi = wi[j];
+            for (int w = 1; w < NT / 32; ++w)
+                if (better<double>(wd[w * k + j], wi[w * k + j], bd, bi)) {
+                    bd = wd[w * k + j];
+                    bi = wi[w * k + j];
+                }
+            part_d[(size_t)blockIdx.x * k + j] = bd;
+            part_i[(size_t)blockIdx.x * k + j] = bi;
+        }
+    }
+}
+
+template <typename T>
+size_t l1_tiled_smem(int d, int k, int mode) {
+    size_t b = ((size_t)k * d + (size_t)NT * (d + 1)) * sizeof(T);
+    b = (b + 15) & ~(size_t)15;
+    if (mode == 1) b += (size_t)(NT / 32) * k * (sizeof(double) + sizeof(int64_t));
+    return b;
+}
+
 __global__ void sum_blocks_kernel(const double* __restrict__ part, int nb, double* __restrict__ out) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         double s = 0.0;
@@ -145,6 +269,7 @@ __global__ void __launch_bounds__(NT) select_hist_kernel(const T* __restrict__ X
         const unsigned digit = (unsigned)((key >> shift) & 255u);
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
+            if (pass == 0 && w == 1) break;  // both targets share the first digit's counts: the caller copies hist[0] to hist[1]
             const size_t base = ((size_t)w * k + (size_t)j) * d + f;
             if (pass == 0 || lead == prefix[base]) atomicAdd(&hist[base * 256 + digit], 1ULL);
         }
@@ -359,7 +484,13 @@ int blocks_for(const Handle* h, int64_t work_items) {
 template <typename T>
 int run_assign_l1(Handle* h, const T* X, int64_t n, int d, int64_t ldx, const T* C, int k, void* labels, int label_kind,
                   double* fv, cudaStream_t st) {
-    const int grid = blocks_for(h, n);
+    const size_t tsz = l1_tiled_smem<T>(d, k, 0);
+    const bool tiled = tsz <= 160 * 1024;
+    int grid = blocks_for(h, n);
+    if (tiled) {
+        const int64_t ntiles = (n + NT - 1) / NT;
+        grid = (int)(ntiles < (int64_t)h->num_sms * 4 ? ntiles : (int64_t)h->num_sms * 4);
+    }
     double* part = nullptr;
     if (fv != nullptr) {
         int rc = ensure_part(h, (size_t)grid * sizeof(double) + 64);
@@ -368,7 +499,10 @@ int run_assign_l1(Handle* h, const T* X, int64_t n, int d, int64_t ldx, const T*
     }
     const size_t csz = (size_t)k * d * sizeof(T);
     prof_begin(h, st);
-    if (csz <= 96 * 1024) {
+    if (tiled) {
+        HK_CUDA(cudaFuncSetAttribute(l1_tiled_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsz));
+        l1_tiled_kernel<T, 0><<<grid, NT, tsz, st>>>(X, n, d, ldx, C, k, labels, label_kind, part, 0, nullptr, nullptr);
+    } else if (csz <= 96 * 1024) {
         HK_CUDA(cudaFuncSetAttribute(assign_l1_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csz));
         assign_l1_kernel<T, true><<<grid, NT, csz, st>>>(X, n, d, ldx, C, k, labels, label_kind, part);
     } else {
@@ -442,13 +576,27 @@ int launch_select_value(Handle* h, const uint64_t* prefix, const double* frac, i
 
 int launch_nearest_rows_l1(Handle* h, const void* X, int64_t n, int d, int64_t ldx, int dtype, const void* P, int k,
                            int64_t row_base, double* out_d, int64_t* out_i, cudaStream_t st) {
-    const int grid = blocks_for(h, n);
+    const size_t tsz = dtype == HK_F64 ? l1_tiled_smem<double>(d, k, 1) : l1_tiled_smem<float>(d, k, 1);
+    const bool tiled = tsz <= 160 * 1024;
+    int grid = blocks_for(h, n);
+    if (tiled) {
+        const int64_t ntiles = (n + NT - 1) / NT;
+        grid = (int)(ntiles < (int64_t)h->num_sms * 4 ? ntiles : (int64_t)h->num_sms * 4);
+    }
     const size_t need = (size_t)grid * k * (sizeof(double) + sizeof(int64_t)) + 64;
     int rc = ensure_part(h, need);
     if (rc) return rc;
     double* pd = reinterpret_cast<double*>(h->part);
     int64_t* pi = reinterpret_cast<int64_t*>(pd + (size_t)grid * k);
-    if (dtype == HK_F64)
+    if (tiled && dtype == HK_F64) {
+        HK_CUDA(cudaFuncSetAttribute(l1_tiled_kernel<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsz));
+        l1_tiled_kernel<double, 1><<<grid, NT, tsz, st>>>((const double*)X, n, d, ldx, (const double*)P, k, nullptr, 0,
+                                                          nullptr, row_base, pd, pi);
+    } else if (tiled) {
+        HK_CUDA(cudaFuncSetAttribute(l1_tiled_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsz));
+        l1_tiled_kernel<float, 1><<<grid, NT, tsz, st>>>((const float*)X, n, d, ldx, (const float*)P, k, nullptr, 0, nullptr,
+                                                         row_base, pd, pi);
+    } else if (dtype == HK_F64)
         nearest_rows_l1_kernel<double><<<grid, NT, 0, st>>>((const double*)X, n, d, ldx, (const double*)P, k, row_base, pd, pi);
     else
         nearest_rows_l1_kernel<float><<<grid, NT, 0, st>>>((const float*)X, n, d, ldx, (const float*)P, k, row_base, pd, pi);

@@ -218,6 +218,8 @@ class CudaEngine:
             hist.zero_()
             check(self.lib.hk_select_hist(self.h, _ptr(x), n, d, ldx, dt, _ptr(lab), _ptr(keep), k, _ptr(prefix), p,
                                           _ptr(hist), st), "hk_select_hist")
+            if p == 0:
+                hist[1].copy_(hist[0])  # pass 0 counts once for both targets
             if allsum is not None:
                 allsum(hist)
             if p == 0:

@@ -163,7 +163,8 @@ int hk_assign_l1(hk_handle_t h, const void* X, int64_t n_local, int d, int64_t l
  * Protocol (every array on the device; w = 0 lower middle, 1 upper middle):
  *   hk_row_keep    keep[i] = row i is not entirely zero
  *   for pass in 0 .. hk_select_passes(dtype)-1:
- *       zero hist[2][k][d][256] (int64); hk_select_hist adds this shard's counts; sum hist over the ranks;
+ *       zero hist[2][k][d][256] (int64); hk_select_hist adds this shard's counts (pass 0 fills hist[0] only: copy it
+ *       to hist[1]); sum hist over the ranks;
  *       (after pass 0 the caller derives the cluster sizes from hist and sets remaining[2][k][d] to the wanted ranks)
  *       hk_select_step   picks the digit holding rank remaining[w][j][f], appends it to prefix[w][j][f] (uint64)
  *   hk_select_value   medians[j][f] = lo + (hi - lo) * frac[j]   (frac = 0.5 for even cluster sizes, else 0) */

@@ -133,7 +133,10 @@ def test_distance_rings_two_gpus(tmp_path):
         off, rows = chunk_rows(96, 2, rank)
         for k, ref in full.items():
             assert r["meta"][k] == (0, ref.shape)
-            np.testing.assert_allclose(r["local"][k].numpy(), ref[off:off + rows], atol=1e-5, rtol=0, err_msg=k)
+            got, want, tol = r["local"][k].numpy(), ref[off:off + rows], 1e-5
+            if k == "cdist_self":  # the diagonal is sqrt(rounding) on both sides: compare squared distances
+                got, want, tol = got * got, want * want, 1e-4
+            np.testing.assert_allclose(got, want, atol=tol, rtol=0, err_msg=k)
         assert r["variant"].startswith("cdist_tc"), r["variant"]
         o2, r2 = chunk_rows(4096, 2, rank)
         assert float((r["big"].double() - want_big[o2:o2 + r2]).abs().max()) <= 1e-5 * float(want_big.max())

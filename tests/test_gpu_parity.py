@@ -439,6 +439,15 @@ def test_l1_assignment_medians_topk_semantics():
         gap = d_all.gather(1, lab.cpu()[bad].view(-1, 1)).view(-1) - d_all.min(dim=1).values
         assert bad.numel() <= 3 and bool((gap <= 1e-5 * d_all.min(dim=1).values).all())  # summation-order near-ties only
         np.testing.assert_allclose(float(fv), float(mins.double().sum()), rtol=1e-6)
+        # wide rows: float64 at d = 100 does not fit the shared-memory tile and takes the row-per-thread kernels
+        xw = torch.randn(5001, 100, generator=g, dtype=torch.float64).to(dt)
+        cw = torch.randn(6, 100, generator=g, dtype=torch.float64).to(dt)
+        ref, _ = con.assign_l1(xw, cw)
+        lab = torch.empty(xw.shape[0], dtype=torch.int64, device=DEV)
+        eng.assign_l1(xw.to(DEV), cw.to(DEV), lab)
+        assert int((lab.cpu() != ref.view(-1)).sum()) == 0
+        bd, bi = eng.nearest_rows_l1(xw.to(DEV), cw.to(DEV), 0)
+        assert bi.cpu().tolist() == torch.min(orc.manhattan_fast(xw, cw), dim=0).indices.tolist()
         # medians: exact selection, zero rows dropped, even and odd cluster sizes, an empty cluster
         xm = torch.randn(200003, 7, generator=g, dtype=torch.float64).to(dt)
         xm[::1000] = 0.0
