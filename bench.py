@@ -598,6 +598,15 @@ def run_extras(args):
             out[key] = ent
         except Exception as ex:  # reported, never hidden
             out[key] = {"error": str(ex)[:200]}
+    # the "next" rows: rbf / manhattan tiles, KMedians / KMedoids passes, kNN — device times in ms
+    try:
+        res = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools",
+                                                           "consumers_bench.py")],
+                             capture_output=True, text=True, timeout=240, cwd=os.path.dirname(os.path.abspath(__file__)))
+        js = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+        out["next_rows_ms"] = json.loads(js[-1]) if js else {"error": (res.stderr or res.stdout)[-200:]}
+    except Exception as ex:
+        out["next_rows_ms"] = {"error": str(ex)[:200]}
     return out
 
 
