@@ -73,6 +73,10 @@ SIGNATURES = {
     ),
     "hk_select_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "hk_select_value": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hk_kmex_update": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p, c_void_p],
+    ),
     "hk_nearest_rows_l1": (
         c_int,
         [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p],

@@ -537,3 +537,204 @@ class KMedoids(_L1Cluster):
             raise ValueError("max_iter must be at least 1")
         self._labels = matching
         return self
+
+
+# ---- batch-parallel clusterers (heat/cluster/batchparallelclustering.py) ----------------------------------------------
+def _plus_plus_rows(xl: torch.Tensor, n_clusters: int, p: int, gen: Optional[torch.Generator], eng) -> torch.Tensor:
+    """k-means++ / k-medians++ seeding of one shard (reference: _initialize_plus_plus, batchparallelclustering.py:23-49):
+    first row uniform, every further row drawn with probability proportional to its distance to the nearest chosen row.
+    The N-sized distance work runs on the device (``hk_pairwise`` against the newest row, running minimum); the draws use
+    the same CPU generator calls as the reference, so a seeded run picks the same rows."""
+    n = xl.shape[0]
+    max_samples = 2**24 - 1  # torch.multinomial's category limit, as in the reference
+    if n > max_samples:
+        sub = torch.randint(0, n, (max_samples,), generator=gen)
+        xl = xl[sub.to(xl.device)].contiguous()
+        n = max_samples
+    idxs = torch.zeros(n_clusters, dtype=torch.long)
+    idxs[0] = torch.randint(0, n, (1,), generator=gen)
+    dmin = torch.full((n,), float("inf"), dtype=xl.dtype, device=xl.device)
+    col = torch.empty((n, 1), dtype=xl.dtype, device=xl.device)
+    for i in range(1, n_clusters):
+        eng.pairwise(xl, xl[idxs[i - 1]:idxs[i - 1] + 1].contiguous(), col, "manhattan" if p == 1 else "euclidean", False)
+        torch.minimum(dmin, col.view(-1), out=dmin)
+        idxs[i] = torch.multinomial(dmin.cpu(), 1, generator=gen)
+    return xl[idxs.to(xl.device)].clone()
+
+
+def _kmex(xl: torch.Tensor, p: int, n_clusters: int, init, max_iter: int, tol: float, random_state: Optional[int], eng):
+    """Single-shard k-means (p = 2) / k-medians (p = 1) of the batch-parallel clusterers (reference: _kmex,
+    batchparallelclustering.py:52-86): empty clusters keep their centre, convergence = allclose(new, old, atol=tol).
+    One device pass per iteration (Lloyd pass, or L1 assignment + radix-selected lower medians) and one tiny update kernel;
+    the flag is read once per iteration like the reference's ``torch.allclose``."""
+    gen = torch.Generator().manual_seed(int(random_state)) if random_state is not None else None
+    if isinstance(init, torch.Tensor):
+        if tuple(init.shape) != (n_clusters, xl.shape[1]):
+            raise ValueError("if a torch tensor, init must have shape (n_clusters, n_features).")
+        centers = init.to(device=xl.device, dtype=xl.dtype).contiguous().clone()
+    elif init == "++":
+        centers = _plus_plus_rows(xl, n_clusters, p, gen, eng)
+    elif init == "random":
+        centers = xl[torch.randint(0, xl.shape[0], (n_clusters,), generator=gen).to(xl.device)].clone()
+    else:
+        raise ValueError("init must be a torch tensor with initial centers, string '++', or 'random'.")
+    k, d = centers.shape
+    flag = torch.zeros(1, dtype=torch.int32, device=xl.device)
+    part = torch.empty(k * (d + 1), dtype=torch.float64, device=xl.device)
+    labels = torch.empty(xl.shape[0], dtype=torch.int64, device=xl.device)
+    it = 0
+    for it in range(1, int(max_iter) + 1):
+        if p == 1:
+            eng.assign_l1(xl, centers, labels)
+            med, counts = eng.cluster_medians(xl, labels, k, None, drop_zero_rows=False, lower=True)
+            eng.kmex_update(centers, flag, tol, medians=med, counts=counts)
+        else:
+            eng.lloyd_accumulate(xl, centers, part)
+            eng.kmex_update(centers, flag, tol, partials=part)
+        if int(flag.item()):
+            break
+    return centers, it
+
+
+class _BatchParallelKCluster(BaseEstimator):
+    """Reference: _BatchParallelKCluster (batchparallelclustering.py:98-331): every rank clusters its own shard, the
+    per-rank centres are merged by clustering them again (hierarchically, ``n_procs_to_merge`` at a time)."""
+
+    _PARAMS = ("init", "max_iter", "n_clusters", "n_procs_to_merge", "random_state", "tol")
+
+    def __init__(self, p: int, n_clusters: int, init: str, max_iter: int, tol: float, random_state, n_procs_to_merge):
+        if not isinstance(n_clusters, int):
+            raise TypeError(f"n_clusters must be int, but was {type(n_clusters)}")
+        if n_clusters <= 0:
+            raise ValueError(f"n_clusters must be positive, but was {n_clusters}")
+        if not isinstance(max_iter, int):
+            raise TypeError(f"max_iter must be int, but was {type(max_iter)}")
+        if max_iter <= 0:
+            raise ValueError(f"max_iter must be positive, but was {max_iter}")
+        if not isinstance(tol, float):
+            raise TypeError(f"tol must be float, but was {type(tol)}")
+        if tol <= 0:
+            raise ValueError(f"tol must be positive, but was {tol}")
+        if not isinstance(random_state, int) and random_state is not None:
+            raise TypeError(f"random_state must be int or None, but was {type(random_state)}")
+        if not isinstance(n_procs_to_merge, int) and n_procs_to_merge is not None:
+            raise TypeError(f"procs_to_merge must be int or None, but was {type(n_procs_to_merge)}")
+        if n_procs_to_merge is not None and n_procs_to_merge <= 1:
+            raise ValueError(f"If an integer, procs_to_merge must be > 1, but was {n_procs_to_merge}.")
+        self.n_clusters = n_clusters
+        self._init = init
+        self.max_iter = max_iter
+        self.tol = tol
+        self.random_state = random_state
+        self.n_procs_to_merge = n_procs_to_merge
+        self._p = p
+        self._cluster_centers = None
+        self._n_iter = None
+        self._functional_value = None
+
+    @property
+    def cluster_centers_(self) -> DNDarray:
+        return self._cluster_centers
+
+    @property
+    def n_iter_(self) -> int:
+        return self._n_iter
+
+    @property
+    def functional_value_(self):
+        return self._functional_value
+
+    @staticmethod
+    def _check_input(x):
+        if not isinstance(x, DNDarray):
+            raise TypeError(f"input needs to be a ht.DNDarray, but was {type(x)}")
+        if not x.ndim == 2:
+            raise ValueError(f"input needs to be 2D, but was {x.ndim}D")
+        if x.split != 0:
+            raise ValueError(f"input needs to be split along the sample axis, but was split along {x.split}")
+
+    def fit(self, x: DNDarray):
+        """Reference: batchparallelclustering.py:171-262."""
+        self._check_input(x)
+        xl, _ = _device_operands(x)
+        eng = _engine.get_engine(xl.device)
+        comm = x.comm
+        size, rank = (comm.size, comm.rank) if comm.is_distributed() else (1, 0)
+        seed = None if self.random_state is None else self.random_state + rank
+        centers, n_iters = _kmex(xl, self._p, self.n_clusters, self._init, self.max_iter, self.tol, seed, eng)
+        merge = self.n_procs_to_merge if self.n_procs_to_merge is not None else size
+        current = list(range(size))
+        k, d = centers.shape
+        while len(current) > 1:
+            everyone = comm.Allgatherv_rows(centers).view(size, k, d)  # collective at every level, on all ranks
+            if rank in current:
+                pos = current.index(rank)
+                if pos % merge == 0:  # root of its group: cluster the group's centres
+                    members = current[pos:pos + merge]
+                    if len(members) > 1:
+                        gathered = everyone[members].reshape(-1, d).contiguous()
+                        centers, extra = _kmex(gathered, self._p, self.n_clusters, self._init, self.max_iter, self.tol, seed, eng)
+                        n_iters += extra
+            current = [current[i] for i in range(len(current)) if i % merge == 0]
+        if size > 1:
+            centers = comm.Allgatherv_rows(centers).view(size, k, d)[0].clone()  # Bcast from rank 0
+        self._cluster_centers = DNDarray(centers, (k, d), centers.dtype, None, xl.device, comm, True)
+        self._n_iter = n_iters
+        return self
+
+    def predict(self, x: DNDarray) -> DNDarray:
+        """Reference: batchparallelclustering.py:264-331 — int32 labels, functional value as a Python float."""
+        self._check_input(x)
+        if self._cluster_centers is None:
+            raise RuntimeError("fit needs to be called before predict")
+        if x.shape[1] != self._cluster_centers.shape[1]:
+            raise ValueError(f"input needs to have {self._cluster_centers.shape[1]} features, but has {x.shape[1]}")
+        xl, _ = _device_operands(x)
+        eng = _engine.get_engine(xl.device)
+        c = self._cluster_centers.larray.to(device=xl.device, dtype=xl.dtype).contiguous()
+        labels = torch.empty((xl.shape[0], 1), dtype=torch.int32, device=xl.device)
+        fv = torch.zeros(1, dtype=torch.float64, device=xl.device)
+        if self._p == 1:
+            eng.assign_l1(xl, c, labels, fv)
+        else:
+            eng.assign(xl, c, labels, fv)
+        if x.comm.is_distributed():
+            x.comm.Allreduce(IN_PLACE, fv)
+        self._functional_value = float(fv.item())
+        return DNDarray(labels, (x.shape[0], 1), torch.int32, x.split, xl.device, x.comm, x.balanced)
+
+
+class BatchParallelKMeans(_BatchParallelKCluster):
+    """Drop-in for ``heat.cluster.BatchParallelKMeans`` (batchparallelclustering.py:339-393)."""
+
+    def __init__(self, n_clusters: int = 8, init: str = "k-means++", max_iter: int = 300, tol: float = 1e-4,
+                 random_state: Optional[int] = None, n_procs_to_merge: Optional[int] = None):
+        if not isinstance(init, str):
+            raise TypeError(f"init must be str, but was {type(init)}")
+        if init == "k-means++":
+            _init = "++"
+        elif init == "random":
+            raise NotImplementedError("random initialization for batch parallel k-means is currently not supported due to "
+                                      "instable behaviour of the algorithm. Use init='k-means++' instead.")
+        else:
+            raise ValueError(f"init must be 'k-means++' or 'random', but was {init}")
+        super().__init__(2, n_clusters, _init, max_iter, tol, random_state, n_procs_to_merge)
+        self.init = init
+
+
+class BatchParallelKMedians(_BatchParallelKCluster):
+    """Drop-in for ``heat.cluster.BatchParallelKMedians`` (batchparallelclustering.py:396-450)."""
+
+    def __init__(self, n_clusters: int = 8, init: str = "k-medians++", max_iter: int = 300, tol: float = 1e-4,
+                 random_state: Optional[int] = None, n_procs_to_merge: Optional[int] = None):
+        if not isinstance(init, str):
+            raise TypeError(f"init must be str, but was {type(init)}")
+        if init == "k-medians++":
+            _init = "++"
+        elif init == "random":
+            raise NotImplementedError("random initialization for batch parallel k-medians is currently not supported due to "
+                                      "instable behaviour of the algorithm. Use init='k-medians++' instead.")
+        else:
+            raise ValueError(f"init must be 'k-medians++' or 'random', but was {init}")
+        super().__init__(1, n_clusters, _init, max_iter, tol, random_state, n_procs_to_merge)
+        self.init = init

@@ -468,6 +468,18 @@ int hk_select_value(hk_handle_t hh, const void* prefix_u64, const double* frac, 
     return launch_select_value(h, reinterpret_cast<const uint64_t*>(prefix_u64), frac, k, d, dtype, medians, st);
 }
 
+int hk_kmex_update(hk_handle_t hh, const double* partials, const void* medians, const void* counts_i64, void* C, int k,
+                   int d, int dtype, double atol, double rtol, void* flag_i32, void* stream) {
+    HK_ARG(dtype == HK_F32 || dtype == HK_F64, "hk_kmex_update: bad dtype");
+    HK_ARG(k >= 1 && d >= 1, "hk_kmex_update: bad shape");
+    HK_HANDLE("hk_kmex_update");
+    HK_ARG(C && flag_i32, "hk_kmex_update: null pointer");
+    HK_ARG((partials != nullptr) != (medians != nullptr && counts_i64 != nullptr),
+           "hk_kmex_update: pass either the partial sums or medians + counts");
+    return launch_kmex_update(h, partials, medians, reinterpret_cast<const int64_t*>(counts_i64), C, k, d, dtype, atol, rtol,
+                              reinterpret_cast<int*>(flag_i32), st);
+}
+
 int hk_nearest_rows_l1(hk_handle_t hh, const void* X, int64_t n_local, int d, int64_t ldx, int dtype, const void* P,
                        int k, int64_t row_base, double* best_dist, void* best_index_i64, void* stream) {
     HK_ARG(dtype == HK_F32 || dtype == HK_F64, "hk_nearest_rows_l1: bad dtype");

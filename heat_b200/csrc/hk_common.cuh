@@ -176,6 +176,8 @@ int launch_select_step(Handle* h, const unsigned long long* hist, int64_t* remai
                        cudaStream_t st);
 int launch_select_value(Handle* h, const uint64_t* prefix, const double* frac, int k, int d, int dtype, void* out,
                         cudaStream_t st);
+int launch_kmex_update(Handle* h, const double* partials, const void* medians, const int64_t* counts, void* C, int k,
+                       int d, int dtype, double atol, double rtol, int* flag, cudaStream_t st);
 int launch_nearest_rows_l1(Handle* h, const void* X, int64_t n, int d, int64_t ldx, int dtype, const void* P, int k,
                            int64_t row_base, double* out_d, int64_t* out_i, cudaStream_t st);
 int launch_topk_rows(Handle* h, const void* D, int64_t m, int64_t n, int64_t ldd, int dtype, int kk, void* vals,

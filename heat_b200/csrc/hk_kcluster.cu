@@ -473,6 +473,36 @@ __global__ void __launch_bounds__(NT) knn_vote_kernel(const int64_t* __restrict_
     classes[i] = bc;
 }
 
+// Centre update of the batch-parallel clusterers' single-process loop (_kmex, heat/cluster/batchparallelclustering.py:67-84):
+// a cluster with rows takes their mean (from the fp64 partial sums | counts of a Lloyd pass) or their median (precomputed),
+// an empty cluster keeps its centre; flag[0] = torch.allclose(new, old, atol=tol) = all |new - old| <= atol + rtol |old|.
+template <typename T>
+__global__ void kmex_update_kernel(const double* __restrict__ partials, const T* __restrict__ medians,
+                                   const int64_t* __restrict__ counts, T* __restrict__ C, int k, int d, double atol,
+                                   double rtol, int* __restrict__ flag) {
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int e = threadIdx.x; e < k * d; e += blockDim.x) {
+        const int j = e / d, f = e - j * d;
+        const T old = C[e];
+        T nv = old;
+        if (partials != nullptr) {
+            const double cnt = partials[(size_t)j * (d + 1) + d];
+            if (cnt > 0.0) nv = (T)(partials[(size_t)j * (d + 1) + f] / cnt);
+        } else if (counts[j] > 0) {
+            nv = medians[e];
+        }
+        C[e] = nv;
+        const double diff = fabs((double)nv - (double)old);
+        if (!(diff <= atol + rtol * fabs((double)old))) mine = 1;  // NaN counts as "not close"
+    }
+    if (mine) atomicOr(&bad, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) flag[0] = bad ? 0 : 1;
+}
+
 int blocks_for(const Handle* h, int64_t work_items) {
     int64_t b = (work_items + NT - 1) / NT;
     const int64_t cap = (int64_t)h->num_sms * 8;
@@ -569,6 +599,17 @@ int launch_select_value(Handle* h, const uint64_t* prefix, const double* frac, i
         select_value_kernel<double><<<(e + 127) / 128, 128, 0, st>>>(prefix, frac, k, d, (double*)out);
     else
         select_value_kernel<float><<<(e + 127) / 128, 128, 0, st>>>(prefix, frac, k, d, (float*)out);
+    HK_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int launch_kmex_update(Handle* h, const double* partials, const void* medians, const int64_t* counts, void* C, int k,
+                       int d, int dtype, double atol, double rtol, int* flag, cudaStream_t st) {
+    if (dtype == HK_F64)
+        kmex_update_kernel<double><<<1, 256, 0, st>>>(partials, (const double*)medians, counts, (double*)C, k, d, atol, rtol, flag);
+    else
+        kmex_update_kernel<float><<<1, 256, 0, st>>>(partials, (const float*)medians, counts, (float*)C, k, d, atol, rtol, flag);
     HK_CUDA(cudaGetLastError());
     h->launches++;
     return 0;

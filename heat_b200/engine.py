@@ -197,16 +197,25 @@ class CudaEngine:
                                     _ptr(labels), _LK[labels.dtype] if labels is not None else HK_LABEL_NONE, _ptr(fv),
                                     _stream(self.device)), "hk_assign_l1")
 
-    def cluster_medians(self, x, labels, k: int, allsum=None):
+    def kmex_update(self, c, flag, atol: float, partials=None, medians=None, counts=None, rtol: float = 1e-5):
+        k, d = c.shape
+        check(self.lib.hk_kmex_update(self.h, _ptr(partials), _ptr(medians), _ptr(counts), _ptr(c), k, d, _DT[c.dtype],
+                                      float(atol), float(rtol), _ptr(flag), _stream(self.device)), "hk_kmex_update")
+
+    def cluster_medians(self, x, labels, k: int, allsum=None, drop_zero_rows: bool = True, lower: bool = False):
         """Medians of every (cluster, feature) over the rows of all ranks (hk_select_* protocol of include/hkmeans.h).
         ``allsum(t)`` sums an int64 device tensor over the ranks in place (None: one process).  Returns
-        ``(medians [k, d], counts [k] int64)``; rows that are entirely zero are not counted (kmedians.py:76-79)."""
+        ``(medians [k, d], counts [k] int64)``; rows that are entirely zero are not counted (kmedians.py:76-79) unless
+        ``drop_zero_rows`` is False."""
         n, d = x.shape
         dt, st = _DT[x.dtype], _stream(self.device)
         ldx = x.stride(0) if n > 1 else d
         dev = x.device
-        keep = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
-        check(self.lib.hk_row_keep(self.h, _ptr(x), n, d, ldx, dt, _ptr(keep), st), "hk_row_keep")
+        if drop_zero_rows:
+            keep = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+            check(self.lib.hk_row_keep(self.h, _ptr(x), n, d, ldx, dt, _ptr(keep), st), "hk_row_keep")
+        else:
+            keep = torch.ones(max(n, 1), dtype=torch.uint8, device=dev)
         lab = labels.reshape(-1)
         if lab.dtype != torch.int64 or not lab.is_contiguous():
             lab = lab.to(torch.int64).contiguous()
@@ -227,7 +236,8 @@ class CudaEngine:
                 remaining[0] = ((counts - 1).clamp(min=0) // 2).view(k, 1)
                 remaining[1] = (counts // 2).view(k, 1)
             check(self.lib.hk_select_step(self.h, _ptr(hist), _ptr(remaining), _ptr(prefix), k, d, st), "hk_select_step")
-        frac = torch.where(counts % 2 == 0, 0.5, 0.0).to(torch.float64)
+        # lower = torch.median's convention (the lower of the two middle values); else ht.median's interpolation
+        frac = torch.zeros(k, dtype=torch.float64, device=dev) if lower else torch.where(counts % 2 == 0, 0.5, 0.0).to(torch.float64)
         med = torch.empty((k, d), dtype=x.dtype, device=dev)
         check(self.lib.hk_select_value(self.h, _ptr(prefix), _ptr(frac), k, d, dt, _ptr(med), st), "hk_select_value")
         return med, counts

@@ -178,6 +178,13 @@ int hk_select_step(hk_handle_t h, const void* hist_i64, void* remaining_i64, voi
 int hk_select_value(hk_handle_t h, const void* prefix_u64, const double* frac, int k, int d, int dtype, void* medians,
                     void* stream);
 
+/* Centre update of the batch-parallel clusterers' local loop: clusters with rows take their mean (partials = the
+ * k x (d+1) fp64 sums | counts of hk_lloyd_accumulate) or their median (medians [k][d] + counts [k], partials NULL),
+ * empty clusters keep their centre; flag[0] (int32) = all |new - old| <= atol + rtol |old|
+ *   <- _kmex, heat/cluster/batchparallelclustering.py:56-84 (torch.allclose(centers, centers_old, atol=tol)) */
+int hk_kmex_update(hk_handle_t h, const double* partials, const void* medians, const void* counts_i64, void* C, int k,
+                   int d, int dtype, double atol, double rtol, void* flag_i32, void* stream);
+
 /* best_index[j] = global index (row_base + i) of the shard row closest in L1 to P[j], first index on ties
  *   <- KMedoids._update_centroids: dist = manhattan(x, median); idx = dist.argmin(axis=0)
  *      heat/cluster/kmedoids.py:94-110 */

@@ -10,6 +10,9 @@ Restated, with the reference lines each function follows (paths relative to /roo
   kmedians_fit     KMedians.fit                                                        heat/cluster/kmedians.py:105-147
   kmedoids_fit     KMedoids.fit / _update_centroids                                    heat/cluster/kmedoids.py:57-156
   knn_predict      KNeighborsClassifier.fit / predict                 heat/classification/kneighborsclassifier.py:55-135
+  plus_plus_rows, kmex, batch_parallel_fit / _predict
+                   _initialize_plus_plus, _kmex, _BatchParallelKCluster.fit / predict
+                                                                    heat/cluster/batchparallelclustering.py:23-86, 171-331
 """
 from __future__ import annotations
 
@@ -94,3 +97,62 @@ def knn_predict(x_train: torch.Tensor, y: torch.Tensor, x_test: torch.Tensor, n_
     _, idx = torch.topk(dist, n_neighbors, dim=1, largest=False)
     votes = y[idx.flatten()].reshape(idx.shape + (y.shape[1],)).sum(dim=1)
     return torch.argmax(votes, dim=1)
+
+
+def plus_plus_rows(x: torch.Tensor, k: int, p: int, gen: Optional[torch.Generator]) -> torch.Tensor:
+    """++ seeding on one shard: uniform first row, then rows drawn proportionally to the distance to the nearest chosen one
+    (same generator calls as the reference after ``torch.manual_seed``: one randint, k-1 multinomials)."""
+    cap = 2**24 - 1
+    if x.shape[0] > cap:
+        x = x[torch.randint(0, x.shape[0], (cap,), generator=gen)]
+    chosen = [int(torch.randint(0, x.shape[0], (1,), generator=gen))]
+    while len(chosen) < k:
+        nearest = torch.cdist(x, x[chosen], p=p).min(dim=1).values
+        chosen.append(int(torch.multinomial(nearest, 1, generator=gen)))
+    return x[chosen]
+
+
+def kmex(x: torch.Tensor, p: int, k: int, init, max_iter: int, tol: float, seed: Optional[int]):
+    """One-shard k-means / k-medians: torch.cdist(p) labels, mean | torch.median (lower) update, empty clusters keep their
+    centre, stop when allclose(new, old, atol=tol)."""
+    gen = torch.Generator().manual_seed(seed) if seed is not None else None
+    centers = init.clone() if isinstance(init, torch.Tensor) else plus_plus_rows(x, k, p, gen).clone()
+    done = 0
+    for done in range(1, max_iter + 1):
+        lab = torch.cdist(x, centers, p=p).argmin(dim=1)
+        before = centers.clone()
+        for j in range(k):
+            rows = x[lab == j]
+            if rows.shape[0]:
+                centers[j] = rows.median(dim=0).values if p == 1 else rows.mean(dim=0)
+        if torch.allclose(centers, before, atol=tol):
+            break
+    return centers, done
+
+
+def batch_parallel_fit(shards, p: int, k: int, max_iter: int, tol: float, random_state: Optional[int],
+                       n_procs_to_merge: Optional[int] = None):
+    """All ranks of _BatchParallelKCluster.fit in one process: returns (centres, n_iter as seen by rank 0)."""
+    size = len(shards)
+    seeds = [None if random_state is None else random_state + r for r in range(size)]
+    local = [kmex(shards[r], p, k, "++", max_iter, tol, seeds[r]) for r in range(size)]
+    cents, iters = [c for c, _ in local], [i for _, i in local]
+    merge = n_procs_to_merge if n_procs_to_merge is not None else size
+    alive = list(range(size))
+    while len(alive) > 1:
+        for pos in range(0, len(alive), merge):
+            group = alive[pos:pos + merge]
+            if len(group) > 1:
+                root = group[0]
+                pooled = torch.cat([cents[r] for r in group], dim=0)
+                cents[root], extra = kmex(pooled, p, k, "++", max_iter, tol, seeds[root])
+                iters[root] += extra
+        alive = alive[::merge]
+    return cents[0], iters[0]
+
+
+def batch_parallel_predict(x: torch.Tensor, centers: torch.Tensor, p: int):
+    lab = torch.cdist(x, centers, p=p).argmin(dim=1)
+    diff = x - centers[lab]
+    fv = float(torch.norm(diff, p="fro") ** 2) if p == 2 else float(torch.norm(diff, p=p, dim=1).sum())
+    return lab.view(-1, 1).to(torch.int32), fv

@@ -167,6 +167,14 @@ def run_consumers():
         out[f"kmedoids_{nm}_centers"] = kd.cluster_centers_.larray.numpy()
         out[f"kmedoids_{nm}_labels"] = kd.labels_.larray.numpy()
         out[f"kmedoids_{nm}_n_iter"] = np.int64(kd.n_iter_)
+        for cls, tag, ini in ((ht.cluster.BatchParallelKMeans, "bpkmeans", "k-means++"),
+                              (ht.cluster.BatchParallelKMedians, "bpkmedians", "k-medians++")):
+            bp = cls(n_clusters=4, init=ini, max_iter=30, tol=1e-4, random_state=5)
+            bp.fit(hx)
+            out[f"{tag}_{nm}_centers"] = bp.cluster_centers_.larray.numpy()
+            out[f"{tag}_{nm}_n_iter"] = np.int64(bp.n_iter_)
+            out[f"{tag}_{nm}_predict"] = bp.predict(hx).larray.numpy()
+            out[f"{tag}_{nm}_fv"] = np.float64(bp.functional_value_)
         knn = ht.classification.kneighborsclassifier.KNeighborsClassifier(n_neighbors=5)
         knn.fit(hx, ht.array(inp["y"], split=0))
         out[f"knn_{nm}_classes"] = knn.predict(ht.array(inp["x_test"].to(dt), split=0)).larray.numpy()

@@ -199,7 +199,9 @@ class Comm:
         pass
 
     def Split(self, color=0, key=0):
-        raise NotImplementedError
+        if self._size == 1:
+            return self.Dup()  # one process: every split is the process itself
+        raise NotImplementedError("mpi4py stand-in: Split is implemented for one process only")
 
     def Barrier(self):
         d = _ensure_dist() if self._size > 1 else None

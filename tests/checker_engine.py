@@ -96,14 +96,26 @@ class CheckerEngine:
         if fv is not None:
             fv[0] = float(mins.double().sum())
 
-    def cluster_medians(self, x, labels, k, allsum=None):
+    def kmex_update(self, c, flag, atol, partials=None, medians=None, counts=None, rtol=1e-5):
+        k, d = c.shape
+        old = c.clone()
+        if partials is not None:
+            p = partials.view(k, d + 1)
+            has = p[:, d] > 0
+            new = (p[:, :d] / p[:, d].clamp(min=1).view(-1, 1)).to(c.dtype)
+        else:
+            has, new = counts > 0, medians
+        c[has] = new[has]
+        flag[0] = int(torch.allclose(c, old, atol=atol, rtol=rtol))
+
+    def cluster_medians(self, x, labels, k, allsum=None, drop_zero_rows=True, lower=False):
         n, d = x.shape
         bits = 32 if x.dtype == torch.float32 else 64
         raw = x.contiguous().numpy().view(np.uint32 if bits == 32 else np.uint64).astype(np.uint64)
         top = np.uint64(1) << np.uint64(bits - 1)
         full = np.uint64((1 << bits) - 1)
         key = np.where(raw & top != 0, raw ^ full, raw ^ top)
-        keep = (x != 0).any(dim=1).numpy()
+        keep = (x != 0).any(dim=1).numpy() if drop_zero_rows else np.ones(n, dtype=bool)
         lab = labels.reshape(-1).numpy()
         prefix = np.zeros((2, k, d), dtype=np.uint64)
         remaining = np.zeros((2, k, d), dtype=np.int64)
@@ -136,7 +148,7 @@ class CheckerEngine:
         dec = np.where(prefix & top != 0, prefix ^ top, prefix ^ full)
         vals = dec.astype(np.uint32 if bits == 32 else np.uint64).view(np.float32 if bits == 32 else np.float64)
         lo, hi = torch.from_numpy(vals[0].copy()), torch.from_numpy(vals[1].copy())
-        frac = torch.from_numpy(np.where(counts % 2 == 0, 0.5, 0.0)).to(x.dtype).view(k, 1)
+        frac = torch.from_numpy(np.where((counts % 2 == 0) & (not lower), 0.5, 0.0)).to(x.dtype).view(k, 1)
         return lo + (hi - lo) * frac, torch.from_numpy(counts.copy())
 
     def nearest_rows_l1(self, x, p, row_base):

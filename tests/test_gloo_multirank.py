@@ -274,3 +274,68 @@ def test_kmedians_kmedoids_knn_host_logic_over_gloo(tmp_path, world):
     res = torch.load(out)
     assert res["knn_split"] == 0
     _check_consumers(res)
+
+
+def _worker_batch_parallel(rank, world, port, out, merge):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    import heat_b200 as hb
+    from cases import consumer_inputs
+    from checker_engine import CheckerEngine
+    from heat_b200 import engine
+
+    hb.init_from_env("gloo")
+    engine.set_engine_factory(lambda dev: CheckerEngine(dev))
+    hx = hb.array(consumer_inputs()["x"], split=0)
+    res = {}
+    for cls, tag, ini in ((hb.cluster.BatchParallelKMeans, "bpkmeans", "k-means++"),
+                          (hb.cluster.BatchParallelKMedians, "bpkmedians", "k-medians++")):
+        bp = cls(n_clusters=4, init=ini, max_iter=30, tol=1e-4, random_state=5, n_procs_to_merge=merge).fit(hx)
+        lab = bp.predict(hx)
+        res[tag] = {"centers": bp.cluster_centers_.larray, "n_iter": bp.n_iter_, "labels": lab.resplit(None).larray,
+                    "fv": bp.functional_value_, "dtype": lab.dtype}
+    if rank == 0:
+        torch.save(res, out)
+    import torch.distributed as dist
+
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _check_batch_parallel(res, world, merge, nm="f32"):
+    """world = 1: against the unmodified reference's golden; more ranks: against the restated algorithm run over the same
+    shards in one process (the reference's sub-communicator merge cannot run under the mpi4py stand-in)."""
+    from cases import consumer_inputs
+    from heat_b200.communication import chunk_rows
+    from helpers import load_golden
+    from oracle import consumers_oracle as con
+
+    dt = torch.float32 if nm == "f32" else torch.float64
+    x = consumer_inputs()["x"].to(dt)
+    g = load_golden("consumers")
+    for p, tag in ((2, "bpkmeans"), (1, "bpkmedians")):
+        r = res[tag]
+        if world == 1:
+            want_c, want_it = torch.from_numpy(g[f"{tag}_{nm}_centers"]), int(g[f"{tag}_{nm}_n_iter"])
+            want_lab, want_fv = torch.from_numpy(g[f"{tag}_{nm}_predict"]), float(g[f"{tag}_{nm}_fv"])
+        else:
+            shards = [x[o:o + c] for o, c in (chunk_rows(x.shape[0], world, rk) for rk in range(world))]
+            want_c, want_it = con.batch_parallel_fit(shards, p, 4, 30, 1e-4, 5, merge)
+            want_lab, want_fv = con.batch_parallel_predict(x, want_c, p)
+        assert r["n_iter"] == want_it, (tag, r["n_iter"], want_it)
+        np.testing.assert_allclose(r["centers"].cpu().numpy(), want_c.numpy(), rtol=2e-5, atol=2e-5, err_msg=tag)
+        assert r["dtype"] == torch.int32
+        assert int((r["labels"].cpu() != want_lab).sum()) <= 2, tag  # rows at the rounding of a boundary
+        np.testing.assert_allclose(r["fv"], want_fv, rtol=1e-4)
+
+
+@pytest.mark.parametrize("world,merge", [(2, None), (3, 2)])
+def test_batch_parallel_clusterers_over_gloo(tmp_path, world, merge):
+    """BatchParallelKMeans / KMedians (heat/cluster/batchparallelclustering.py:171-331): per-rank clustering, hierarchical
+    merge of the centres (3 ranks merged 2 at a time: two levels), centres of rank 0 everywhere, int32 labels."""
+    out = str(tmp_path / "bp.pt")
+    mp.spawn(_worker_batch_parallel, args=(world, _free_port(), out, merge), nprocs=world, join=True)
+    _check_batch_parallel(torch.load(out), world, merge)

@@ -184,3 +184,39 @@ def test_kmedians_kmedoids_knn_two_gpus(tmp_path):
     out = str(tmp_path / "consumers.pt")
     mp.spawn(_worker_consumers, args=(2, _free_port(), out), nprocs=2, join=True)
     _check_consumers(torch.load(out))
+
+
+def _worker_batch_parallel(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                      LOCAL_RANK=str(rank))
+    import heat_b200 as hb
+    from cases import consumer_inputs
+
+    hb.init_from_env("nccl")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    hx = hb.array(consumer_inputs()["x"].to(dev), split=0)
+    res = {}
+    for cls, tag, ini in ((hb.cluster.BatchParallelKMeans, "bpkmeans", "k-means++"),
+                          (hb.cluster.BatchParallelKMedians, "bpkmedians", "k-medians++")):
+        bp = cls(n_clusters=4, init=ini, max_iter=30, tol=1e-4, random_state=5).fit(hx)
+        lab = bp.predict(hx)
+        res[tag] = {"centers": bp.cluster_centers_.larray.cpu(), "n_iter": bp.n_iter_,
+                    "labels": lab.resplit(None).larray.cpu(), "fv": bp.functional_value_, "dtype": lab.dtype}
+    if rank == 0:
+        torch.save(res, out)
+    import torch.distributed as dist
+
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_batch_parallel_clusterers_two_gpus(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from test_gloo_multirank import _check_batch_parallel
+
+    out = str(tmp_path / "bp.pt")
+    mp.spawn(_worker_batch_parallel, args=(2, _free_port(), out), nprocs=2, join=True)
+    _check_batch_parallel(torch.load(out), 2, None)

@@ -412,6 +412,33 @@ def test_kmedians_kmedoids_knn_match_reference(nm):
                       "kmedoids_n_iter": kd.n_iter_, "knn_classes": cls.larray}, nm)
 
 
+@pytest.mark.parametrize("nm", ["f32", "f64"])
+def test_batch_parallel_clusterers_match_reference(nm):
+    """BatchParallelKMeans / KMedians on the device against the unmodified reference (same seed: the same ++ rows are
+    drawn), heat/cluster/batchparallelclustering.py."""
+    from cases import consumer_inputs
+    from test_gloo_multirank import _check_batch_parallel
+
+    dt = torch.float32 if nm == "f32" else torch.float64
+    hx = hb.array(consumer_inputs()["x"].to(dt).to(DEV), split=0)
+    eng = engine.get_engine(DEV)
+    l0 = eng.launch_count()
+    res = {}
+    for cls, tag, ini in ((hb.cluster.BatchParallelKMeans, "bpkmeans", "k-means++"),
+                          (hb.cluster.BatchParallelKMedians, "bpkmedians", "k-medians++")):
+        bp = cls(n_clusters=4, init=ini, max_iter=30, tol=1e-4, random_state=5).fit(hx)
+        lab = bp.predict(hx)
+        assert bp.cluster_centers_.larray.is_cuda and lab.larray.is_cuda and isinstance(bp.functional_value_, float)
+        res[tag] = {"centers": bp.cluster_centers_.larray, "n_iter": bp.n_iter_, "labels": lab.larray, "fv": bp.functional_value_,
+                    "dtype": lab.dtype}
+    assert eng.launch_count() > l0 + 20
+    _check_batch_parallel(res, 1, None, nm)
+    with pytest.raises(NotImplementedError):
+        hb.cluster.BatchParallelKMeans(init="random")
+    with pytest.raises(ValueError):
+        hb.cluster.BatchParallelKMeans(n_clusters=4).fit(hb.array(torch.zeros(8, 2, device=DEV)))  # not split
+
+
 def test_l1_assignment_medians_topk_semantics():
     """Device kernels of the N4 consumers against their CPU restatement on inputs with ties, NaN and all-zero rows."""
     from oracle import consumers_oracle as con

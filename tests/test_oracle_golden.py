@@ -142,6 +142,13 @@ def test_consumer_goldens_kmedians_kmedoids_knn():
         assert np.array_equal(c.numpy(), g[f"kmedoids_{nm}_centers"])  # medoids are data rows: exact
         cls = con.knn_predict(x, inp["y"], inp["x_test"].to(dt), 5)
         assert np.array_equal(cls.numpy(), g[f"knn_{nm}_classes"])
+        for p, tag in ((2, "bpkmeans"), (1, "bpkmedians")):  # BatchParallelKMeans / KMedians, one process, random_state 5
+            c, n_iter = con.batch_parallel_fit([x], p, 4, 30, 1e-4, 5)
+            assert n_iter == int(g[f"{tag}_{nm}_n_iter"])
+            np.testing.assert_allclose(c.numpy(), g[f"{tag}_{nm}_centers"], rtol=tol, atol=tol)
+            lab, fv = con.batch_parallel_predict(x, c, p)
+            assert np.array_equal(lab.numpy(), g[f"{tag}_{nm}_predict"])
+            np.testing.assert_allclose(fv, float(g[f"{tag}_{nm}_fv"]), rtol=1e-5)
 
 
 def test_argmin_first_index_and_quirks():
