@@ -48,7 +48,7 @@ class KMeans(BaseEstimator):
     Parameters are those of the reference (heat/cluster/kmeans.py:55-62).  ``init`` may be a DNDarray of
     shape (n_clusters, n_features) (the parity entry point, _kcluster.py:136-143), ``"random"`` or ``"kmeans++"`` /
     ``"probability_based"`` (k-means||, _kcluster.py:146-245, with the N-sized work on the device).
-    ``"batchparallel"`` is a different algorithm and not part of this path.
+    ``"batchparallel"`` takes the centres of ``BatchParallelKMeans`` (_kcluster.py:249-275).
     """
 
     def __init__(self, n_clusters: int = 8, init: Union[str, DNDarray] = "random", max_iter: int = 300,
@@ -126,10 +126,20 @@ class KMeans(BaseEstimator):
         elif self.init == "probability_based":
             self._cluster_centers = self._probability_based_init(x, oversampling, iter_multiplier)
         else:
-            raise NotImplementedError(
-                'init="batchparallel" runs a different algorithm (per-rank k-means + hierarchical merge, '
-                'heat/cluster/batchparallelclustering.py) and is not part of this path; use "kmeans++", "random" or a '
-                "DNDarray of initial centroids")
+            # init="batchparallel" (reference: _kcluster.py:249-275): the batch-parallel clusterer's centres
+            if x.split != 0:
+                raise NotImplementedError(
+                    f"Batch parallel initalization only implemented for split = 0, but split was {x.split}")
+            if self._p == 2:
+                bp = BatchParallelKMeans(n_clusters=self.n_clusters, init="k-means++", max_iter=100,
+                                         random_state=self.random_state)
+            elif self._p == 1:
+                bp = BatchParallelKMedians(n_clusters=self.n_clusters, init="k-medians++", max_iter=100,
+                                           random_state=self.random_state)
+            else:
+                raise ValueError("Batch parallel initialization only implemented for KMeans and KMedians")
+            bp.fit(x)
+            self._cluster_centers = bp.cluster_centers_
 
     # -- k-means|| initialisation (reference: _kcluster.py:146-245, 283-350) ------------------------------------
     def _probability_based_init(self, x: DNDarray, oversampling: float, iter_multiplier: float) -> DNDarray:

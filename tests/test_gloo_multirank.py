@@ -297,6 +297,11 @@ def _worker_batch_parallel(rank, world, port, out, merge):
         lab = bp.predict(hx)
         res[tag] = {"centers": bp.cluster_centers_.larray, "n_iter": bp.n_iter_, "labels": lab.resplit(None).larray,
                     "fv": bp.functional_value_, "dtype": lab.dtype}
+    # KMeans(init="batchparallel") takes the batch-parallel centres (max_iter=100) as its start (_kcluster.py:249-275)
+    km = hb.cluster.KMeans(n_clusters=4, init="batchparallel", random_state=5)
+    km._initialize_cluster_centers(hx, 2, 1)
+    ref = hb.cluster.BatchParallelKMeans(n_clusters=4, init="k-means++", max_iter=100, random_state=5).fit(hx)
+    assert torch.equal(km.cluster_centers_.larray, ref.cluster_centers_.larray)
     if rank == 0:
         torch.save(res, out)
     import torch.distributed as dist

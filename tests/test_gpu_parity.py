@@ -433,6 +433,9 @@ def test_batch_parallel_clusterers_match_reference(nm):
                     "dtype": lab.dtype}
     assert eng.launch_count() > l0 + 20
     _check_batch_parallel(res, 1, None, nm)
+    # KMeans(init="batchparallel") starts from the batch-parallel centres (_kcluster.py:249-275)
+    km = hb.cluster.KMeans(n_clusters=4, init="batchparallel", random_state=5, max_iter=3).fit(hx)
+    assert km.n_iter_ >= 1 and km.cluster_centers_.shape == (4, 5) and km.labels_.shape == (1500, 1)
     with pytest.raises(NotImplementedError):
         hb.cluster.BatchParallelKMeans(init="random")
     with pytest.raises(ValueError):
