@@ -108,7 +108,22 @@ __global__ void __launch_bounds__(NT) assign_l1_kernel(const T* __restrict__ X, 
 // thread == row reads them without bank conflicts) and the k points in shared memory.
 //   MODE 0: labels + per-block sum of the row minima (assignment)
 //   MODE 1: per point the closest row, first index on ties -> one candidate per block and point
-template <typename T, int MODE>
+// sum_f |x_f - c_f| with the row in registers (DREG == d, a multiple of 4) and the point read as 16-byte broadcasts
+template <typename T, int DREG>
+__device__ __forceinline__ T l1_reg(const T (&xr)[DREG > 0 ? DREG : 1], const T* __restrict__ c) {
+    T s = T(0);
+    constexpr int V = 16 / sizeof(T);
+#pragma unroll
+    for (int f = 0; f < DREG; f += V) {
+        T cv[V];
+        *reinterpret_cast<int4*>(cv) = *reinterpret_cast<const int4*>(c + f);
+#pragma unroll
+        for (int u = 0; u < V; ++u) s += fabs(xr[f + u] - cv[u]);
+    }
+    return s;
+}
+
+template <typename T, int MODE, int DREG>
 __global__ void __launch_bounds__(NT) l1_tiled_kernel(const T* __restrict__ X, int64_t n, int d, int64_t ldx,
                                                       const T* __restrict__ C, int k, void* labels, int label_kind,
                                                       double* __restrict__ fv_part, int64_t row_base,
@@ -151,6 +166,11 @@ __global__ void __launch_bounds__(NT) l1_tiled_kernel(const T* __restrict__ X, i
         __syncthreads();
         const bool act = tid < rows;
         const T* xr = xs + (size_t)tid * pd;
+        T xreg[DREG > 0 ? DREG : 1];
+        if (DREG > 0) {
+#pragma unroll
+            for (int f = 0; f < DREG; ++f) xreg[f] = xr[f];
+        }
         if (MODE == 0) {
             if (act) {
                 T best = T(0);
@@ -158,7 +178,10 @@ __global__ void __launch_bounds__(NT) l1_tiled_kernel(const T* __restrict__ X, i
                 for (int j = 0; j < k; ++j) {
                     const T* c = cs + (size_t)j * d;
                     T s = T(0);
-                    for (int f = 0; f < d; ++f) s += fabs(xr[f] - c[f]);
+                    if (DREG > 0)
+                        s = l1_reg<T, DREG>(xreg, c);
+                    else
+                        for (int f = 0; f < d; ++f) s += fabs(xr[f] - c[f]);
                     if (j == 0 || s < best || (s != s && best == best)) {
                         best = s;
                         bj = j;
@@ -174,7 +197,10 @@ __global__ void __launch_bounds__(NT) l1_tiled_kernel(const T* __restrict__ X, i
                 if (act) {
                     const T* c = cs + (size_t)j * d;
                     T s = T(0);
-                    for (int f = 0; f < d; ++f) s += fabs(xr[f] - c[f]);
+                    if (DREG > 0)
+                        s = l1_reg<T, DREG>(xreg, c);
+                    else
+                        for (int f = 0; f < d; ++f) s += fabs(xr[f] - c[f]);
                     bd = (double)s;
                     bi = row_base + r0 + tid;
                 }
@@ -218,6 +244,31 @@ __global__ void __launch_bounds__(NT) l1_tiled_kernel(const T* __restrict__ X, i
             part_i[(size_t)blockIdx.x * k + j] = bi;
         }
     }
+}
+
+// rows of 8 / 16 / 32 / 64 features are kept in registers (the centre reads become 16-byte broadcasts)
+template <typename T, int MODE>
+int launch_l1_tiled(int grid, size_t smem, cudaStream_t st, const T* X, int64_t n, int d, int64_t ldx, const T* C, int k,
+                    void* labels, int label_kind, double* fv_part, int64_t row_base, double* part_d, int64_t* part_i) {
+#define HK_L1_LAUNCH(DREG)                                                                                              \
+    do {                                                                                                               \
+        HK_CUDA(cudaFuncSetAttribute(l1_tiled_kernel<T, MODE, DREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                     (int)smem));                                                                      \
+        l1_tiled_kernel<T, MODE, DREG><<<grid, NT, smem, st>>>(X, n, d, ldx, C, k, labels, label_kind, fv_part,         \
+                                                               row_base, part_d, part_i);                              \
+    } while (0)
+    if (d == 8)
+        HK_L1_LAUNCH(8);
+    else if (d == 16)
+        HK_L1_LAUNCH(16);
+    else if (d == 32)
+        HK_L1_LAUNCH(32);
+    else if (d == 64)
+        HK_L1_LAUNCH(64);
+    else
+        HK_L1_LAUNCH(0);
+#undef HK_L1_LAUNCH
+    return 0;
 }
 
 template <typename T>
@@ -530,8 +581,8 @@ int run_assign_l1(Handle* h, const T* X, int64_t n, int d, int64_t ldx, const T*
     const size_t csz = (size_t)k * d * sizeof(T);
     prof_begin(h, st);
     if (tiled) {
-        HK_CUDA(cudaFuncSetAttribute(l1_tiled_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsz));
-        l1_tiled_kernel<T, 0><<<grid, NT, tsz, st>>>(X, n, d, ldx, C, k, labels, label_kind, part, 0, nullptr, nullptr);
+        int rc = launch_l1_tiled<T, 0>(grid, tsz, st, X, n, d, ldx, C, k, labels, label_kind, part, 0, nullptr, nullptr);
+        if (rc) return rc;
     } else if (csz <= 96 * 1024) {
         HK_CUDA(cudaFuncSetAttribute(assign_l1_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csz));
         assign_l1_kernel<T, true><<<grid, NT, csz, st>>>(X, n, d, ldx, C, k, labels, label_kind, part);
@@ -630,13 +681,13 @@ int launch_nearest_rows_l1(Handle* h, const void* X, int64_t n, int d, int64_t l
     double* pd = reinterpret_cast<double*>(h->part);
     int64_t* pi = reinterpret_cast<int64_t*>(pd + (size_t)grid * k);
     if (tiled && dtype == HK_F64) {
-        HK_CUDA(cudaFuncSetAttribute(l1_tiled_kernel<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsz));
-        l1_tiled_kernel<double, 1><<<grid, NT, tsz, st>>>((const double*)X, n, d, ldx, (const double*)P, k, nullptr, 0,
-                                                          nullptr, row_base, pd, pi);
+        rc = launch_l1_tiled<double, 1>(grid, tsz, st, (const double*)X, n, d, ldx, (const double*)P, k, nullptr, 0, nullptr,
+                                        row_base, pd, pi);
+        if (rc) return rc;
     } else if (tiled) {
-        HK_CUDA(cudaFuncSetAttribute(l1_tiled_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsz));
-        l1_tiled_kernel<float, 1><<<grid, NT, tsz, st>>>((const float*)X, n, d, ldx, (const float*)P, k, nullptr, 0, nullptr,
-                                                         row_base, pd, pi);
+        rc = launch_l1_tiled<float, 1>(grid, tsz, st, (const float*)X, n, d, ldx, (const float*)P, k, nullptr, 0, nullptr,
+                                       row_base, pd, pi);
+        if (rc) return rc;
     } else if (dtype == HK_F64)
         nearest_rows_l1_kernel<double><<<grid, NT, 0, st>>>((const double*)X, n, d, ldx, (const double*)P, k, row_base, pd, pi);
     else

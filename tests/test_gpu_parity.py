@@ -478,6 +478,20 @@ def test_l1_assignment_medians_topk_semantics():
         assert int((lab.cpu() != ref.view(-1)).sum()) == 0
         bd, bi = eng.nearest_rows_l1(xw.to(DEV), cw.to(DEV), 0)
         assert bi.cpu().tolist() == torch.min(orc.manhattan_fast(xw, cw), dim=0).indices.tolist()
+        # rows of 8 / 16 / 32 / 64 features take the register-resident variant of the tiled kernels
+        for dd in (8, 16, 32, 64):
+            xa = torch.randn(20011, dd, generator=g, dtype=torch.float64).to(dt)
+            ca = torch.randn(7, dd, generator=g, dtype=torch.float64).to(dt)
+            ref, mins = con.assign_l1(xa, ca)
+            lab = torch.empty(xa.shape[0], dtype=torch.int32, device=DEV)
+            fv = torch.zeros(1, dtype=torch.float64, device=DEV)
+            eng.assign_l1(xa.to(DEV), ca.to(DEV), lab, fv)
+            assert int((lab.cpu().long() != ref.view(-1)).sum()) <= 1, dd
+            np.testing.assert_allclose(float(fv), float(mins.double().sum()), rtol=1e-6)
+            bd, bi = eng.nearest_rows_l1(xa.to(DEV), ca.to(DEV), 5)
+            want = torch.min(orc.manhattan_fast(xa, ca), dim=0)
+            assert (bi.cpu() - 5).tolist() == want.indices.tolist(), dd
+            np.testing.assert_allclose(bd.cpu().numpy(), want.values.double().numpy(), rtol=1e-5)
         # medians: exact selection, zero rows dropped, even and odd cluster sizes, an empty cluster
         xm = torch.randn(200003, 7, generator=g, dtype=torch.float64).to(dt)
         xm[::1000] = 0.0
