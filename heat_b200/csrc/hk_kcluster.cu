@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(NT) select_hist_kernel(const T* __restrict__ X
                                                          const int64_t* __restrict__ labels,
                                                          const uint8_t* __restrict__ keep, int k,
                                                          const uint64_t* __restrict__ prefix, int pass,
-                                                         unsigned long long* __restrict__ hist) {
+                                                         unsigned int* __restrict__ hist) {
     const int shift = Key<T>::BITS - 8 * (pass + 1);
     const int64_t total = n * (int64_t)d;
     for (int64_t e = (int64_t)blockIdx.x * NT + threadIdx.x; e < total; e += (int64_t)gridDim.x * NT) {
@@ -322,9 +322,15 @@ __global__ void __launch_bounds__(NT) select_hist_kernel(const T* __restrict__ X
         for (int w = 0; w < 2; ++w) {
             if (pass == 0 && w == 1) break;  // both targets share the first digit's counts: the caller copies hist[0] to hist[1]
             const size_t base = ((size_t)w * k + (size_t)j) * d + f;
-            if (pass == 0 || lead == prefix[base]) atomicAdd(&hist[base * 256 + digit], 1ULL);
+            if (pass == 0 || lead == prefix[base]) atomicAdd(&hist[base * 256 + digit], 1u);  // 32-bit RED: no return value
         }
     }
+}
+
+// the shard's 32-bit counts (a bin holds at most n_local < 2^32 values) are added to the caller's 64-bit histogram
+__global__ void widen_add_kernel(const unsigned int* __restrict__ h32, unsigned long long* __restrict__ h64, size_t entries) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < entries) h64[i] += h32[i];
 }
 
 // choose the digit that holds the wanted rank, descend into it
@@ -625,12 +631,19 @@ int launch_select_hist(Handle* h, const void* X, int64_t n, int d, int64_t ldx, 
                        const uint8_t* keep, int k, const uint64_t* prefix, int pass, unsigned long long* hist,
                        cudaStream_t st) {
     const int grid = blocks_for(h, n * (int64_t)d);
+    const size_t entries = (size_t)2 * k * d * 256;
+    int rc = ensure_part(h, entries * sizeof(unsigned int) + 64);
+    if (rc) return rc;
+    unsigned int* h32 = reinterpret_cast<unsigned int*>(h->part);
+    HK_CUDA(cudaMemsetAsync(h32, 0, entries * sizeof(unsigned int), st));
     if (dtype == HK_F64)
-        select_hist_kernel<double><<<grid, NT, 0, st>>>((const double*)X, n, d, ldx, labels, keep, k, prefix, pass, hist);
+        select_hist_kernel<double><<<grid, NT, 0, st>>>((const double*)X, n, d, ldx, labels, keep, k, prefix, pass, h32);
     else
-        select_hist_kernel<float><<<grid, NT, 0, st>>>((const float*)X, n, d, ldx, labels, keep, k, prefix, pass, hist);
+        select_hist_kernel<float><<<grid, NT, 0, st>>>((const float*)X, n, d, ldx, labels, keep, k, prefix, pass, h32);
     HK_CUDA(cudaGetLastError());
-    h->launches++;
+    widen_add_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, st>>>(h32, hist, entries);
+    HK_CUDA(cudaGetLastError());
+    h->launches += 2;
     h->variant = dtype == HK_F64 ? "select_hist<f64>" : "select_hist<f32>";
     return 0;
 }
