@@ -287,16 +287,25 @@ __global__ void sum_blocks_kernel(const double* __restrict__ part, int nb, doubl
     }
 }
 
-// keep[i] = 0 for rows that are entirely zero (the reference drops them before the median, kmedians.py:76-79)
+// keep[i] = 0 for rows that are entirely zero (the reference drops them before the median, kmedians.py:76-79).
+// A warp covers rpw = max(1, 32 / d) rows at a time, lanes stride over the features (coalesced), one ballot per group.
 template <typename T>
 __global__ void __launch_bounds__(NT) row_keep_kernel(const T* __restrict__ X, int64_t n, int d, int64_t ldx,
                                                       uint8_t* __restrict__ keep) {
-    const int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x;
-    if (i >= n) return;
-    const T* x = X + i * ldx;
-    bool any = false;
-    for (int f = 0; f < d; ++f) any |= (x[f] != T(0));
-    keep[i] = any ? 1 : 0;
+    const int lane = threadIdx.x & 31;
+    const int dl = d < 32 ? d : 32;   // lanes per row
+    const int rpw = 32 / dl;          // rows per warp step
+    const int sub = lane / dl, f0 = lane - sub * dl;
+    const int64_t warp0 = ((int64_t)blockIdx.x * NT + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * NT) >> 5;
+    for (int64_t base = warp0 * rpw; base < n; base += nwarps * rpw) {
+        const int64_t i = base + sub;
+        bool any = false;
+        if (sub < rpw && i < n)
+            for (int f = f0; f < d; f += dl) any |= (X[i * ldx + f] != T(0));
+        const unsigned m = __ballot_sync(0xffffffffu, any);
+        if (sub < rpw && i < n && f0 == 0) keep[i] = ((m >> (sub * dl)) & (dl == 32 ? 0xffffffffu : ((1u << dl) - 1u))) ? 1 : 0;
+    }
 }
 
 // One digit (8 bits) of the radix selection: for both order statistics w (lower / upper middle) of every (cluster,
@@ -308,21 +317,27 @@ __global__ void __launch_bounds__(NT) select_hist_kernel(const T* __restrict__ X
                                                          const uint64_t* __restrict__ prefix, int pass,
                                                          unsigned int* __restrict__ hist) {
     const int shift = Key<T>::BITS - 8 * (pass + 1);
-    const int64_t total = n * (int64_t)d;
-    for (int64_t e = (int64_t)blockIdx.x * NT + threadIdx.x; e < total; e += (int64_t)gridDim.x * NT) {
-        const int64_t i = e / d;
-        const int f = (int)(e - i * d);
+    const int lane = threadIdx.x & 31;
+    const int dl = d < 32 ? d : 32;  // lanes per row; a warp covers 32 / dl rows at a time, lanes stride over the features
+    const int rpw = 32 / dl;
+    const int sub = lane / dl, f0 = lane - sub * dl;
+    const int64_t warp0 = ((int64_t)blockIdx.x * NT + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * NT) >> 5;
+    if (sub >= rpw) return;
+    for (int64_t i = warp0 * rpw + sub; i < n; i += nwarps * rpw) {
         if (!keep[i]) continue;
         const int64_t j = labels[i];
         if (j < 0 || j >= k) continue;
-        const uint64_t key = Key<T>::enc(X[i * ldx + f]);
-        const uint64_t lead = pass == 0 ? 0 : (key >> (shift + 8));
-        const unsigned digit = (unsigned)((key >> shift) & 255u);
+        for (int f = f0; f < d; f += dl) {
+            const uint64_t key = Key<T>::enc(X[i * ldx + f]);
+            const uint64_t lead = pass == 0 ? 0 : (key >> (shift + 8));
+            const unsigned digit = (unsigned)((key >> shift) & 255u);
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
-            if (pass == 0 && w == 1) break;  // both targets share the first digit's counts: the caller copies hist[0] to hist[1]
-            const size_t base = ((size_t)w * k + (size_t)j) * d + f;
-            if (pass == 0 || lead == prefix[base]) atomicAdd(&hist[base * 256 + digit], 1u);  // 32-bit RED: no return value
+            for (int w = 0; w < 2; ++w) {
+                if (pass == 0 && w == 1) break;  // both targets share the first digit's counts: the caller copies hist[0] to hist[1]
+                const size_t base = ((size_t)w * k + (size_t)j) * d + f;
+                if (pass == 0 || lead == prefix[base]) atomicAdd(&hist[base * 256 + digit], 1u);  // 32-bit RED: no return value
+            }
         }
     }
 }
@@ -617,7 +632,8 @@ int launch_assign_l1(Handle* h, const void* X, int64_t n, int d, int64_t ldx, in
 }
 
 int launch_row_keep(Handle* h, const void* X, int64_t n, int d, int64_t ldx, int dtype, uint8_t* keep, cudaStream_t st) {
-    const unsigned grid = (unsigned)((n + NT - 1) / NT);
+    const int dl = d < 32 ? d : 32;
+    const unsigned grid = (unsigned)blocks_for(h, (n + (32 / dl) - 1) / (32 / dl) * 32);
     if (dtype == HK_F64)
         row_keep_kernel<double><<<grid, NT, 0, st>>>((const double*)X, n, d, ldx, keep);
     else
@@ -630,7 +646,8 @@ int launch_row_keep(Handle* h, const void* X, int64_t n, int d, int64_t ldx, int
 int launch_select_hist(Handle* h, const void* X, int64_t n, int d, int64_t ldx, int dtype, const int64_t* labels,
                        const uint8_t* keep, int k, const uint64_t* prefix, int pass, unsigned long long* hist,
                        cudaStream_t st) {
-    const int grid = blocks_for(h, n * (int64_t)d);
+    const int dl = d < 32 ? d : 32;
+    const int grid = blocks_for(h, (n + (32 / dl) - 1) / (32 / dl) * 32);
     const size_t entries = (size_t)2 * k * d * 256;
     int rc = ensure_part(h, entries * sizeof(unsigned int) + 64);
     if (rc) return rc;
