@@ -16,6 +16,11 @@ everything else falls through to the reference implementation untouched:
   accelerates ``cdist(quadratic_expansion=True)`` for every caller without touching ``_dist``'s split logic
   (the operator plug point, distance.py:209-227).
 
+* ``heat.cluster.KMedians / KMedoids`` (``fit``, ``_assign_to_cluster``), ``BatchParallelKMeans / BatchParallelKMedians``
+  (``fit``, ``predict``) and ``heat.classification.KNeighborsClassifier.predict`` (default metric) -> the standalone classes of
+  this package (``hk_assign_l1``, ``hk_select_*``, ``hk_nearest_rows_l1``, ``hk_kmex_update``, ``hk_topk_rows``,
+  ``hk_knn_vote``) on the same device tensors; initialisation stays the reference's code.
+
 The per-iteration allreduce uses NCCL through ``torch.distributed``: the process group must map rank r of ``x.comm`` to
 the same rank (one process per GPU, ``cuda:{rank % device_count}`` as in heat/core/devices.py:116-120).
 """
@@ -143,6 +148,114 @@ def install() -> bool:
         tile.__name__ = name
         setattr(hdist, name, tile)
 
+    # ---- other consumers: Heat's own KMedians / KMedoids / BatchParallel* / KNeighborsClassifier objects,
+    # the work delegated to the standalone classes of this package on views of the same device tensors
+    from . import classification as _hbk
+    from . import cluster as _hbc
+    from .dndarray import DNDarray as _HB
+
+    def _to_hb(a):
+        return _HB(a.larray, tuple(a.shape), a.larray.dtype, a.split, a.larray.device, _pg(a), a.balanced)
+
+    def _l1_fit(cls_name, mine_cls):
+        cls = getattr(ht.cluster, cls_name)
+        _ORIG["patch_" + cls_name + ".fit"] = (cls, "fit", cls.__dict__.get("fit"))
+        _ORIG["patch_" + cls_name + "._assign_to_cluster"] = (cls, "_assign_to_cluster", cls.__dict__.get("_assign_to_cluster"))
+        orig_fit = cls.fit
+        orig_assign = cls._assign_to_cluster
+
+        def _mine(self):
+            kw = dict(n_clusters=self.n_clusters, init=_to_hb(self._cluster_centers), max_iter=self.max_iter,
+                      random_state=self.random_state)
+            if mine_cls is _hbc.KMedians:
+                kw["tol"] = self.tol
+            m = mine_cls(**kw)
+            m._cluster_centers = _to_hb(self._cluster_centers)
+            return m
+
+        def l1_fit(self, x, oversampling=2, iter_multiplier=1):
+            if not isinstance(x, DNDarray) or not _eligible(x) or int(self.max_iter) < 1:
+                return orig_fit(self, x, oversampling, iter_multiplier)
+            self._initialize_cluster_centers(x, oversampling, iter_multiplier)  # reference code
+            hdt = self._cluster_centers.dtype
+            m = _mine(self)
+            m.fit(_to_hb(x))
+            self._cluster_centers = _wrap(m.cluster_centers_.larray, tuple(m.cluster_centers_.shape), hdt, None, x)
+            self._labels = DNDarray(m.labels_.larray, (x.shape[0], 1), ht.int64, x.split, x.device, x.comm, x.balanced)
+            self._n_iter = m.n_iter_
+            if m.inertia_ is not None:
+                self._inertia = _wrap(m.inertia_.larray, (), hdt, None, x)
+            return self
+
+        def l1_assign(self, x, eval_functional_value=False):
+            if not isinstance(x, DNDarray) or not _eligible(x):
+                return orig_assign(self, x, eval_functional_value)
+            m = _mine(self)
+            lab = m._assign_to_cluster(_to_hb(x), eval_functional_value)
+            if eval_functional_value:
+                self._functional_value = _wrap(m.functional_value_.larray, (), x.dtype, None, x)
+            return DNDarray(lab.larray, (x.shape[0], 1), ht.int64, x.split, x.device, x.comm, x.balanced)
+
+        cls.fit = l1_fit
+        cls._assign_to_cluster = l1_assign
+
+    _l1_fit("KMedians", _hbc.KMedians)
+    _l1_fit("KMedoids", _hbc.KMedoids)
+
+    def _bp(cls_name):
+        cls = getattr(ht.cluster, cls_name)
+        base = cls.__mro__[1]  # _BatchParallelKCluster holds fit / predict
+        if "patch_bp.fit" not in _ORIG:
+            _ORIG["patch_bp.fit"] = (base, "fit", base.__dict__.get("fit"))
+            _ORIG["patch_bp.predict"] = (base, "predict", base.__dict__.get("predict"))
+            orig_fit, orig_predict = base.fit, base.predict
+
+            def _mine(self):
+                return _hbc._BatchParallelKCluster(self._p, self.n_clusters, self._init, self.max_iter, self.tol,
+                                                   self.random_state, self.n_procs_to_merge)
+
+            def bp_fit(self, x):
+                if not isinstance(x, DNDarray) or not _eligible(x) or x.split != 0 or self._p not in (1, 2):
+                    return orig_fit(self, x)
+                m = _mine(self).fit(_to_hb(x))
+                c = m.cluster_centers_.larray
+                self._cluster_centers = DNDarray(c, tuple(c.shape), x.dtype, None, x.device, x.comm, True)
+                self._n_iter = m.n_iter_
+                return self
+
+            def bp_predict(self, x):
+                if (not isinstance(x, DNDarray) or not _eligible(x) or x.split != 0 or self._cluster_centers is None
+                        or self._p not in (1, 2) or x.shape[1] != self._cluster_centers.shape[1]):
+                    return orig_predict(self, x)
+                m = _mine(self)
+                m._cluster_centers = _to_hb(self._cluster_centers)
+                lab = m.predict(_to_hb(x))
+                self._functional_value = m.functional_value_
+                return DNDarray(lab.larray, (x.shape[0], 1), ht.int32, x.split, x.device, x.comm, x.balanced)
+
+            base.fit = bp_fit
+            base.predict = bp_predict
+
+    _bp("BatchParallelKMeans")
+
+    KNN = ht.classification.kneighborsclassifier.KNeighborsClassifier
+    _ORIG["patch_knn.predict"] = (KNN, "predict", KNN.__dict__.get("predict"))
+    orig_knn_predict = KNN.predict
+
+    def knn_predict(self, x):
+        ok = (isinstance(x, DNDarray) and _eligible(x) and isinstance(self.x, DNDarray) and _eligible(self.x)
+              and self.effective_metric_ is ht.spatial.cdist and self.x.larray.dtype == x.larray.dtype
+              and self.y.larray.dim() == 2 and self.y.split in (None, 0))
+        if not ok:
+            return orig_knn_predict(self, x)
+        m = _hbk.KNeighborsClassifier(n_neighbors=self.n_neighbors)
+        m.x, m.y = _to_hb(self.x), _to_hb(self.y)
+        cls = m.predict(_to_hb(x))
+        self.classes_ = DNDarray(cls.larray, (x.shape[0],), ht.int64, cls.split, x.device, x.comm, x.balanced)
+        return self.classes_
+
+    KNN.predict = knn_predict
+
     KM.fit = fit
     KM._assign_to_cluster = _assign_to_cluster
     hdist._euclidian_fast = _euclidian_fast
@@ -166,4 +279,10 @@ def uninstall() -> None:
     for key, fn in _ORIG.items():
         if key.startswith("tile_"):
             setattr(hdist, key[5:], fn)
+        elif key.startswith("patch_"):
+            owner, name, orig = fn
+            if orig is None:
+                delattr(owner, name)  # the attribute was inherited before the patch
+            else:
+                setattr(owner, name, orig)
     _ORIG.clear()

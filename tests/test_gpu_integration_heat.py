@@ -113,3 +113,45 @@ def test_heat_rbf_and_manhattan_run_on_the_native_path(ht):
             else:
                 tol = atol
             assert torch.allclose(got, ref, atol=tol, rtol=0), (name, float((got - ref).abs().max()))
+
+
+def test_heat_kmedians_kmedoids_batchparallel_knn_run_on_the_native_path(ht):
+    """Heat's own KMedians / KMedoids / BatchParallelKMeans / BatchParallelKMedians / KNeighborsClassifier objects on CUDA
+    DNDarrays after install(): the kernels of libhkmeans.so run, results equal the unmodified reference's CPU goldens."""
+    from cases import consumer_inputs
+    from heat_b200 import engine
+    from test_gloo_multirank import _check_batch_parallel, _check_consumers
+
+    inp = consumer_inputs()
+    eng = engine.get_engine(torch.device("cuda", 0))
+    hx = ht.array(inp["x"], split=0, device="gpu")
+    init = ht.array(inp["init"], device="gpu")
+    l0 = eng.launch_count()
+    km = ht.cluster.KMedians(n_clusters=4, init=init, max_iter=30, tol=1e-4)
+    km.fit(hx)
+    assert eng.last_variant().startswith(("assign_l1", "select_hist")), eng.last_variant()
+    assert isinstance(km.cluster_centers_, ht.DNDarray) and km.cluster_centers_.larray.is_cuda
+    pred = km.predict(hx)
+    kd = ht.cluster.KMedoids(n_clusters=4, init=init, max_iter=30)
+    kd.fit(hx)
+    knn = ht.classification.kneighborsclassifier.KNeighborsClassifier(n_neighbors=5)
+    knn.fit(hx, ht.array(inp["y"], split=0, device="gpu"))
+    cls = knn.predict(ht.array(inp["x_test"], split=0, device="gpu"))
+    assert eng.last_variant() == "topk_rows<f32>", eng.last_variant()
+    assert eng.launch_count() > l0 + 30
+    _check_consumers({"kmedians_centers": km.cluster_centers_.larray, "kmedians_labels": km.labels_.larray,
+                      "kmedians_n_iter": km.n_iter_, "kmedians_inertia": float(km._inertia.item()),
+                      "kmedians_predict": pred.larray, "kmedians_fv": float(km.functional_value_.item()),
+                      "kmedoids_centers": kd.cluster_centers_.larray, "kmedoids_labels": kd.labels_.larray,
+                      "kmedoids_n_iter": kd.n_iter_, "knn_classes": cls.larray})
+    res = {}
+    for klass, tag, ini in ((ht.cluster.BatchParallelKMeans, "bpkmeans", "k-means++"),
+                            (ht.cluster.BatchParallelKMedians, "bpkmedians", "k-medians++")):
+        l1 = eng.launch_count()
+        bp = klass(n_clusters=4, init=ini, max_iter=30, tol=1e-4, random_state=5)
+        bp.fit(hx)
+        lab = bp.predict(hx)
+        assert eng.launch_count() > l1 + 10 and lab.dtype == ht.int32
+        res[tag] = {"centers": bp.cluster_centers_.larray, "n_iter": bp.n_iter_, "labels": lab.larray,
+                    "fv": bp.functional_value_, "dtype": torch.int32}
+    _check_batch_parallel(res, 1, None)
