@@ -57,7 +57,12 @@ class KNeighborsClassifier:
 
     def predict(self, x: DNDarray) -> DNDarray:
         """Reference: kneighborsclassifier.py:106-135."""
-        distances = self.effective_metric_(x, self.x)
+        train = self.x
+        if x.split is None and train.split == 0:
+            # replicated queries against split training rows would give a column-split matrix (distance.py:375-390); the
+            # neighbour search needs whole rows, so the training rows are gathered instead (the result is the same)
+            train = train.resplit(None)
+        distances = self.effective_metric_(x, train)
         if distances.split not in (None, 0):
             raise NotImplementedError("the neighbour search needs whole rows of the distance matrix (split 0 or None)")
         dl = distances.larray
