@@ -288,7 +288,9 @@ __global__ void sum_blocks_kernel(const double* __restrict__ part, int nb, doubl
 }
 
 // keep[i] = 0 for rows that are entirely zero (the reference drops them before the median, kmedians.py:76-79).
-// A warp covers rpw = max(1, 32 / d) rows at a time, lanes stride over the features (coalesced), one ballot per group.
+// A warp covers rpw = max(1, 32 / d) rows per step and UNR steps per iteration (independent loads in flight: the pass
+// is latency-bound otherwise); lanes stride over the features (coalesced), one ballot per step.
+constexpr int UNR = 4;
 template <typename T>
 __global__ void __launch_bounds__(NT) row_keep_kernel(const T* __restrict__ X, int64_t n, int d, int64_t ldx,
                                                       uint8_t* __restrict__ keep) {
@@ -296,20 +298,30 @@ __global__ void __launch_bounds__(NT) row_keep_kernel(const T* __restrict__ X, i
     const int dl = d < 32 ? d : 32;   // lanes per row
     const int rpw = 32 / dl;          // rows per warp step
     const int sub = lane / dl, f0 = lane - sub * dl;
+    const unsigned gmask = dl == 32 ? 0xffffffffu : ((1u << dl) - 1u);
     const int64_t warp0 = ((int64_t)blockIdx.x * NT + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * NT) >> 5;
-    for (int64_t base = warp0 * rpw; base < n; base += nwarps * rpw) {
-        const int64_t i = base + sub;
-        bool any = false;
-        if (sub < rpw && i < n)
-            for (int f = f0; f < d; f += dl) any |= (X[i * ldx + f] != T(0));
-        const unsigned m = __ballot_sync(0xffffffffu, any);
-        if (sub < rpw && i < n && f0 == 0) keep[i] = ((m >> (sub * dl)) & (dl == 32 ? 0xffffffffu : ((1u << dl) - 1u))) ? 1 : 0;
+    for (int64_t base = warp0 * rpw * UNR; base < n; base += nwarps * rpw * UNR) {
+        bool any[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t i = base + (int64_t)u * rpw + sub;
+            any[u] = false;
+            if (sub < rpw && i < n)
+                for (int f = f0; f < d; f += dl) any[u] |= (X[i * ldx + f] != T(0));
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t i = base + (int64_t)u * rpw + sub;
+            const unsigned m = __ballot_sync(0xffffffffu, any[u]);
+            if (sub < rpw && i < n && f0 == 0) keep[i] = ((m >> (sub * dl)) & gmask) ? 1 : 0;
+        }
     }
 }
 
 // One digit (8 bits) of the radix selection: for both order statistics w (lower / upper middle) of every (cluster,
 // feature), count the kept values of that cluster whose leading digits equal prefix[w][j][f] by their next digit.
+// Global-atomics version (any k); rows are taken UNR at a time so that their loads overlap.
 template <typename T>
 __global__ void __launch_bounds__(NT) select_hist_kernel(const T* __restrict__ X, int64_t n, int d, int64_t ldx,
                                                          const int64_t* __restrict__ labels,
@@ -324,21 +336,70 @@ __global__ void __launch_bounds__(NT) select_hist_kernel(const T* __restrict__ X
     const int64_t warp0 = ((int64_t)blockIdx.x * NT + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * NT) >> 5;
     if (sub >= rpw) return;
-    for (int64_t i = warp0 * rpw + sub; i < n; i += nwarps * rpw) {
+    for (int64_t base = warp0 * rpw * UNR + sub; base < n; base += nwarps * rpw * UNR) {
+        int64_t j[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t i = base + (int64_t)u * rpw;
+            j[u] = -1;
+            if (i < n && keep[i]) j[u] = labels[i];
+            if (j[u] >= k) j[u] = -1;
+        }
+        for (int f = f0; f < d; f += dl) {
+            uint64_t key[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                if (j[u] >= 0) key[u] = Key<T>::enc(X[(base + (int64_t)u * rpw) * ldx + f]);
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (j[u] < 0) continue;
+                const uint64_t lead = pass == 0 ? 0 : (key[u] >> (shift + 8));
+                const unsigned digit = (unsigned)((key[u] >> shift) & 255u);
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    if (pass == 0 && w == 1) break;  // both targets share the first digit's counts (the caller copies hist[0])
+                    const size_t e = ((size_t)w * k + (size_t)j[u]) * d + f;
+                    if (pass == 0 || lead == prefix[e]) atomicAdd(&hist[e * 256 + digit], 1u);  // 32-bit RED: no return value
+                }
+            }
+        }
+    }
+}
+
+// Pass 0 with block-private counters: every kept element is counted in this pass, which as reduction atomics to global
+// memory costs ~4 ms per 320 M elements.  A block owns a group of G consecutive features (one 32-byte sector of every fp32
+// row at G = 8), counts its rows in shared memory ([k][G][256] counters, thread == row) and flushes the non-zero counters
+// once: 1.5 ms.  (Measured alternatives that were slower: the same kernel for the later passes with two targets in 128 KB
+// of shared memory, 3.4-3.8 ms per pass; thread == (row, feature) with 64 KB, 2.5 ms; a 12-bit first digit, no change.)
+template <typename T>
+__global__ void __launch_bounds__(NT) select_hist0_smem_kernel(const T* __restrict__ X, int64_t n, int d, int64_t ldx,
+                                                               const int64_t* __restrict__ labels,
+                                                               const uint8_t* __restrict__ keep, int k, int G,
+                                                               unsigned int* __restrict__ hist) {
+    extern __shared__ unsigned int cnt[];  // [k][G][256]
+    const int tid = threadIdx.x;
+    const int f0 = blockIdx.y * G;
+    const int gw = (d - f0) < G ? (d - f0) : G;  // features of this group
+    const int total = k * G * 256;
+    for (int i = tid; i < total; i += NT) cnt[i] = 0;
+    __syncthreads();
+    constexpr int shift = Key<T>::BITS - 8;
+    for (int64_t i = (int64_t)blockIdx.x * NT + tid; i < n; i += (int64_t)gridDim.x * NT) {
         if (!keep[i]) continue;
         const int64_t j = labels[i];
         if (j < 0 || j >= k) continue;
-        for (int f = f0; f < d; f += dl) {
-            const uint64_t key = Key<T>::enc(X[i * ldx + f]);
-            const uint64_t lead = pass == 0 ? 0 : (key >> (shift + 8));
-            const unsigned digit = (unsigned)((key >> shift) & 255u);
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-                if (pass == 0 && w == 1) break;  // both targets share the first digit's counts: the caller copies hist[0] to hist[1]
-                const size_t base = ((size_t)w * k + (size_t)j) * d + f;
-                if (pass == 0 || lead == prefix[base]) atomicAdd(&hist[base * 256 + digit], 1u);  // 32-bit RED: no return value
-            }
+        const T* x = X + i * ldx + f0;
+        for (int g = 0; g < gw; ++g) {
+            const unsigned digit = (unsigned)(Key<T>::enc(x[g]) >> shift);
+            atomicAdd(&cnt[((int)j * G + g) * 256 + digit], 1u);
         }
+    }
+    __syncthreads();
+    for (int i = tid; i < total; i += NT) {
+        const unsigned c = cnt[i];
+        if (c == 0) continue;
+        const int digit = i & 255, g = (i >> 8) % G, j = (i >> 8) / G;
+        if (g < gw) atomicAdd(&hist[((size_t)j * d + f0 + g) * 256 + digit], c);  // target w = 0 (the caller copies it to w = 1)
     }
 }
 
@@ -633,7 +694,7 @@ int launch_assign_l1(Handle* h, const void* X, int64_t n, int d, int64_t ldx, in
 
 int launch_row_keep(Handle* h, const void* X, int64_t n, int d, int64_t ldx, int dtype, uint8_t* keep, cudaStream_t st) {
     const int dl = d < 32 ? d : 32;
-    const unsigned grid = (unsigned)blocks_for(h, (n + (32 / dl) - 1) / (32 / dl) * 32);
+    const unsigned grid = (unsigned)blocks_for(h, (n + (32 / dl) * UNR - 1) / ((32 / dl) * UNR) * 32);
     if (dtype == HK_F64)
         row_keep_kernel<double><<<grid, NT, 0, st>>>((const double*)X, n, d, ldx, keep);
     else
@@ -653,7 +714,31 @@ int launch_select_hist(Handle* h, const void* X, int64_t n, int d, int64_t ldx, 
     if (rc) return rc;
     unsigned int* h32 = reinterpret_cast<unsigned int*>(h->part);
     HK_CUDA(cudaMemsetAsync(h32, 0, entries * sizeof(unsigned int), st));
-    if (dtype == HK_F64)
+    // pass 0: block-private counters when a group of at least one feature fits in shared memory
+    int G = 0;
+    if (pass == 0) {
+        const int per_sector = dtype == HK_F64 ? 4 : 8;
+        for (int g = per_sector; g >= 1; g >>= 1)
+            if ((size_t)k * g * 256 * sizeof(unsigned int) <= 96 * 1024) {
+                G = g;
+                break;
+            }
+    }
+    if (G > 0) {
+        const size_t smem = (size_t)k * G * 256 * sizeof(unsigned int);
+        const int groups = (d + G - 1) / G;
+        int bx = (h->num_sms * 2 + groups - 1) / groups;
+        const int64_t need = (n + NT - 1) / NT;
+        if (bx > need) bx = (int)(need < 1 ? 1 : need);
+        dim3 g2((unsigned)bx, (unsigned)groups);
+        if (dtype == HK_F64) {
+            HK_CUDA(cudaFuncSetAttribute(select_hist0_smem_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            select_hist0_smem_kernel<double><<<g2, NT, smem, st>>>((const double*)X, n, d, ldx, labels, keep, k, G, h32);
+        } else {
+            HK_CUDA(cudaFuncSetAttribute(select_hist0_smem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            select_hist0_smem_kernel<float><<<g2, NT, smem, st>>>((const float*)X, n, d, ldx, labels, keep, k, G, h32);
+        }
+    } else if (dtype == HK_F64)
         select_hist_kernel<double><<<grid, NT, 0, st>>>((const double*)X, n, d, ldx, labels, keep, k, prefix, pass, h32);
     else
         select_hist_kernel<float><<<grid, NT, 0, st>>>((const float*)X, n, d, ldx, labels, keep, k, prefix, pass, h32);
