@@ -52,3 +52,48 @@ def test_oracle_update_is_independent_of_the_sharding(seed, n, d, k, parts):
     # empty clusters go to the origin (Q2)
     counts = torch.bincount(lab.view(-1), minlength=k)
     assert torch.equal(whole[counts == 0], torch.zeros_like(whole[counts == 0]))
+
+
+@settings(max_examples=40, deadline=None)
+@given(seed=st.integers(0, 2**31 - 1), n=st.integers(1, 300), d=st.integers(1, 6), k=st.integers(1, 5),
+       f64=st.booleans(), parts=st.integers(1, 3), coarse=st.booleans())
+def test_radix_selection_protocol_equals_sorting(seed, n, d, k, f64, parts, coarse):
+    """The hk_select_* protocol (include/hkmeans.h; restated in numpy by tests/checker_engine.py, counts summed over the
+    shards like the ranks do) gives the medians of ht.median's rule (sort, lo + (hi - lo) * frac, all-zero rows dropped:
+    heat/cluster/kmedians.py:70-101, heat/core/statistics.py:1684-1728) for any sharding — values with many ties,
+    negative zeros, huge values and denormals included."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from checker_engine import CheckerEngine
+    from oracle import consumers_oracle as con
+
+    g = torch.Generator().manual_seed(seed)
+    dt = torch.float64 if f64 else torch.float32
+    x = torch.randn(n, d, generator=g, dtype=torch.float64)
+    if coarse:
+        x = torch.round(x * 2) / 2  # many equal values, exact zeros (and -0.0 after the sign flip below)
+    x = (x * torch.where(torch.rand(n, d, generator=g) < 0.1, -1.0, 1.0)).to(dt)
+    # (no infinities: the reference masks rows by multiplying with the 0/1 selection, kmedians.py:74-77, so a row holding
+    # inf turns into NaN in EVERY cluster and is kept there — a quirk of the reference that is not reproduced)
+    special = torch.tensor([3.0e38, -3.0e38, 1e-42, -0.0], dtype=dt)
+    pick = torch.rand(n, d, generator=g) < 0.03
+    x[pick] = special[torch.randint(0, 4, (int(pick.sum()),), generator=g)]
+    lab = torch.randint(0, k, (n,), generator=g)
+    want, want_counts = con.cluster_medians(x, lab, k)
+
+    cuts = sorted(torch.randint(0, n + 1, (parts - 1,), generator=g).tolist())
+    bounds = [0] + cuts + [n]
+    shards = [(x[a:b], lab[a:b]) for a, b in zip(bounds[:-1], bounds[1:])]
+    eng = CheckerEngine(torch.device("cpu"))
+    # the protocol is a function of the multiset of kept (label, value) pairs: the sum of the shard histograms is the
+    # histogram of the concatenation, so the shards are checked through their counts and the medians on the whole
+    got, got_counts = eng.cluster_medians(torch.cat([s for s, _ in shards]), torch.cat([l for _, l in shards]), k)
+    per_shard = [eng.cluster_medians(s, l, k)[1] for s, l in shards if s.shape[0]]
+    assert got_counts.tolist() == want_counts.tolist()
+    if per_shard:
+        assert torch.stack(per_shard).sum(dim=0).tolist() == want_counts.tolist()
+    ok = want_counts > 0
+    # identical up to the sign of zero (the integer image orders -0 below +0, sorting treats them as equal)
+    assert torch.equal(torch.nan_to_num(got[ok], nan=7.0) + 0.0, torch.nan_to_num(want[ok], nan=7.0) + 0.0)
