@@ -182,7 +182,10 @@ class KMeans(BaseEstimator):
             for r0 in range(0, n_loc, rows):
                 r1 = min(n_loc, r0 + rows)
                 out = buf[: r1 - r0]
-                eng.cdist(xl[r0:r1], new, out, quadratic_expansion=True)
+                if self._p == 1:  # KMedians / KMedoids sample on Manhattan distances (their metric, kmedians.py:43-50)
+                    eng.pairwise(xl[r0:r1], new, out, "manhattan", True)
+                else:
+                    eng.cdist(xl[r0:r1], new, out, quadratic_expansion=True)
                 torch.minimum(dmin[r0:r1], out.min(dim=1).values, out=dmin[r0:r1])
 
         idx0 = torch.randint(0, max(x.shape[0] - 1, 1), (1,), generator=g_all)
@@ -218,7 +221,10 @@ class KMeans(BaseEstimator):
         # weights = number of rows closest to each candidate
         m = cents.shape[0]
         lab = torch.empty(n_loc, dtype=torch.int32, device=dev)
-        eng.assign(xl, cents.contiguous(), lab)
+        if self._p == 1:
+            eng.assign_l1(xl, cents.contiguous(), lab)
+        else:
+            eng.assign(xl, cents.contiguous(), lab)
         weights = allsum(torch.bincount(lab.long(), minlength=m).to(torch.float64))
         # recluster the candidates (m x d, small): weighted k-means++ seeding + Lloyd, identically on every rank
         # (reference: batchparallelclustering.py:23-88 run on rank 0 and broadcast)

@@ -131,8 +131,11 @@ def _worker_kmeanspp(rank, world, port, out):
     km = hb.cluster.KMeans(n_clusters=6, init="kmeans++", max_iter=50, tol=1e-4, random_state=5)
     assert km.init == "probability_based"  # the reference's alias (kmeans.py:63-64)
     km.fit(hx)
+    # the same initialiser under the Manhattan metric (kmedians++ / kmedoids++ aliases)
+    kmed = hb.cluster.KMedians(n_clusters=6, init="kmedians++", max_iter=50, tol=1e-4, random_state=5).fit(hx)
     if rank == 0:
-        torch.save({"centers": km.cluster_centers_.larray, "true": true_centres(6, 8, 4.0, 21), "n_iter": km.n_iter_}, out)
+        torch.save({"centers": km.cluster_centers_.larray, "true": true_centres(6, 8, 4.0, 21), "n_iter": km.n_iter_,
+                    "kmedians_centers": kmed.cluster_centers_.larray, "kmedians_n_iter": kmed.n_iter_}, out)
     import torch.distributed as dist
 
     dist.barrier()
@@ -148,6 +151,8 @@ def test_kmeanspp_init_host_logic_over_gloo(tmp_path):
     dist = torch.cdist(res["true"].double(), res["centers"].double())
     assert float(dist.min(dim=1).values.max()) < 0.2, dist.min(dim=1).values
     assert res["n_iter"] <= 20
+    dist = torch.cdist(res["true"].double(), res["kmedians_centers"].double())
+    assert float(dist.min(dim=1).values.max()) < 0.3 and res["kmedians_n_iter"] <= 30, dist.min(dim=1).values
 
 
 def _worker_rings(rank, world, port, out):
