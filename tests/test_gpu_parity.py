@@ -647,21 +647,6 @@ def test_kmeanspp_init_on_device():
         hb.cluster.KMeans(n_clusters=k, init="kmeans++").fit(hb.array(x, split=0), oversampling=1)
 
 
-def test_kmedianspp_init_on_device():
-    """init="kmedians++" / "kmedoids++": the same k-means|| scheme on Manhattan distances (hk_pairwise, hk_assign_l1)."""
-    from heat_b200.synthetic import blobs_shard, true_centres
-
-    n, d, k = 60_000, 8, 6
-    x, _ = blobs_shard(n, d, k, device=DEV, offset=4.0, seed=21)
-    hx = hb.array(x, split=0)
-    want = true_centres(k, d, 4.0, 21).double()
-    for cls in (hb.cluster.KMedians, hb.cluster.KMedoids):
-        est = cls(n_clusters=k, init="kmedians++" if cls is hb.cluster.KMedians else "kmedoids++", max_iter=30, random_state=5)
-        est.fit(hx)
-        dist = torch.cdist(want, est.cluster_centers_.larray.cpu().double())
-        assert float(dist.min(dim=1).values.max()) < 0.5, (cls.__name__, dist.min(dim=1).values)
-
-
 @pytest.mark.parametrize("k,d", [(96, 32), (160, 32), (128, 32), (32, 64), (32, 32), (48, 64)])
 def test_tc_many_tiles_per_cta(k, d):
     """The fused tensor-core kernel over tens of tiles per CTA for every TMEM plan (2, 4 and 8 accumulator buffers, 8-12
